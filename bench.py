@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""Benchmark of the GIMS matcher forward path on B200 — BASELINE.json metric: image pairs/sec at
+2048 keypoints/image (configs[1]: fp32, 100 Sinkhorn iterations, r/p/m = 25/7/8).
+
+  python bench.py --gpus N --steps K --warmup W            our CUDA path
+  python bench.py --impl reference ...                     the reference algorithm on the host CPU cores
+                                                           (oracle port; the reference is Python)
+A step = one batch of `--pairs-per-step` synthetic pairs per GPU through the whole hot path
+(AGC graphs -> SAGE -> kenc -> 18 attention layers -> scores -> Sinkhorn -> matches).
+`value`   : pairs/s, inputs already resident in HBM, pairs issued over several CUDA streams.
+`e2e`     : pairs/s through the reference-facing call `Matching(config)(data)` with pinned HOST tensors
+            (H2D of keypoints/descriptors/scores and D2H of matches/scores inside the timed region).
+`roofline`: dominant kernel, timed live with CUDA events inside the library on its own stream.
+Multi-GPU: one process per GPU (torchrun), pairs sharded, no collective on the data path (weak scaling).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+from gims_b200.synth import make_pair, make_state_dict  # noqa: E402
+
+METRIC = 'image_pairs_per_sec_2048kp'
+UNIT = 'pairs/s'
+FALLBACK_PEAKS = {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, 'MEASURED_PEAKS.json')
+    if os.path.exists(p):
+        with open(p) as fh:
+            d = json.load(fh)
+        d['_source'] = 'measured'
+        return d
+    d = dict(FALLBACK_PEAKS)
+    d['_source'] = 'fallback'
+    return d
+
+
+def pair_flops(n0, n1, layers=18, d=256):
+    """Algorithmic FLOPs of one pair, N = surviving keypoints per image."""
+    per_node = layers * (4 * 2 * d * d + 2 * (2 * d) * (2 * d) + 2 * (2 * d) * d) + 2 * 108608 + \
+        2 * (2 * 256 * 128 + 2 * 128 * 128 + 2 * 128 * 256) + 2 * d * d
+    attn = 0
+    for l in range(layers):
+        cross = l % 2 == 1
+        attn += 2 * 2 * d * (n0 * (n1 if cross else n0) + n1 * (n0 if cross else n1))
+    return per_node * (n0 + n1) + attn + 2 * n0 * n1 * d
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, index):
+        self.index = index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
+             'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
+             'clocks_event_reasons.sw_power_cap')
+        try:
+            self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
+                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, smax, reasons = [], None, set()
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(',')]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[0]))
+                smax = float(f[1])
+            except ValueError:
+                continue
+            for name, val in zip(('hw_slowdown', 'hw_thermal_slowdown', 'sw_thermal_slowdown', 'sw_power_cap'), f[4:8]):
+                if val.lower().startswith('active'):
+                    reasons.add(name)
+        sm.sort()
+        med = sm[len(sm) // 2] if sm else None
+        return {'sm_mhz': med, 'sm_max_mhz': smax, 'reasons': sorted(reasons), 'samples': len(sm)}
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference algorithm (oracle port, torch-CPU + numpy) on the host cores."""
+    if rank != 0:
+        return
+    from oracle import gims_oracle as orc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = make_state_dict(0)
+    cfg = {'sinkhorn_iterations': 100, 'match_threshold': 0.2}
+
+    def one(seed):
+        data = make_pair(args.kpts, seed=seed)
+        data.update({'radius': 25, 'percentile': 7, 'min_size': 8})
+        with torch.no_grad():
+            return orc.gmatcher_forward(sd, data, cfg)
+
+    for w in range(max(1, min(args.warmup, 1))):
+        one(1000 + w)
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        one(2000 + s)
+    dt = time.perf_counter() - t0
+    val = args.steps / dt
+    line = {
+        'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
+        'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'GMatcher forward, 1 pair/step, %d kp/image, 100 Sinkhorn it, AGC 25/7/8' % args.kpts,
+                   'pairs_per_step': 1},
+        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+                         'sample': '%d pairs of the bench workload, oracle/gims_oracle.py, torch %d threads' %
+                                   (args.steps, cores)},
+        'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
+        'gpu_launches': 0,
+    }
+    print(json.dumps(line))
+
+
+def cpu_baseline(args):
+    from oracle import gims_oracle as orc
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = make_state_dict(0)
+    cfg = {'sinkhorn_iterations': 100, 'match_threshold': 0.2}
+    timings = {}
+
+    def one(seed):
+        data = make_pair(args.kpts, seed=seed)
+        data.update({'radius': 25, 'percentile': 7, 'min_size': 8})
+        with torch.no_grad():
+            orc.gmatcher_forward(sd, data, cfg, timings=timings)
+
+    one(1000)
+    n = 3
+    t0 = time.perf_counter()
+    for s in range(n):
+        one(2000 + s)
+    dt = time.perf_counter() - t0
+    return {'value': n / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
+            'sample': '%d pairs at %d kp (1 warm-up), oracle port of the reference, torch %d threads' % (n, args.kpts, cores),
+            'stage_seconds_last_pair': {k: round(v, 4) for k, v in timings.items()}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument('--gpus', type=int, default=1)
+    ap.add_argument('--steps', type=int, default=5)
+    ap.add_argument('--warmup', type=int, default=3)
+    ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
+    ap.add_argument('--kpts', type=int, default=2048)
+    ap.add_argument('--pairs-per-step', type=int, default=8)
+    ap.add_argument('--streams', type=int, default=4)
+    ap.add_argument('--pool', type=int, default=40, help='distinct resident input pairs (> L2 in total)')
+    ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-e2e', action='store_true')
+    ap.add_argument('--prof-kernel', default='attention')
+    args = ap.parse_args()
+
+    rank = int(os.environ.get('RANK', 0))
+    world = int(os.environ.get('WORLD_SIZE', 1))
+    local = int(os.environ.get('LOCAL_RANK', 0))
+    if args.impl == 'reference':
+        run_reference(args, rank, world)
+        return
+    if args.warmup < 3:
+        args.warmup = 3
+
+    import torch.distributed as dist
+    from gims_b200 import Matching, _lib
+    from gims_b200.engine import PairBatchRunner
+
+    torch.cuda.set_device(local)
+    dev = torch.device('cuda', local)
+    if world > 1:
+        dist.init_process_group('nccl', device_id=dev)
+    L = _lib.lib()
+
+    cfg = {'sinkhorn_iterations': 100, 'match_threshold': 0.2}
+    matching = Matching(cfg)
+    matching.gmodel.load_state_dict(make_state_dict(0))
+    matching = matching.eval().to(dev)
+    gm = matching.gmodel
+
+    # resident input pool: distinct pairs, total bytes > L2 so no step re-reads inputs from cache
+    P = args.pairs_per_step
+    pool_host = [make_pair(args.kpts, seed=10000 * (rank + 1) + i) for i in range(args.pool)]
+    pool = []
+    for d in pool_host:
+        pool.append({'keypoints0': d['keypoints0'][0].to(dev), 'keypoints1': d['keypoints1'][0].to(dev),
+                     'descriptors0': d['descriptors0'][0].to(dev), 'descriptors1': d['descriptors1'][0].to(dev),
+                     'scores0': d['scores0'][0].to(dev), 'scores1': d['scores1'][0].to(dev),
+                     'shape0': d['image0'].shape, 'shape1': d['image1'].shape})
+    in_bytes = sum(v.numel() * 4 for k, v in pool[0].items() if torch.is_tensor(v))
+    runner = PairBatchRunner(gm, n_streams=args.streams)
+    cursor = [0]
+
+    def step():
+        batch = [pool[(cursor[0] + i) % len(pool)] for i in range(P)]
+        cursor[0] += P
+        return runner.run(batch)
+
+    for _ in range(args.warmup):
+        outs = step()
+    torch.cuda.synchronize(dev)
+    counts = outs[0]['n_kept_dev'].cpu().tolist()
+    if counts[6] != 0:
+        raise RuntimeError('edge capacity overflow in the benchmark workload')
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize(dev)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.gims_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        outs = step()
+    e1.record()
+    torch.cuda.synchronize(dev)
+    ms = e0.elapsed_time(e1)
+    launches = L.gims_launch_count() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    value = world * P * args.steps / (ms / 1e3)
+
+    # --- roofline of the dominant kernel: CUDA events inside the library, same workload, one stream ----------
+    import ctypes as C
+    roof = None
+    if rank == 0:
+        peaks = load_peaks()
+        L.gims_profile_begin(_lib.PROF[args.prof_kernel], 4096)
+        torch.cuda.synchronize(dev)
+        outs1 = PairBatchRunner(gm, n_streams=1).run([pool[i % len(pool)] for i in range(min(P, 4))])
+        torch.cuda.synchronize(dev)
+        tot, cnt = C.c_double(0), C.c_int(0)
+        L.gims_profile_end(C.byref(tot), C.byref(cnt))
+        c = outs1[0]['n_kept_dev'].cpu().tolist()
+        n0k, n1k = c[0], c[1]
+        if cnt.value:
+            avg_s = tot.value / cnt.value / 1e3
+            if args.prof_kernel == 'attention':
+                # QK^T + PV over 4 heads x 64: 4*D*nq*nk per image; averaged over self / cross layers
+                flops = 2.0 * 256 * (n0k + n1k) ** 2
+                ach = flops / avg_s / 1e12
+                peak = peaks['bf16_tflops_sustained']
+                roof = {'kernel': 'k_attention_simt', 'bound': 'tensor', 'achieved': ach, 'peak': peak,
+                        'unit': 'TFLOP/s', 'frac': ach / peak, 'traffic': None,
+                        'peak_source': peaks['_source'] + ' bf16 sustained', 'launches_timed': cnt.value,
+                        'avg_launch_ms': avg_s * 1e3, 'flops_per_launch': flops}
+            elif args.prof_kernel == 'sinkhorn':
+                byts = 4.0 * (n0k + 1) * (n1k + 1)
+                ach = byts / avg_s / 1e9
+                peak = peaks['hbm_gbs']
+                roof = {'kernel': 'k_sinkhorn', 'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
+                        'frac': ach / peak, 'traffic': None, 'peak_source': peaks['_source'],
+                        'launches_timed': cnt.value, 'avg_launch_ms': avg_s * 1e3, 'bytes_per_launch': byts}
+
+    # --- e2e: the reference-facing call with pinned host tensors ------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        n_e2e = max(4, min(P * args.steps, 16))
+        host = []
+        for i in range(n_e2e):
+            d = pool_host[i % len(pool_host)]
+            h = {k: (v.pin_memory() if torch.is_tensor(v) and k != 'image0' and k != 'image1' else v) for k, v in d.items()}
+            h['device'] = dev
+            host.append(h)
+        with torch.no_grad():
+            for i in range(2):
+                pred = matching(dict(host[i]))
+                _ = pred['matches0'].cpu()
+            torch.cuda.synchronize(dev)
+            if world > 1:
+                dist.barrier()
+            t0 = time.perf_counter()
+            d2h = 0
+            for h in host:
+                pred = matching(dict(h))
+                m0 = pred['matches0'].cpu()
+                s0 = pred['matching_scores0'].cpu()
+                d2h = m0.numel() * 8 + s0.numel() * 4
+            torch.cuda.synchronize(dev)
+            dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t.item())
+        e2e = {'value': world * n_e2e / dt, 'unit': UNIT, 'h2d_bytes_per_step': in_bytes * P, 'd2h_bytes_per_step': d2h * P,
+               'pairs_timed': n_e2e, 'note': 'sequential Matching(data) calls, wall clock incl. H2D/D2H, max over ranks'}
+
+    if rank == 0:
+        line = {
+            'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
+            'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
+            'dtype': 'f32', 'data': 'synthetic',
+            'config': {'workload': 'BASELINE configs[1]: GMatcher forward, %d kp/image, fp32, 100 Sinkhorn it, AGC r/p/m 25/7/8, '
+                                   'random-init weights' % args.kpts,
+                       'pairs_per_step_per_gpu': P, 'streams': args.streams, 'kept_keypoints': counts[:2],
+                       'l2': 'input pool of %d distinct pairs (%.0f MB) > L2' % (args.pool, args.pool * in_bytes / 1e6),
+                       'parallelism': 'pair-parallel x%d, no collective' % world},
+            'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roof,
+            'pair_gflop': pair_flops(counts[0], counts[1]) / 1e9,
+            'model_tflops': value / world * pair_flops(counts[0], counts[1]) / 1e12,
+        }
+        if not args.no_cpu_baseline and world == 1:
+            line['cpu_baseline'] = cpu_baseline(args)
+        print(json.dumps(line))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == '__main__':
+    main()

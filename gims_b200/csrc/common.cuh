@@ -1,0 +1,121 @@
+// Shared helpers for the gims_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+
+#include "../../include/gims_b200.h"
+
+namespace gims {
+
+void set_error(const char* fmt, ...);
+void count_launch(int n = 1);
+
+#define GIMS_CUDA_OK(expr)                                                                   \
+  do {                                                                                       \
+    cudaError_t e__ = (expr);                                                                \
+    if (e__ != cudaSuccess) {                                                                \
+      ::gims::set_error("%s:%d CUDA error %s: %s", __FILE__, __LINE__, #expr,                \
+                        cudaGetErrorString(e__));                                            \
+      return GIMS_ERR_CUDA;                                                                  \
+    }                                                                                        \
+  } while (0)
+
+#define GIMS_LAUNCH_OK()                                                                     \
+  do {                                                                                       \
+    ::gims::count_launch();                                                                  \
+    cudaError_t e__ = cudaGetLastError();                                                    \
+    if (e__ != cudaSuccess) {                                                                \
+      ::gims::set_error("%s:%d kernel launch failed: %s", __FILE__, __LINE__,                \
+                        cudaGetErrorString(e__));                                            \
+      return GIMS_ERR_CUDA;                                                                  \
+    }                                                                                        \
+  } while (0)
+
+#define GIMS_TRY(expr)                                                                       \
+  do {                                                                                       \
+    int rc__ = (expr);                                                                       \
+    if (rc__ != GIMS_OK) return rc__;                                                        \
+  } while (0)
+
+// RAII event pair around a launch of the profiled kernel class (see gims_profile_begin).
+struct ProfScope {
+  int slot;
+  cudaStream_t st;
+  ProfScope(int kernel_class, cudaStream_t s);
+  ~ProfScope();
+};
+
+// Cooperative (grid-synchronising) kernels of different streams must never be partially co-resident:
+// they are chained through one per-process event.  Call before / after such a launch.
+int coop_chain_wait(cudaStream_t st);
+int coop_chain_record(cudaStream_t st);
+
+constexpr int kD = GIMS_DESC_DIM;     // 256
+constexpr int kHeads = GIMS_NUM_HEADS;
+constexpr int kHeadDim = kD / kHeads;  // 64
+
+static inline int cdiv(int a, int b) { return (a + b - 1) / b; }
+static inline size_t align_up(size_t x, size_t a) { return (x + a - 1) / a * a; }
+
+// Bump allocator over a caller-provided workspace.
+struct Arena {
+  char* base;
+  size_t cap;
+  size_t off;
+  Arena(void* p, size_t c) : base(static_cast<char*>(p)), cap(c), off(0) {}
+  template <typename T>
+  T* take(size_t count) {
+    off = align_up(off, 256);
+    T* r = reinterpret_cast<T*>(base + off);
+    off += count * sizeof(T);
+    return r;
+  }
+  bool ok() const { return off <= cap; }
+};
+
+// Row segments of the two images inside one stacked activation buffer:
+// image s lives in rows [base[s], base[s] + count), count = n_dev ? n_dev[s] : nmax[s].
+struct Segs {
+  int base[2];
+  int nmax[2];
+  const int* n_dev;   // may be null
+  int nseg;
+};
+
+__device__ __forceinline__ int seg_count(const Segs& s, int i) {
+  return s.n_dev ? min(s.n_dev[i], s.nmax[i]) : s.nmax[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// internal (non-ABI) launchers shared between translation units
+// ---------------------------------------------------------------------------------------------
+struct GemmArgs {
+  const float* A0; int lda0; int K0;      // A(r,k) = k < K0 ? A0[r*lda0+k] : A1[r*lda1 + k-K0]
+  const float* A1; int lda1; int K1;
+  const float* W;                          // [N][K0+K1] row-major (K-major), nn.Linear / Conv1d(k=1) layout
+  const float* bias;                       // [N] or null
+  const float* R; int ldr;                 // residual added in the epilogue (may alias Y) or null
+  float* Y; int ldy;
+  int N;
+  int relu;
+  Segs segs;
+};
+int launch_gemm(const GemmArgs& a, cudaStream_t st);
+
+// scores GEMM: couplings[i][j] = scale * <A_i, B_j>, with the dustbin border (gmatcher.py:59-60)
+int launch_score_gemm(const float* mdesc, int n0_max, int n1_max, const int* n_dev, const float* bin_score,
+                      float* couplings, cudaStream_t st);
+
+// flash attention over the stacked QKV buffer [rows][768] (Q|K|V, each head-major h*64+d)
+int launch_attention(const float* qkv, float* out, int n0_max, int n1_max, const int* n_dev, int cross,
+                     cudaStream_t st);
+
+int launch_sage_aggregate(const float* src, int lds, int width, const int* indptr, const int* indices,
+                          int n_max, const int* n_dev, const float* self_add, int ldself, const float* bias,
+                          int relu, float* out, int ldo, cudaStream_t st);
+
+int launch_kenc_first(const float* kpts, int n_max, const int* n_dev, float img_w, float img_h, const float* W,
+                      const float* b, int cout, float* out, cudaStream_t st);
+
+}  // namespace gims

@@ -1,0 +1,96 @@
+"""Pack a reference `GMatcher.state_dict()` into the flat fp32 buffer the CUDA library consumes.
+
+Done once at load time, in float64 then rounded to fp32:
+  * eval-mode BatchNorm1d folded into the preceding Conv1d(k=1)  (models/gmatcher.py:11-24):
+        s = gamma / sqrt(running_var + eps);  W' = s[:,None] * W;  b' = (b - running_mean) * s + beta
+  * attention heads de-interleaved: the reference views channels as (dim=64, heads=4), i.e. channel
+    c = d*4 + h (gmatcher.py:108-111); packed channel c' = h*64 + d, applied to the output rows of
+    proj[0..2] and to the input columns of `merge`
+  * proj[0] | proj[1] | proj[2] stacked into one [768][256] matrix (Q | K | V)
+  * SAGEConv layer 0 (in > out: fc_neigh before aggregation) stacked as rows [fc_neigh; fc_self];
+    layers 1, 2 stacked along K as [fc_self | fc_neigh] acting on cat[h, mean_neigh(h)]
+  * Conv1d weights (out, in, 1) -> (out, in)
+
+Blob order (== offsets passed to gims_model_create):
+  bin_score, (kenc W_i, b_i) for every kenc conv, (sage W_l, b_l) l=0..2,
+  per attention layer: Wqkv, bqkv, Wmerge, bmerge, W1, b1, W2, b2; final_proj W, b.
+"""
+import torch
+
+from .config import BN_EPS, DEFAULT_CONFIG, NUM_HEADS, kenc_channels
+
+
+def _fold_bn(w, b, sd, bn_prefix):
+    gamma = sd[bn_prefix + '.weight'].double()
+    beta = sd[bn_prefix + '.bias'].double()
+    mean = sd[bn_prefix + '.running_mean'].double()
+    var = sd[bn_prefix + '.running_var'].double()
+    s = gamma / torch.sqrt(var + BN_EPS)
+    return w * s[:, None], (b - mean) * s + beta
+
+
+def head_permutation(d):
+    """perm[c'] = original channel of packed channel c' = h*hd + dd."""
+    hd = d // NUM_HEADS
+    cp = torch.arange(d)
+    return (cp % hd) * NUM_HEADS + cp // hd
+
+
+def pack_state_dict(sd, config=None):
+    """Returns (flat fp32 CPU tensor, list of float offsets, list of blob names)."""
+    cfg = {**DEFAULT_CONFIG, **(config or {})}
+    d = cfg['descriptor_dim']
+    sd = {k: v.detach().cpu() for k, v in sd.items()}
+    blobs = []
+
+    def add(name, t):
+        blobs.append((name, t.double().contiguous()))
+
+    add('bin_score', sd['bin_score'].reshape(1))
+    ch = kenc_channels(cfg)
+    n_conv = len(ch) - 1
+    for i in range(n_conv):
+        w = sd['kenc.encoder.%d.weight' % (3 * i)].double().squeeze(-1)
+        b = sd['kenc.encoder.%d.bias' % (3 * i)].double()
+        if i < n_conv - 1:
+            w, b = _fold_bn(w, b, sd, 'kenc.encoder.%d' % (3 * i + 1))
+        add('kenc.w%d' % i, w)
+        add('kenc.b%d' % i, b)
+    for l in range(3):
+        p = 'gnn_encoder.layers.%d' % l
+        wn, ws = sd[p + '.fc_neigh.weight'].double(), sd[p + '.fc_self.weight'].double()
+        bias = sd[p + '.bias'] if (p + '.bias') in sd else sd[p + '.fc_self.bias']
+        if wn.shape[1] > wn.shape[0]:
+            w = torch.cat([wn, ws], 0)          # rows: [fc_neigh; fc_self]
+        else:
+            w = torch.cat([ws, wn], 1)          # cols: [fc_self | fc_neigh]
+        add('sage.w%d' % l, w)
+        add('sage.b%d' % l, bias.double())
+    perm = head_permutation(d)
+    for l in range(len(cfg['transformer_layers'])):
+        p = 'gnn.layers.%d' % l
+        wq = [sd['%s.attn.proj.%d.weight' % (p, j)].double().squeeze(-1)[perm] for j in range(3)]
+        bq = [sd['%s.attn.proj.%d.bias' % (p, j)].double()[perm] for j in range(3)]
+        add('l%d.wqkv' % l, torch.cat(wq, 0))
+        add('l%d.bqkv' % l, torch.cat(bq, 0))
+        add('l%d.wmerge' % l, sd[p + '.attn.merge.weight'].double().squeeze(-1)[:, perm])
+        add('l%d.bmerge' % l, sd[p + '.attn.merge.bias'].double())
+        w1, b1 = _fold_bn(sd[p + '.mlp.0.weight'].double().squeeze(-1), sd[p + '.mlp.0.bias'].double(), sd, p + '.mlp.1')
+        add('l%d.w1' % l, w1)
+        add('l%d.b1' % l, b1)
+        add('l%d.w2' % l, sd[p + '.mlp.3.weight'].double().squeeze(-1))
+        add('l%d.b2' % l, sd[p + '.mlp.3.bias'].double())
+    add('final.w', sd['final_proj.weight'].double().squeeze(-1))
+    add('final.b', sd['final_proj.bias'].double())
+
+    offsets, names, parts, off = [], [], [], 0
+    for name, t in blobs:
+        flat = t.reshape(-1).float()
+        pad = (-flat.numel()) % 64              # keep every blob 256-byte aligned
+        offsets.append(off)
+        names.append(name)
+        parts.append(flat)
+        if pad:
+            parts.append(torch.zeros(pad))
+        off += flat.numel() + pad
+    return torch.cat(parts).contiguous(), offsets, names

@@ -1,0 +1,204 @@
+/*
+ * gims_b200.h — C ABI of the B200-native GIMS matcher forward path (libgims_b200.so).
+ *
+ * The reference (songxf1024/GIMS) has no native/FFI interface: its boundary for this path is the
+ * Python call `Matching(config)(data)` -> `GMatcher.forward` (models/matching.py:15-30,
+ * models/gmatcher.py:219-307).  The entry points below are what a binding for that call needs;
+ * each one names the reference code it replaces.  `gims_b200/gmatcher.py` is the ctypes host side
+ * that mirrors the reference's Python interface on top of this ABI; INTEGRATION.md shows the stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless its name ends in `_host`;
+ *   - `stream` is a `cudaStream_t` passed as `void*`; all work is enqueued on it, nothing
+ *     synchronises unless stated;
+ *   - no hidden allocation: scratch memory comes from caller-provided workspaces sized by the
+ *     matching `*_workspace_bytes()` query; a `gims_model` only stores pointers/config (host heap);
+ *   - functions return 0 on success, a negative `GIMS_ERR_*` otherwise; `gims_last_error()` gives the
+ *     thread-local message;
+ *   - features are node-major fp32 rows `[n][256]`; graphs are int32 CSR; counts that depend on the
+ *     data (kept keypoints N', edges E) live in device memory (`*_dev` int pointers) so the whole
+ *     forward can be enqueued (and captured in a CUDA graph) without a host round trip.
+ */
+#ifndef GIMS_B200_H
+#define GIMS_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define GIMS_API __attribute__((visibility("default")))
+#else
+#define GIMS_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GIMS_OK              0
+#define GIMS_ERR_ARG        -1   /* bad argument / unsupported configuration */
+#define GIMS_ERR_CUDA       -2   /* CUDA runtime error (message has the CUDA string) */
+#define GIMS_ERR_WORKSPACE  -3   /* workspace too small */
+#define GIMS_ERR_OVERFLOW   -4   /* a data-dependent capacity (edge list) was exceeded */
+
+#define GIMS_DESC_DIM      256   /* descriptor_dim the kernels are built for (gmatcher.py:167) */
+#define GIMS_NUM_HEADS       4   /* hard-coded in the reference too (gmatcher.py:131) */
+#define GIMS_MAX_LAYERS     64
+#define GIMS_MAX_KENC        8
+#define GIMS_MAX_KPTS    32768   /* per image */
+
+/* status words written by the kernels into `gims_pair_outputs.status_dev` / agc `status_dev` */
+#define GIMS_STATUS_EDGE_OVERFLOW  1u
+
+typedef struct gims_model gims_model;
+
+/* Mirror of GMatcher.default_config (gmatcher.py:166-176) — the fields the forward path reads. */
+typedef struct {
+  int   descriptor_dim;                    /* must be 256 */
+  int   num_layers;                        /* len(transformer_layers), 18 */
+  int   layer_is_cross[GIMS_MAX_LAYERS];   /* 0 = 'self', 1 = 'cross' (gmatcher.py:136-140) */
+  int   kenc_num;                          /* number of Conv1d in kenc: len(keypoint_encoder)+1 */
+  int   kenc_dims[GIMS_MAX_KENC + 1];      /* [2, 32, 64, 128, 256, 256] */
+  int   sinkhorn_iterations;               /* 100 */
+  float match_threshold;                   /* 0.2 */
+} gims_config;
+
+/* ---- library ---------------------------------------------------------------------------- */
+GIMS_API int         gims_version(void);
+GIMS_API const char* gims_last_error(void);
+/* number of kernels this library has launched in the calling process (for bench `gpu_launches`) */
+GIMS_API long long   gims_launch_count(void);
+
+/* ---- profiling hooks (bench.py roofline): CUDA-event timing of ONE kernel class, recorded on the
+ * stream each launch goes to.  begin() arms it for at most max_launches launches; end() waits for
+ * the recorded events and returns the summed device time and the number of launches timed. */
+#define GIMS_PROF_NONE        0
+#define GIMS_PROF_GEMM        1   /* projection / MLP GEMMs */
+#define GIMS_PROF_ATTENTION   2   /* flash attention */
+#define GIMS_PROF_SINKHORN    3   /* fused Sinkhorn + argmax kernel */
+#define GIMS_PROF_SCORE       4   /* descriptor score GEMM */
+#define GIMS_PROF_COSINE      5   /* AGC cosine-similarity matrix */
+#define GIMS_PROF_SAGE_GATHER 6   /* SAGE mean aggregation */
+GIMS_API int gims_profile_begin(int kernel_class, int max_launches);
+GIMS_API int gims_profile_end(double* total_ms_host, int* launches_host);
+
+/* ---- model: replaces GMatcher.__init__ / load_state_dict (gmatcher.py:177-217) ------------
+ * `packed` is ONE device buffer of fp32 weights already packed by the host side
+ * (gims_b200/packing.py: BatchNorm folded, attention heads de-interleaved, K|V|Q stacked);
+ * `offsets_host[i]` is the float offset of blob i in the order documented in packing.py /
+ * DESIGN.md §"Packed weights".  The model keeps the pointer; the caller keeps the buffer alive. */
+GIMS_API int  gims_model_create(const gims_config* cfg_host, const float* packed, const int64_t* offsets_host,
+                       int n_offsets, gims_model** out_host);
+GIMS_API void gims_model_destroy(gims_model* m);
+GIMS_API int  gims_packed_blob_count(const gims_config* cfg_host);
+
+/* ---- a-1..a-7: adaptive graph construction for ONE image ----------------------------------
+ * replaces models/agc.py:682-709 build_optimize_graph_with_cosine_similarity (+ 367-391, 413-449,
+ * 476-565, 660-678) and the repack of gmatcher.py:244-252.
+ *   kpts      [n][2]   pixel xy
+ *   desc      descriptors, channel-major [256][n] if desc_channel_major else node-major [n][256]
+ *   scores    [n]
+ *   k_rank    = min(int(L*percentile/100), L-1), L = n(n-1)/2   (agc.py:377-378; host computes it
+ *               with the reference's own float arithmetic)
+ * outputs (capacity n unless noted):
+ *   kept_idx  [n]      original ids of surviving keypoints, ascending (agc.py:677)
+ *   n_kept_dev         N'
+ *   indptr    [n+1], indices [edge_cap]  relabelled CSR, neighbours ascending; n_edges_dev = E
+ *   kpts_out [n][2], feat_out [n][256], scores_out [n]   = ndata point/feat/score (agc.py:705-707)
+ *   thr_out            the cosine threshold (agc.py:439-440)
+ *   n_comp_dev         number of components after pruning (the value agc.py:540 prints)
+ *   status_dev         GIMS_STATUS_* bits (edge_cap overflow)
+ * edge_cap = capacity of `indices` in ints (directed edges). */
+GIMS_API size_t gims_agc_workspace_bytes(int n, int edge_cap);
+GIMS_API int gims_agc_build(const float* kpts, const float* desc, int desc_channel_major, const float* scores, int n,
+                   double radius, long long k_rank, int min_size,
+                   void* workspace, size_t workspace_bytes,
+                   int* kept_idx, int* n_kept_dev, int* indptr, int* indices, int edge_cap, int* n_edges_dev,
+                   float* kpts_out, float* feat_out, float* scores_out, float* thr_out, int* n_comp_dev,
+                   unsigned* status_dev, void* stream);
+
+/* ---- a-9: GraphSAGE encoder (gmatcher.py:145-162, 268-269; dgl SAGEConv 'mean') ------------
+ * feat [n_max][256] -> out [n_max][256]; rows >= *n_dev are untouched.  scratch: 3*n_max*256 floats. */
+GIMS_API int gims_sage_forward(const gims_model* m, const float* feat, const int* indptr, const int* indices,
+                      int n_max, const int* n_dev, float* out, float* scratch, void* stream);
+
+/* ---- a-8 + a-10: normalize_keypoints + KeypointEncoder (gmatcher.py:26-33, 87-97, 265-271) --
+ * desc[i] = add[i] + kenc(normalize(kpts[i]))  (add = SAGE output, gmatcher.py:270-271; may be NULL).
+ * img_w / img_h are `width`/`height` as gmatcher.py:28 unpacks them from image.shape.
+ * scratch: 2*n_max*256 floats. */
+GIMS_API int gims_kenc_forward(const gims_model* m, const float* kpts, int n_max, const int* n_dev, float img_w, float img_h,
+                      const float* add, float* desc, float* scratch, void* stream);
+
+/* ---- a-11 + a-12: one AttentionalPropagation layer for BOTH images (gmatcher.py:99-143) -----
+ * desc holds image 0 in rows [0,n0_max) and image 1 in rows [n0_max, n0_max+n1_max); n_dev[2] are the
+ * live row counts.  Updates desc in place: desc += MLP(cat[desc, MHA(desc, src, src)]).
+ * scratch: gims_attn_scratch_floats(n0_max + n1_max) floats. */
+GIMS_API size_t gims_attn_scratch_floats(int rows);
+GIMS_API int gims_attn_layer_forward(const gims_model* m, int layer, float* desc, int n0_max, int n1_max, const int* n_dev,
+                            float* scratch, void* stream);
+
+/* ---- a-13: final_proj + score matrix (gmatcher.py:273-275) ----------------------------------
+ * mdesc [rows][256] = final_proj(desc); couplings (n0_max+1) x ld, ld = n1_max+1:
+ *   Z0[i][j] = <mdesc0_i, mdesc1_j>/16 for i<N0', j<N1'; bin_score on row N0' and column N1'
+ *   (the torch.cat of gmatcher.py:59-60). */
+GIMS_API int gims_final_scores(const gims_model* m, const float* desc, int n0_max, int n1_max, const int* n_dev,
+                      float* mdesc, float* couplings, void* stream);
+
+/* ---- a-14 + a-15: log-domain Sinkhorn + mutual-NN matches (gmatcher.py:41-69, 284-294) ------
+ * couplings as written by gims_final_scores.  Outputs (capacities n0_max / n1_max):
+ *   u [n0_max+1], v [n1_max+1]  final potentials (log_sinkhorn_iterations' u, v)
+ *   indices0/1 int32  pre-threshold row/column argmax (gmatcher.py:284-285)
+ *   matches0/1 int64 (-1 = unmatched), mscores0/1 fp32 (gmatcher.py:286-294)
+ * workspace: gims_sinkhorn_workspace_bytes(n0_max, n1_max). */
+GIMS_API size_t gims_sinkhorn_workspace_bytes(int n0_max, int n1_max);
+GIMS_API int gims_sinkhorn_match(const float* couplings, int n0_max, int n1_max, const int* n_dev, int iters,
+                        float match_threshold, void* workspace, size_t workspace_bytes,
+                        float* u, float* v, int* indices0, int* indices1,
+                        int64_t* matches0, int64_t* matches1, float* mscores0, float* mscores1, void* stream);
+
+/* ---- whole pair: replaces GMatcher.forward (gmatcher.py:219-307), test mode ----------------- */
+typedef struct {
+  const float* kpts[2];          /* [n][2] */
+  const float* desc[2];          /* [256][n] channel-major (reference layout) or [n][256] */
+  const float* scores[2];        /* [n] */
+  int   n[2];                    /* input keypoint counts */
+  int   desc_channel_major;
+  float img_w[2], img_h[2];      /* as unpacked by gmatcher.py:28 from image{0,1}.shape */
+  double radius;                 /* data.get('radius', 25) */
+  long long k_rank[2];           /* see gims_agc_build */
+  int   min_size;                /* data.get('min_size', 8) */
+  int   edge_cap;                /* per-image capacity of csr_indices */
+} gims_pair_inputs;
+
+typedef struct {
+  int*     n_kept_dev;           /* [2]  N0', N1' */
+  int*     kept_idx[2];          /* [n]  kept_kpts{0,1}_indices */
+  int*     csr_indptr[2];        /* [n+1] */
+  int*     csr_indices[2];       /* [edge_cap] */
+  int*     n_edges_dev;          /* [2] */
+  int*     n_comp_dev;           /* [2] */
+  float*   thr_dev;              /* [2] */
+  float*   kpts[2];              /* [n][2]    data['keypoints*'] after pruning */
+  float*   feat[2];              /* [n][256]  data['descriptors*'] after pruning (node-major) */
+  float*   scores[2];            /* [n] */
+  float*   mdesc;                /* [(n0+n1)][256], image 1 at row n0 */
+  int64_t* matches[2];           /* [n] */
+  float*   mscores[2];           /* [n] */
+  int*     indices[2];           /* [n]  pre-threshold argmax */
+  float*   u;                    /* [n0+1] */
+  float*   v;                    /* [n1+1] */
+  float*   couplings;            /* optional (may be NULL -> internal): (n0+1) x (n1+1) */
+  float*   desc_gnn;             /* optional: [(n0+n1)][256] descriptors after the attention stack */
+  float*   desc_in;              /* optional: [(n0+n1)][256] SAGE + kenc (input of the attention stack) */
+  unsigned* status_dev;          /* [1] GIMS_STATUS_* bits */
+} gims_pair_outputs;
+
+GIMS_API size_t gims_pair_workspace_bytes(const gims_model* m, int n0, int n1, int edge_cap);
+GIMS_API int gims_forward_pair(const gims_model* m, const gims_pair_inputs* in_host, const gims_pair_outputs* out_host,
+                      void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GIMS_B200_H */

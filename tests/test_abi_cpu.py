@@ -1,0 +1,150 @@
+"""CPU: the C-ABI library loads and exports every symbol include/gims_b200.h declares; host-only
+queries work without a GPU; host-side logic (weight packing, k-rank, config mirror)."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+import torch.nn.functional as F
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope='module')
+def lib():
+    from gims_b200 import build, _lib
+    build.build()
+    return _lib.lib()
+
+
+def test_header_symbols_exported(lib):
+    hdr = open(os.path.join(ROOT, 'include', 'gims_b200.h')).read()
+    declared = set(re.findall(r'GIMS_API[^;]*?\b(gims_\w+)\s*\(', hdr))
+    assert len(declared) >= 17
+    from gims_b200 import _lib
+    assert declared == set(_lib.SIGNATURES), 'ctypes table and header disagree'
+    for name in declared:
+        assert hasattr(lib, name), name
+
+
+def test_host_queries(lib):
+    assert lib.gims_version() >= 100
+    assert lib.gims_agc_workspace_bytes(2048, 131072) > 2048 * 2048 * 4
+    assert lib.gims_sinkhorn_workspace_bytes(2048, 2048) > 0
+    assert lib.gims_attn_scratch_floats(4096) == 4096 * 256 * 7
+    from gims_b200 import GMatcher
+    m = GMatcher({})
+    c = m.c_config()
+    assert lib.gims_packed_blob_count(C.byref(c)) == 1 + 10 + 6 + 18 * 8 + 2
+    assert [c.layer_is_cross[i] for i in range(4)] == [0, 1, 0, 1]
+    assert [c.kenc_dims[i] for i in range(6)] == [2, 32, 64, 128, 256, 256]
+
+
+def test_no_cpu_fallback():
+    from gims_b200 import GMatcher, _lib
+    from gims_b200.synth import make_pair
+    m = GMatcher({})
+    if torch.cuda.is_available():
+        pytest.skip('GPU present')
+    with pytest.raises(_lib.GimsError):
+        m(make_pair(64, seed=1, width=100, height=100))
+
+
+def test_state_dict_keys_match_reference_schema():
+    from gims_b200 import GMatcher
+    from gims_b200.config import state_dict_schema
+    m = GMatcher({})
+    sch = state_dict_schema()
+    sd = m.state_dict()
+    assert set(sd) == set(sch)
+    for k, shape in sch.items():
+        assert tuple(sd[k].shape) == tuple(shape), k
+    assert sum(v.numel() for k, v in sd.items() if 'num_batches' not in k and 'running' not in k) == 12187617
+    # DGL spelling with the bias on fc_self is accepted too
+    alt = {k.replace('gnn_encoder.layers.0.bias', 'gnn_encoder.layers.0.fc_self.bias'): v for k, v in sd.items()}
+    m.load_state_dict(alt)
+
+
+def test_k_rank_matches_reference_arithmetic():
+    from gims_b200 import GMatcher
+    for n, p in [(2048, 7), (512, 2), (300, 50), (64, 100), (97, 0), (1000, 33.3)]:
+        length = n * (n - 1) // 2
+        vals = np.zeros(length, dtype=np.float32)
+        k = int(len(vals) * p / 100)
+        if k >= len(vals):
+            k = len(vals) - 1
+        assert GMatcher._k_rank(n, p) == k
+
+
+def test_packing_equals_oracle_layer():
+    """BN folding, head de-interleave and Q|K|V stacking: a torch emulation of what the kernels compute
+    from the PACKED weights equals the oracle's AttentionalPropagation on the raw state dict."""
+    from gims_b200.packing import pack_state_dict
+    from gims_b200.synth import make_state_dict
+    from oracle import gims_oracle as orc
+    sd = make_state_dict(5)
+    flat, off, names = pack_state_dict(sd)
+    blob = {}
+    for i, nme in enumerate(names):
+        end = off[i + 1] if i + 1 < len(off) else flat.numel()
+        blob[nme] = flat[off[i]:end]
+    g = torch.Generator().manual_seed(0)
+    x = torch.randn(70, 256, generator=g)
+    src = torch.randn(50, 256, generator=g)
+    l = 3
+    wqkv = blob['l3.wqkv'][:768 * 256].view(768, 256)
+    bqkv = blob['l3.bqkv'][:768]
+    q = x @ wqkv[:256].t() + bqkv[:256]
+    k = src @ wqkv[256:512].t() + bqkv[256:512]
+    v = src @ wqkv[512:].t() + bqkv[512:]
+    att = torch.empty(70, 256)
+    for h in range(4):
+        sl = slice(h * 64, (h + 1) * 64)
+        p = torch.softmax(q[:, sl] @ k[:, sl].t() / 8.0, dim=-1)
+        att[:, sl] = p @ v[:, sl]
+    msg = att @ blob['l3.wmerge'][:65536].view(256, 256).t() + blob['l3.bmerge'][:256]
+    hid = F.relu(torch.cat([x, msg], 1) @ blob['l3.w1'][:512 * 512].view(512, 512).t() + blob['l3.b1'][:512])
+    delta = hid @ blob['l3.w2'][:256 * 512].view(256, 512).t() + blob['l3.b2'][:256]
+    want = orc.attn_propagation(sd, l, x.t()[None], src.t()[None])[0].t()
+    assert torch.allclose(delta, want, rtol=1e-4, atol=1e-5)
+
+
+def test_packing_equals_oracle_sage_kenc():
+    from gims_b200.packing import pack_state_dict
+    from gims_b200.synth import make_state_dict
+    from oracle import gims_oracle as orc
+    sd = make_state_dict(6)
+    flat, off, names = pack_state_dict(sd)
+    blob = {nme: flat[off[i]:(off[i + 1] if i + 1 < len(off) else flat.numel())] for i, nme in enumerate(names)}
+    g = torch.Generator().manual_seed(1)
+    n = 40
+    feat = torch.randn(n, 256, generator=g)
+    # ring graph + a chord, symmetric CSR
+    nbrs = [sorted({(i - 1) % n, (i + 1) % n} | ({20} if i == 0 else set()) | ({0} if i == 20 else set())) for i in range(n)]
+    indptr = np.cumsum([0] + [len(a) for a in nbrs])
+    indices = np.array([j for a in nbrs for j in a])
+    want = orc.sage_forward(sd, indptr, indices, feat)
+
+    def mean(hh):
+        return torch.stack([hh[a].sum(0) / len(a) for a in nbrs])
+    w0 = blob['sage.w0'][:256 * 256].view(256, 256)
+    y0 = feat @ w0.t()
+    h1 = F.relu(mean(y0[:, :128]) + y0[:, 128:] + blob['sage.b0'][:128])
+    w1 = blob['sage.w1'][:128 * 256].view(128, 256)
+    h2 = F.relu(torch.cat([h1, mean(h1)], 1) @ w1.t() + blob['sage.b1'][:128])
+    w2 = blob['sage.w2'][:256 * 256].view(256, 256)
+    out = torch.cat([h2, mean(h2)], 1) @ w2.t() + blob['sage.b2'][:256]
+    assert torch.allclose(out, want, rtol=1e-4, atol=1e-5)
+    # kenc with folded BN
+    kp = torch.rand(1, n, 2, generator=g) * 2 - 1
+    want_k = orc.kenc_forward(sd, kp)[0].t()
+    hcur = kp[0]
+    dims = [2, 32, 64, 128, 256, 256]
+    for i in range(5):
+        w = blob['kenc.w%d' % i][:dims[i + 1] * dims[i]].view(dims[i + 1], dims[i])
+        hcur = hcur @ w.t() + blob['kenc.b%d' % i][:dims[i + 1]]
+        if i < 4:
+            hcur = F.relu(hcur)
+    assert torch.allclose(hcur, want_k, rtol=1e-4, atol=1e-5)

@@ -1,0 +1,338 @@
+"""GPU parity tests (run on the B200 box: `pytest -m gpu`).
+
+The CUDA path (libgims_b200.so through the C ABI, driven by gims_b200.GMatcher) is compared
+  * with the committed golden fixtures produced by the unmodified reference (tests/golden), and
+  * with the CPU oracle (oracle/gims_oracle.py) on the same seeded inputs, stage by stage.
+Bars: kept indices + CSR bit-exact; |dscores| <= 2e-5*max(1,|s|); |dZ|,|du|,|dv| <= 1e-4
+(scaled by max(1,|.|)); pre-threshold argmax agreement >= 99.9 % (tie-aware); matching scores within
+1e-4*max + 1e-7.
+"""
+import numpy as np
+import pytest
+import torch
+
+from golden_util import golden_names, index_agreement, inputs_for, load_golden, weights_for
+from gims_b200.synth import make_pair, make_state_dict
+
+pytestmark = pytest.mark.gpu
+
+
+def _model(sd, cfg):
+    from gims_b200 import GMatcher
+    m = GMatcher(cfg)
+    m.load_state_dict(sd)
+    return m.cuda().eval()
+
+
+def _run_pair(model, data, debug=True):
+    dev = torch.device('cuda')
+    r = model.run_pair(data['keypoints0'][0].to(dev), data['descriptors0'][0].to(dev), data['scores0'][0].to(dev),
+                       data['keypoints1'][0].to(dev), data['descriptors1'][0].to(dev), data['scores1'][0].to(dev),
+                       data['image0'].shape, data['image1'].shape, data.get('radius', 25), data.get('percentile', 7),
+                       data.get('min_size', 8), debug=debug)
+    torch.cuda.synchronize()
+    cnt = r['n_kept_dev'].cpu().numpy()
+    assert cnt[6] == 0, 'edge capacity overflow'
+    return r, cnt
+
+
+def _csr(r, s, cnt):
+    n, e = int(cnt[s]), int(cnt[2 + s])
+    return (r['kept_idx%d' % s][:n].cpu().numpy().astype(np.int64),
+            r['csr_indptr%d' % s][:n + 1].cpu().numpy().astype(np.int64),
+            r['csr_indices%d' % s][:e].cpu().numpy().astype(np.int64))
+
+
+def _agc_only(data, rec):
+    """gims_agc_build through the C ABI for both images."""
+    import ctypes as C
+    from gims_b200 import _lib
+    from gims_b200.gmatcher import GMatcher
+    L = _lib.lib()
+    dev = torch.device('cuda')
+    outs = []
+    for s in ('0', '1'):
+        kp = data['keypoints' + s][0].to(dev).contiguous()
+        de = data['descriptors' + s][0].to(dev).contiguous()
+        sc = data['scores' + s][0].to(dev).contiguous()
+        n = kp.shape[0]
+        cap = max(1024, 64 * n)
+        ws = torch.empty(L.gims_agc_workspace_bytes(n, cap), dtype=torch.uint8, device=dev)
+        kept = torch.empty(n, dtype=torch.int32, device=dev)
+        cnt = torch.zeros(4, dtype=torch.int32, device=dev)       # n_kept, n_edges, n_comp, status
+        indptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+        indices = torch.empty(cap, dtype=torch.int32, device=dev)
+        kpo = torch.empty(n, 2, device=dev)
+        fo = torch.empty(n, 256, device=dev)
+        so = torch.empty(n, device=dev)
+        thr = torch.zeros(1, device=dev)
+        st = torch.cuda.current_stream()
+        _lib.check(L.gims_agc_build(_lib.ptr(kp), _lib.ptr(de), 1, _lib.ptr(sc), n, float(rec['radius']),
+                                    GMatcher._k_rank(n, rec['percentile']), int(rec['min_size']), _lib.ptr(ws), ws.numel(),
+                                    _lib.ptr(kept), C.c_void_p(cnt.data_ptr()), _lib.ptr(indptr), _lib.ptr(indices), cap,
+                                    C.c_void_p(cnt.data_ptr() + 4), _lib.ptr(kpo), _lib.ptr(fo), _lib.ptr(so), _lib.ptr(thr),
+                                    C.c_void_p(cnt.data_ptr() + 8), C.c_void_p(cnt.data_ptr() + 12),
+                                    C.c_void_p(st.cuda_stream)), 'gims_agc_build')
+        torch.cuda.synchronize()
+        c = cnt.cpu().numpy()
+        assert c[3] == 0
+        nk, ne = int(c[0]), int(c[1])
+        outs.append(dict(kept=kept[:nk].cpu().numpy().astype(np.int64), indptr=indptr[:nk + 1].cpu().numpy().astype(np.int64),
+                         indices=indices[:ne].cpu().numpy().astype(np.int64), n_comp=int(c[2]), thr=float(thr.cpu()),
+                         kpts=kpo[:nk].cpu(), feat=fo[:nk].cpu(), scores=so[:nk].cpu()))
+    return outs
+
+
+@pytest.mark.parametrize('name', golden_names('agc_'))
+def test_agc_golden_bit_exact(name):
+    """a-1..a-7 against the reference's own graphs (tests/golden/agc_*.npz)."""
+    rec, g = load_golden(name)
+    data = inputs_for(rec)
+    outs = _agc_only(data, rec)
+    for s, o in zip(('0', '1'), outs):
+        assert np.array_equal(o['kept'], g['kept' + s]), 'kept indices differ (image %s)' % s
+        assert np.array_equal(o['indptr'], g['csr_indptr' + s]), 'indptr differs (image %s)' % s
+        assert np.array_equal(o['indices'], g['csr_indices' + s]), 'indices differ (image %s)' % s
+        kept = torch.from_numpy(o['kept'])
+        assert torch.equal(o['kpts'], data['keypoints' + s][0][kept])
+        assert torch.equal(o['feat'], data['descriptors' + s][0].t()[kept])
+        assert torch.equal(o['scores'], data['scores' + s][0][kept])
+
+
+@pytest.mark.parametrize('n,width,height,r,p,m,seed', [
+    (700, 500, 400, 25, 7, 8, 101), (333, 300, 300, 10, 30, 2, 102), (1500, 800, 600, 15, 2, 7, 103),
+    (2048, 640, 480, 25, 7, 8, 104), (97, 60, 60, 9, 0, 1, 105), (512, 2000, 2000, 25, 7, 8, 106),
+])
+def test_agc_vs_oracle(n, width, height, r, p, m, seed):
+    """a-1..a-7 against the oracle, including the threshold value and the component count."""
+    from oracle import gims_oracle as orc
+    rec = dict(radius=r, percentile=p, min_size=m)
+    data = make_pair(n, max(2, n - 17), seed=seed, width=width, height=height)
+    outs = _agc_only(data, rec)
+    for s, o in zip(('0', '1'), outs):
+        ref = orc.agc_build(data['keypoints' + s][0].numpy(), data['descriptors' + s][0].t().contiguous().numpy(), r, p, m)
+        assert np.float32(o['thr']) == ref['thr'], 'cosine threshold differs'
+        assert np.array_equal(o['kept'], ref['kept'])
+        assert np.array_equal(o['indptr'], ref['indptr'])
+        assert np.array_equal(o['indices'], ref['indices'])
+        assert o['n_comp'] == ref['n_components']
+
+
+def _rel(a, b):
+    a, b = np.asarray(a, dtype=np.float64), np.asarray(b, dtype=np.float64)
+    return np.abs(a - b) / np.maximum(1.0, np.abs(b))
+
+
+def _check_forward(rec, data, sd, cfg, ref, label):
+    """ref: dict with the reference/oracle values (full or sub-sampled)."""
+    model = _model(sd, cfg)
+    r, cnt = _run_pair(model, data)
+    n0, n1 = int(cnt[0]), int(cnt[1])
+    n0_in = data['keypoints0'].shape[1]
+    msgs = []
+    for s in (0, 1):
+        kept, indptr, indices = _csr(r, s, cnt)
+        assert np.array_equal(kept, ref['kept%d' % s]), label + ': kept%d' % s
+        assert np.array_equal(indices, ref['csr_indices%d' % s]), label + ': csr%d' % s
+    coup = r['couplings'].cpu().numpy()
+    scores = coup[:n0, :n1]
+    assert np.all(coup[n0, :n1 + 1] == float(sd['bin_score'])) and np.all(coup[:n0 + 1, n1] == float(sd['bin_score']))
+    sub = ref['scores_sub'].shape
+    e_sc = _rel(scores[:sub[0], :sub[1]], ref['scores_sub']).max()
+    msgs.append('scores %.2e' % e_sc)
+    u, v = r['u'].cpu().numpy()[:n0 + 1], r['v'].cpu().numpy()[:n1 + 1]
+    e_u, e_v = _rel(u, ref['u']).max(), _rel(v, ref['v']).max()
+    msgs.append('u %.2e v %.2e' % (e_u, e_v))
+    # Z of ours from our own potentials (the fused kernel never materialises it)
+    norm = -np.log(np.float32(n0 + n1))
+    z_ours = (coup[:n0 + 1, :n1 + 1] + u[:, None]) + v[None, :] - norm
+    e_z = _rel(z_ours[:sub[0], :sub[1]], ref['Z_sub']).max()
+    msgs.append('Z %.2e' % e_z)
+    i0, i1 = r['indices0'][:n0].cpu().numpy(), r['indices1'][:n1].cpu().numpy()
+    # tie-aware agreement, judged on our Z (close to the reference's within e_z)
+    zi = z_ours[:n0, :n1]
+    a0 = index_agreement(i0, ref['indices0'], zi[np.arange(n0), i0], zi[np.arange(n0), ref['indices0']])
+    a1 = index_agreement(i1, ref['indices1'], zi[i1, np.arange(n1)], zi[ref['indices1'], np.arange(n1)])
+    raw0, raw1 = (i0 == ref['indices0']).mean(), (i1 == ref['indices1']).mean()
+    msgs.append('argmax agree raw %.4f/%.4f tie-aware %.4f/%.4f' % (raw0, raw1, a0, a1))
+    m0, m1 = r['matches0'][:n0].cpu().numpy(), r['matches1'][:n1].cpu().numpy()
+    ms0, ms1 = r['mscores0'][:n0].cpu().numpy(), r['mscores1'][:n1].cpu().numpy()
+    am0, am1 = (m0 == ref['matches0']).mean(), (m1 == ref['matches1']).mean()
+    tol_ms = 1e-4 * max(ref['matching_scores0'].max(), 1e-3) + 1e-7
+    # scores of keypoints whose mutual status agrees
+    same0 = (ms0 > 0) == (ref['matching_scores0'] > 0)
+    e_ms = np.abs(ms0 - ref['matching_scores0'])[same0].max() if same0.any() else 0.0
+    msgs.append('matches agree %.4f/%.4f, mscores err %.2e (tol %.2e), mutual-status agree %.4f' %
+                (am0, am1, e_ms, tol_ms, same0.mean()))
+    md = r['mdesc'].cpu().numpy()
+    e_md = (np.abs(md[:sub[0]] - ref['mdesc0_sub']).max() / max(1e-6, np.abs(ref['mdesc0_sub']).max()))
+    msgs.append('mdesc rel %.2e' % e_md)
+    print('\n[%s] N\'=(%d,%d) ' % (label, n0, n1) + '; '.join(msgs))
+    assert e_sc <= 2e-5, msgs
+    assert e_u <= 1e-4 and e_v <= 1e-4 and e_z <= 1e-4, msgs
+    assert a0 >= 0.999 and a1 >= 0.999, msgs
+    assert am0 >= 0.999 and am1 >= 0.999, msgs
+    assert e_ms <= tol_ms and same0.mean() >= 0.999, msgs
+    assert e_md <= 2e-5, msgs
+    assert r['matches0'].dtype == torch.int64 and r['mscores0'].dtype == torch.float32
+    return r, cnt
+
+
+@pytest.mark.parametrize('name', golden_names('fwd_'))
+def test_forward_golden(name):
+    """Whole forward (a-1..a-15) against the reference's outputs (tests/golden/fwd_*.npz)."""
+    rec, g = load_golden(name)
+    data = inputs_for(rec)
+    sd = weights_for(rec)
+    cfg = {'sinkhorn_iterations': rec['iters'], 'match_threshold': rec['match_threshold']}
+    ref = {k: g[k] for k in g.files if k != 'recipe'}
+    _check_forward(rec, data, sd, cfg, ref, name)
+
+
+def test_forward_stages_vs_oracle():
+    """Stage-by-stage against the oracle on a ragged pair: SAGE+kenc, every attention layer's output,
+    mdesc, scores, potentials, matches."""
+    from oracle import gims_oracle as orc
+    data = make_pair(600, 555, seed=301, width=420, height=330)
+    data.update({'radius': 25, 'percentile': 7, 'min_size': 8})
+    sd = make_state_dict(3, damped=True)
+    cfg = {'sinkhorn_iterations': 50, 'match_threshold': 0.01}
+    with torch.no_grad():
+        out = orc.gmatcher_forward(sd, data, cfg, stages=True)
+    st = out['_stages']
+    ref = {'scores_sub': st['scores'][0].numpy(), 'Z_sub': st['Z'][0].numpy(), 'u': st['u'][0].numpy(),
+           'v': st['v'][0].numpy(), 'indices0': st['indices0'][0].numpy(), 'indices1': st['indices1'][0].numpy(),
+           'matches0': out['matches0'][0].numpy(), 'matches1': out['matches1'][0].numpy(),
+           'matching_scores0': out['matching_scores0'][0].numpy(), 'matching_scores1': out['matching_scores1'][0].numpy(),
+           'mdesc0_sub': out['mdesc0'].numpy()}
+    for s in (0, 1):
+        ref['kept%d' % s] = st['graph%d' % s]['kept']
+        ref['csr_indices%d' % s] = st['graph%d' % s]['indices']
+    r, cnt = _check_forward(None, data, sd, cfg, ref, 'stages')
+    n0, n1, n0_in = int(cnt[0]), int(cnt[1]), 600
+    din = r['desc_in'].cpu()
+    for s, (a, b) in enumerate(((0, n0), (n0_in, n0_in + n1))):
+        want = st['desc_in%d' % s][0].t()
+        err = (din[a:b] - want).abs().max() / want.abs().max()
+        print('desc_in%d rel err %.2e' % (s, err))
+        assert err <= 1e-5
+    dg = r['desc_gnn'].cpu()
+    for s, (a, b) in enumerate(((0, n0), (n0_in, n0_in + n1))):
+        want = st['desc_out%d' % s][0].t()
+        err = (dg[a:b] - want).abs().max() / want.abs().max()
+        print('desc_gnn%d rel err %.2e' % (s, err))
+        assert err <= 2e-5
+
+
+@pytest.mark.parametrize('n0,n1,iters,scale', [(1, 1, 3, 1.0), (5, 9, 100, 1.0), (300, 257, 20, 5.0), (2048, 2048, 100, 1.0),
+                                                (1000, 3100, 10, 30.0), (4500, 4000, 4, 1.0)])
+def test_sinkhorn_vs_oracle(n0, n1, iters, scale):
+    """a-14/a-15 alone on random couplings: resident (smem slab) and streamed regimes, ragged, tiny."""
+    import ctypes as C
+    from gims_b200 import _lib
+    from oracle import gims_oracle as orc
+    L = _lib.lib()
+    g = torch.Generator().manual_seed(n0 * 7 + n1)
+    scores = torch.randn(1, n0, n1, generator=g) * scale
+    alpha = torch.tensor(0.7)
+    z, u, v, coup = orc.log_optimal_transport(scores, alpha, iters)
+    m = orc.extract_matches(z, 0.0)
+    dev = torch.device('cuda')
+    # exercise device-side counts: allocate for larger maxima than the live sizes
+    n0m, n1m = n0 + 3, n1 + 5
+    cbuf = torch.zeros(n0m + 1, n1m + 1, device=dev)
+    cbuf[:n0 + 1, :n1 + 1] = coup[0].to(dev)
+    cbuf = cbuf.contiguous()
+    nd = torch.tensor([n0, n1], dtype=torch.int32, device=dev)
+    ws = torch.empty(L.gims_sinkhorn_workspace_bytes(n0m, n1m), dtype=torch.uint8, device=dev)
+    uo, vo = torch.zeros(n0m + 1, device=dev), torch.zeros(n1m + 1, device=dev)
+    i0, i1 = torch.zeros(n0m, dtype=torch.int32, device=dev), torch.zeros(n1m, dtype=torch.int32, device=dev)
+    m0, m1 = torch.zeros(n0m, dtype=torch.int64, device=dev), torch.zeros(n1m, dtype=torch.int64, device=dev)
+    s0, s1 = torch.zeros(n0m, device=dev), torch.zeros(n1m, device=dev)
+    _lib.check(L.gims_sinkhorn_match(_lib.ptr(cbuf), n0m, n1m, _lib.ptr(nd), iters, 0.0, _lib.ptr(ws), ws.numel(),
+                                     _lib.ptr(uo), _lib.ptr(vo), _lib.ptr(i0), _lib.ptr(i1), _lib.ptr(m0), _lib.ptr(m1),
+                                     _lib.ptr(s0), _lib.ptr(s1), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+               'gims_sinkhorn_match')
+    torch.cuda.synchronize()
+    eu = _rel(uo[:n0 + 1].cpu().numpy(), u[0].numpy()).max()
+    ev = _rel(vo[:n1 + 1].cpu().numpy(), v[0].numpy()).max()
+    zi = z[0, :-1, :-1].numpy()
+    a0 = index_agreement(i0[:n0].cpu().numpy(), m['indices0'][0].numpy(), zi.max(1),
+                         zi[np.arange(n0), i0[:n0].cpu().numpy()])
+    a1 = index_agreement(i1[:n1].cpu().numpy(), m['indices1'][0].numpy(), zi.max(0),
+                         zi[i1[:n1].cpu().numpy(), np.arange(n1)])
+    ems = np.abs(s0[:n0].cpu().numpy() - m['matching_scores0'][0].numpy()).max()
+    print('\n[sinkhorn %dx%d it=%d] du %.2e dv %.2e agree %.4f/%.4f dms %.2e' % (n0, n1, iters, eu, ev, a0, a1, ems))
+    assert eu <= 1e-4 and ev <= 1e-4
+    assert a0 >= 0.999 and a1 >= 0.999
+    assert ems <= 1e-4 * max(1e-3, float(m['matching_scores0'].max())) + 1e-6
+    same = (m0[:n0].cpu() == m['matches0'][0]).float().mean()
+    assert same >= 0.999
+
+
+def test_drop_in_call_signature():
+    """The reference-facing call: Matching(config)(data) with host tensors, dict in / dict out, the
+    side effects of gmatcher.py:244-252, dtypes and shapes of matching.py / gmatcher.py:296-307."""
+    from gims_b200 import Matching
+    rec, g = load_golden('fwd_n512_damped')
+    data = inputs_for(rec)
+    data['device'] = 'cuda'
+    matching = Matching({'sinkhorn_iterations': rec['iters'], 'match_threshold': rec['match_threshold']})
+    matching.gmodel.load_state_dict(weights_for(rec))
+    matching = matching.eval().to('cuda')
+    with torch.no_grad():
+        pred = matching(data)
+    n0, n1 = len(g['kept0']), len(g['kept1'])
+    assert pred['keypoints0'].shape == (1, n0, 2) and pred['descriptors0'].shape == (1, 256, n0)
+    assert pred['matches0'].shape == (1, n0) and pred['matches0'].dtype == torch.int64
+    assert pred['matches1'].shape == (1, n1) and pred['matching_scores1'].shape == (1, n1)
+    assert pred['mdesc0'].shape == (n0, 256) and pred['mdesc1'].shape == (n1, 256)
+    assert (pred['matches0'][0].cpu().numpy() == g['matches0']).mean() >= 0.999
+    assert np.allclose(pred['keypoints0'][0].cpu().numpy(), g['keypoints0'])
+    pred_np = {k: v[0].cpu().numpy() for k, v in pred.items()}       # what eval_homography.py:181 does
+    assert pred_np['matches0'].shape == (n0,)
+
+
+def test_round_trip_properties_full_size():
+    """BASELINE config 2 (2048 kp, 100 Sinkhorn iterations): size-independent properties.
+    * marginals: exp(Z) rows/cols sum to the prescribed masses (Sinkhorn fixed point, last update is v)
+    * matches are mutual and consistent: matches1[matches0[i]] == i
+    * permutation equivariance: shuffling image-1 keypoints permutes matches0 accordingly."""
+    data = make_pair(2048, seed=77)
+    sd = make_state_dict(0, damped=True)
+    cfg = {'sinkhorn_iterations': 100, 'match_threshold': 0.005}
+    model = _model(sd, cfg)
+    r, cnt = _run_pair(model, data)
+    n0, n1 = int(cnt[0]), int(cnt[1])
+    coup = r['couplings'][:n0 + 1, :n1 + 1].double()
+    u, v = r['u'][:n0 + 1].double(), r['v'][:n1 + 1].double()
+    logp = coup + u[:, None] + v[None, :]
+    col = torch.logsumexp(logp, 0)
+    norm = -np.log(n0 + n1)
+    log_nu = torch.full((n1 + 1,), norm, dtype=torch.float64, device=col.device)
+    log_nu[-1] = np.log(n0) + norm
+    assert (col - log_nu).abs().max() < 1e-4                        # v was updated last: columns are exact
+    row = torch.logsumexp(logp, 1)
+    log_mu = torch.full((n0 + 1,), norm, dtype=torch.float64, device=col.device)
+    log_mu[-1] = np.log(n1) + norm
+    assert (row - log_mu).abs().max() < 1.0                         # rows: converging, not exact
+    m0, m1 = r['matches0'][:n0], r['matches1'][:n1]
+    idx = torch.nonzero(m0 >= 0)[:, 0]
+    assert idx.numel() > 50
+    assert torch.equal(m1[m0[idx]], idx)
+    perm = torch.randperm(2048, generator=torch.Generator().manual_seed(5))
+    data2 = dict(data)
+    data2['keypoints1'] = data['keypoints1'][:, perm]
+    data2['descriptors1'] = data['descriptors1'][:, :, perm]
+    data2['scores1'] = data['scores1'][:, perm]
+    r2, cnt2 = _run_pair(model, data2)
+    assert int(cnt2[0]) == n0 and int(cnt2[1]) == n1
+    kept1 = r['kept_idx1'][:n1].cpu()
+    kept1b = r2['kept_idx1'][:n1].cpu()
+    # original ids matched by each image-0 keypoint must coincide
+    inv = torch.empty(2048, dtype=torch.long)
+    inv[torch.arange(2048)] = perm
+    a = torch.where(m0.cpu() >= 0, kept1[m0.cpu().clamp(min=0)].long(), torch.full_like(m0.cpu(), -1))
+    mb = r2['matches0'][:n0].cpu()
+    b = torch.where(mb >= 0, perm[kept1b[mb.clamp(min=0)].long()], torch.full_like(mb, -1))
+    assert (a == b).float().mean() >= 0.995
