@@ -216,7 +216,7 @@ class GMatcher(nn.Module):
         for the INPUT counts plus `n_kept_dev`; nothing synchronises.  `forward` slices them."""
         L = _lib.lib()
         model = self.handle()
-        dev = kpts0.device
+        dev = self.bin_score.device          # host inputs are copied here (the H2D of the e2e path)
         n0, n1 = int(kpts0.shape[0]), int(kpts1.shape[0])
         if n0 < 2 or n1 < 2:
             raise ValueError('each image needs at least 2 keypoints (the reference fails earlier, agc.py:439)')
@@ -252,7 +252,7 @@ class GMatcher(nn.Module):
         ins = ((kpts0, desc0, scores0), (kpts1, desc1, scores1))
         keep = []
         for s in (0, 1):
-            k, de, sc = [t.to(dev, torch.float32).contiguous() for t in ins[s]]
+            k, de, sc = [t.to(dev, torch.float32, non_blocking=True).contiguous() for t in ins[s]]
             keep += [k, de, sc]
             pin.kpts[s], pin.desc[s], pin.scores[s] = k.data_ptr(), de.data_ptr(), sc.data_ptr()
             pin.n[s] = ns[s]

@@ -200,7 +200,7 @@ def test_forward_stages_vs_oracle():
     with torch.no_grad():
         out = orc.gmatcher_forward(sd, data, cfg, stages=True)
     st = out['_stages']
-    ref = {'scores_sub': st['scores'][0].numpy(), 'Z_sub': st['Z'][0].numpy(), 'u': st['u'][0].numpy(),
+    ref = {'scores_sub': st['scores'][0].numpy(), 'Z_sub': st['Z'][0, :-1, :-1].numpy(), 'u': st['u'][0].numpy(),
            'v': st['v'][0].numpy(), 'indices0': st['indices0'][0].numpy(), 'indices1': st['indices1'][0].numpy(),
            'matches0': out['matches0'][0].numpy(), 'matches1': out['matches1'][0].numpy(),
            'matching_scores0': out['matching_scores0'][0].numpy(), 'matching_scores1': out['matching_scores1'][0].numpy(),
@@ -261,12 +261,23 @@ def test_sinkhorn_vs_oracle(n0, n1, iters, scale):
                          zi[np.arange(n0), i0[:n0].cpu().numpy()])
     a1 = index_agreement(i1[:n1].cpu().numpy(), m['indices1'][0].numpy(), zi.max(0),
                          zi[i1[:n1].cpu().numpy(), np.arange(n1)])
-    ems = np.abs(s0[:n0].cpu().numpy() - m['matching_scores0'][0].numpy()).max()
-    print('\n[sinkhorn %dx%d it=%d] du %.2e dv %.2e agree %.4f/%.4f dms %.2e' % (n0, n1, iters, eu, ev, a0, a1, ems))
+    # mutual status may legitimately flip where a column has an (almost) exact tie between two rows:
+    # such rows are excused only if the oracle's own column gap is below 1e-3
+    ours_ms, ref_ms = s0[:n0].cpu().numpy(), m['matching_scores0'][0].numpy()
+    flip = np.nonzero((ours_ms > 0) != (ref_ms > 0))[0]
+    for i in flip:
+        col = np.sort(zi[:, int(m['indices0'][0, i])])
+        assert col[-1] - col[-2] < 1e-3, 'mutual status of row %d differs without a tie' % i
+    keep = np.ones(n0, dtype=bool)
+    keep[flip] = False
+    ems = np.abs(ours_ms - ref_ms)[keep].max() if keep.any() else 0.0
+    print('\n[sinkhorn %dx%d it=%d] du %.2e dv %.2e agree %.4f/%.4f dms %.2e tie-flips %d' %
+          (n0, n1, iters, eu, ev, a0, a1, ems, len(flip)))
     assert eu <= 1e-4 and ev <= 1e-4
     assert a0 >= 0.999 and a1 >= 0.999
+    assert len(flip) <= max(2, n0 // 200)
     assert ems <= 1e-4 * max(1e-3, float(m['matching_scores0'].max())) + 1e-6
-    same = (m0[:n0].cpu() == m['matches0'][0]).float().mean()
+    same = (m0[:n0].cpu() == m['matches0'][0]).numpy()[keep].mean()
     assert same >= 0.999
 
 
