@@ -11,6 +11,7 @@ MAX_LAYERS = 64
 MAX_KENC = 8
 MAX_KPTS = 32768
 STATUS_EDGE_OVERFLOW = 1
+GEMM_SIMT, GEMM_TC = 0, 1
 PROF = {'gemm': 1, 'attention': 2, 'sinkhorn': 3, 'score': 4, 'cosine': 5, 'sage_gather': 6}
 
 
@@ -95,7 +96,13 @@ SIGNATURES = {
     'gims_attn_layer_forward': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                           C.c_void_p]),
     'gims_final_scores': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
-                                    C.c_void_p]),
+                                    C.c_void_p, C.c_void_p]),
+    'gims_set_gemm_mode': (C.c_int, [C.c_int]),
+    'gims_get_gemm_mode': (C.c_int, []),
+    'gims_linear': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
+                              C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+    'gims_split_tf32': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     'gims_sinkhorn_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int]),
     'gims_sinkhorn_match': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_void_p,
                                       C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
@@ -122,6 +129,9 @@ def lib():
         fn = getattr(handle, name)     # AttributeError if the symbol is missing
         fn.restype = res
         fn.argtypes = args
+    mode = os.environ.get('GIMS_GEMM_MODE')
+    if mode:
+        handle.gims_set_gemm_mode(GEMM_SIMT if mode.lower() == 'simt' else GEMM_TC)
     _LIB = handle
     return _LIB
 

@@ -106,33 +106,49 @@ extern "C" int gims_profile_end(double* total_ms, int* launches) {
 using namespace gims;
 
 // Packed weight blobs, in the order gims_b200/packing.py emits them.
+struct Wt {                    // one weight matrix [N][K]: fp32 + its tensor-core planes
+  const float* w;
+  const float* hi;             // tf32(W)
+  const float* lo;             // W - tf32(W)
+};
+
 struct gims_model {
   gims_config cfg;
   const float* bin_score;
-  const float* kenc_w[GIMS_MAX_KENC];
+  Wt kenc_w[GIMS_MAX_KENC];
   const float* kenc_b[GIMS_MAX_KENC];
-  const float* sage_w[3];      // L0: [256][256] rows 0..127 fc_neigh, 128..255 fc_self
+  Wt sage_w[3];                // L0: [256][256] rows 0..127 fc_neigh, 128..255 fc_self
                                // L1: [128][256] cols 0..127 fc_self, 128..255 fc_neigh;  L2: [256][256] likewise
   const float* sage_b[3];
-  const float* wqkv[GIMS_MAX_LAYERS];    // [768][256]  Q|K|V rows, head-major
+  Wt wqkv[GIMS_MAX_LAYERS];    // [768][256]  Q|K|V rows, head-major
   const float* bqkv[GIMS_MAX_LAYERS];
-  const float* wmerge[GIMS_MAX_LAYERS];  // [256][256]  input columns head-major
+  Wt wmerge[GIMS_MAX_LAYERS];  // [256][256]  input columns head-major
   const float* bmerge[GIMS_MAX_LAYERS];
-  const float* w1[GIMS_MAX_LAYERS];      // [512][512]  BN folded, input = [x | message]
+  Wt w1[GIMS_MAX_LAYERS];      // [512][512]  BN folded, input = [x | message]
   const float* b1[GIMS_MAX_LAYERS];
-  const float* w2[GIMS_MAX_LAYERS];      // [256][512]
+  Wt w2[GIMS_MAX_LAYERS];      // [256][512]
   const float* b2[GIMS_MAX_LAYERS];
-  const float* wfinal;
+  Wt wfinal;
   const float* bfinal;
 };
+
+static std::atomic<int> g_gemm_mode{GIMS_GEMM_TC};
 
 extern "C" int gims_version(void) { return 100; }
 extern "C" const char* gims_last_error(void) { return g_err; }
 extern "C" long long gims_launch_count(void) { return g_launches.load(); }
 
+extern "C" int gims_set_gemm_mode(int mode) {
+  if (mode != GIMS_GEMM_SIMT && mode != GIMS_GEMM_TC) { set_error("gims_set_gemm_mode: bad mode %d", mode); return GIMS_ERR_ARG; }
+  g_gemm_mode.store(mode);
+  return GIMS_OK;
+}
+extern "C" int gims_get_gemm_mode(void) { return g_gemm_mode.load(); }
+
 extern "C" int gims_packed_blob_count(const gims_config* c) {
   if (!c) return -1;
-  return 1 + 2 * c->kenc_num + 6 + 8 * c->num_layers + 2;
+  // every weight matrix contributes 3 blobs (W, W_hi, W_lo), every bias 1
+  return 1 + 4 * c->kenc_num + 4 * 3 + 16 * c->num_layers + 4;
 }
 
 extern "C" int gims_model_create(const gims_config* c, const float* packed, const int64_t* off, int n_off,
@@ -151,14 +167,15 @@ extern "C" int gims_model_create(const gims_config* c, const float* packed, cons
   m->cfg = *c;
   int k = 0;
   auto next = [&]() { return packed + off[k++]; };
+  auto next_w = [&]() { Wt w; w.w = next(); w.hi = next(); w.lo = next(); return w; };
   m->bin_score = next();
-  for (int i = 0; i < c->kenc_num; ++i) { m->kenc_w[i] = next(); m->kenc_b[i] = next(); }
-  for (int i = 0; i < 3; ++i) { m->sage_w[i] = next(); m->sage_b[i] = next(); }
+  for (int i = 0; i < c->kenc_num; ++i) { m->kenc_w[i] = next_w(); m->kenc_b[i] = next(); }
+  for (int i = 0; i < 3; ++i) { m->sage_w[i] = next_w(); m->sage_b[i] = next(); }
   for (int l = 0; l < c->num_layers; ++l) {
-    m->wqkv[l] = next(); m->bqkv[l] = next(); m->wmerge[l] = next(); m->bmerge[l] = next();
-    m->w1[l] = next(); m->b1[l] = next(); m->w2[l] = next(); m->b2[l] = next();
+    m->wqkv[l] = next_w(); m->bqkv[l] = next(); m->wmerge[l] = next_w(); m->bmerge[l] = next();
+    m->w1[l] = next_w(); m->b1[l] = next(); m->w2[l] = next_w(); m->b2[l] = next();
   }
-  m->wfinal = next(); m->bfinal = next();
+  m->wfinal = next_w(); m->bfinal = next();
   *out = m;
   return GIMS_OK;
 }
@@ -172,12 +189,15 @@ static Segs two_segs(int n0_max, int n1_max, const int* n_dev) {
   Segs s; s.base[0] = 0; s.base[1] = n0_max; s.nmax[0] = n0_max; s.nmax[1] = n1_max; s.n_dev = n_dev; s.nseg = 2; return s;
 }
 
-static GemmArgs gemm(const float* A0, int lda0, int K0, const float* A1, int lda1, int K1, const float* W,
-                     const float* bias, const float* R, int ldr, float* Y, int ldy, int N, int relu, Segs s) {
+// Y = epi(A W^T + bias): tcgen05 3xTF32 kernel when the shape allows and the mode asks for it, else fp32 SIMT.
+static int gemm(const float* A0, int lda0, int K0, const float* A1, int lda1, int K1, const Wt& W, const float* bias,
+                const float* R, int ldr, float* Y, int ldy, int N, int relu, Segs s, cudaStream_t st) {
   GemmArgs g;
-  g.A0 = A0; g.lda0 = lda0; g.K0 = K0; g.A1 = A1; g.lda1 = lda1; g.K1 = K1; g.W = W; g.bias = bias;
+  g.A0 = A0; g.lda0 = lda0; g.K0 = K0; g.A1 = A1; g.lda1 = lda1; g.K1 = K1; g.W = W.w; g.bias = bias;
   g.R = R; g.ldr = ldr; g.Y = Y; g.ldy = ldy; g.N = N; g.relu = relu; g.segs = s;
-  return g;
+  bool tc_ok = W.hi && W.lo && K0 % 32 == 0 && K1 % 32 == 0 && N % 32 == 0 && lda0 % 4 == 0 && (K1 == 0 || lda1 % 4 == 0);
+  if (g_gemm_mode.load() == GIMS_GEMM_TC && tc_ok) return launch_gemm_tc(g, W.hi, W.lo, st);
+  return launch_gemm(g, st);
 }
 
 // a-9 ------------------------------------------------------------------------------------------
@@ -192,14 +212,14 @@ extern "C" int gims_sage_forward(const gims_model* m, const float* feat, const i
   float* h2 = agg + (size_t)n_max * H;          // [n][128]   (total 2.5 * n * 256 floats)
   Segs s = one_seg(n_max, n_dev);
   // layer 0 (256 -> 128, fc_neigh before aggregation)
-  GIMS_TRY(launch_gemm(gemm(feat, kD, kD, nullptr, 0, 0, m->sage_w[0], nullptr, nullptr, 0, y0, kD, kD, 0, s), st));
+  GIMS_TRY(gemm(feat, kD, kD, nullptr, 0, 0, m->sage_w[0], nullptr, nullptr, 0, y0, kD, kD, 0, s, st));
   GIMS_TRY(launch_sage_aggregate(y0, kD, H, indptr, indices, n_max, n_dev, y0 + H, kD, m->sage_b[0], 1, h1, H, st));
   // layer 1 (128 -> 128, aggregate then fc_neigh)
   GIMS_TRY(launch_sage_aggregate(h1, H, H, indptr, indices, n_max, n_dev, nullptr, 0, nullptr, 0, agg, H, st));
-  GIMS_TRY(launch_gemm(gemm(h1, H, H, agg, H, H, m->sage_w[1], m->sage_b[1], nullptr, 0, h2, H, H, 1, s), st));
+  GIMS_TRY(gemm(h1, H, H, agg, H, H, m->sage_w[1], m->sage_b[1], nullptr, 0, h2, H, H, 1, s, st));
   // layer 2 (128 -> 256)
   GIMS_TRY(launch_sage_aggregate(h2, H, H, indptr, indices, n_max, n_dev, nullptr, 0, nullptr, 0, agg, H, st));
-  GIMS_TRY(launch_gemm(gemm(h2, H, H, agg, H, H, m->sage_w[2], m->sage_b[2], nullptr, 0, out, kD, kD, 0, s), st));
+  GIMS_TRY(gemm(h2, H, H, agg, H, H, m->sage_w[2], m->sage_b[2], nullptr, 0, out, kD, kD, 0, s, st));
   return GIMS_OK;
 }
 
@@ -211,14 +231,14 @@ extern "C" int gims_kenc_forward(const gims_model* m, const float* kpts, int n_m
   const gims_config& c = m->cfg;
   float* buf[2] = {scratch, scratch + (size_t)n_max * kD};
   Segs s = one_seg(n_max, n_dev);
-  GIMS_TRY(launch_kenc_first(kpts, n_max, n_dev, img_w, img_h, m->kenc_w[0], m->kenc_b[0], c.kenc_dims[1], buf[0], st));
+  GIMS_TRY(launch_kenc_first(kpts, n_max, n_dev, img_w, img_h, m->kenc_w[0].w, m->kenc_b[0], c.kenc_dims[1], buf[0], st));
   int cur = 0;
   for (int i = 1; i < c.kenc_num; ++i) {
     int cin = c.kenc_dims[i], cout = c.kenc_dims[i + 1];
     bool last = (i == c.kenc_num - 1);
     float* y = last ? desc : buf[cur ^ 1];
-    GIMS_TRY(launch_gemm(gemm(buf[cur], cin, cin, nullptr, 0, 0, m->kenc_w[i], m->kenc_b[i], last ? add : nullptr, kD, y,
-                              last ? kD : cout, cout, last ? 0 : 1, s), st));
+    GIMS_TRY(gemm(buf[cur], cin, cin, nullptr, 0, 0, m->kenc_w[i], m->kenc_b[i], last ? add : nullptr, kD, y,
+                              last ? kD : cout, cout, last ? 0 : 1, s, st));
     cur ^= 1;
   }
   return GIMS_OK;
@@ -237,23 +257,48 @@ extern "C" int gims_attn_layer_forward(const gims_model* m, int layer, float* de
   float* msg = att + rows * kD;            // [rows][256]
   float* hid = msg + rows * kD;            // [rows][512]
   Segs s = two_segs(n0_max, n1_max, n_dev);
-  GIMS_TRY(launch_gemm(gemm(desc, kD, kD, nullptr, 0, 0, m->wqkv[layer], m->bqkv[layer], nullptr, 0, qkv, 3 * kD, 3 * kD, 0, s), st));
+  GIMS_TRY(gemm(desc, kD, kD, nullptr, 0, 0, m->wqkv[layer], m->bqkv[layer], nullptr, 0, qkv, 3 * kD, 3 * kD, 0, s, st));
   GIMS_TRY(launch_attention(qkv, att, n0_max, n1_max, n_dev, m->cfg.layer_is_cross[layer], st));
-  GIMS_TRY(launch_gemm(gemm(att, kD, kD, nullptr, 0, 0, m->wmerge[layer], m->bmerge[layer], nullptr, 0, msg, kD, kD, 0, s), st));
-  GIMS_TRY(launch_gemm(gemm(desc, kD, kD, msg, kD, kD, m->w1[layer], m->b1[layer], nullptr, 0, hid, 2 * kD, 2 * kD, 1, s), st));
-  GIMS_TRY(launch_gemm(gemm(hid, 2 * kD, 2 * kD, nullptr, 0, 0, m->w2[layer], m->b2[layer], desc, kD, desc, kD, kD, 0, s), st));
+  GIMS_TRY(gemm(att, kD, kD, nullptr, 0, 0, m->wmerge[layer], m->bmerge[layer], nullptr, 0, msg, kD, kD, 0, s, st));
+  GIMS_TRY(gemm(desc, kD, kD, msg, kD, kD, m->w1[layer], m->b1[layer], nullptr, 0, hid, 2 * kD, 2 * kD, 1, s, st));
+  GIMS_TRY(gemm(hid, 2 * kD, 2 * kD, nullptr, 0, 0, m->w2[layer], m->b2[layer], desc, kD, desc, kD, kD, 0, s, st));
   return GIMS_OK;
 }
 
 // a-13 -----------------------------------------------------------------------------------------
 extern "C" int gims_final_scores(const gims_model* m, const float* desc, int n0_max, int n1_max, const int* n_dev,
-                                 float* mdesc, float* couplings, void* stream) {
+                                 float* mdesc, float* couplings, float* scratch, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!m) { set_error("gims_final_scores: null model"); return GIMS_ERR_ARG; }
   Segs s = two_segs(n0_max, n1_max, n_dev);
-  GIMS_TRY(launch_gemm(gemm(desc, kD, kD, nullptr, 0, 0, m->wfinal, m->bfinal, nullptr, 0, mdesc, kD, kD, 0, s), st));
-  GIMS_TRY(launch_score_gemm(mdesc, n0_max, n1_max, n_dev, m->bin_score, couplings, st));
+  GIMS_TRY(gemm(desc, kD, kD, nullptr, 0, 0, m->wfinal, m->bfinal, nullptr, 0, mdesc, kD, kD, 0, s, st));
+  if (g_gemm_mode.load() == GIMS_GEMM_TC && scratch) {
+    GIMS_TRY(launch_score_gemm_tc(mdesc, n0_max, n1_max, n_dev, scratch, couplings, st));
+    GIMS_TRY(launch_score_border(n0_max, n1_max, n_dev, m->bin_score, couplings, st));
+  } else {
+    GIMS_TRY(launch_score_gemm(mdesc, n0_max, n1_max, n_dev, m->bin_score, couplings, st));
+  }
   return GIMS_OK;
+}
+
+// test / bring-up entry points ----------------------------------------------------------------
+extern "C" int gims_linear(const float* A0, int lda0, int K0, const float* A1, int lda1, int K1, const float* W,
+                           const float* W_hi, const float* W_lo, const float* bias, const float* R, int ldr, float* Y,
+                           int ldy, int N, int relu, int rows_max, const int* rows_dev, int mode, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  GemmArgs g;
+  g.A0 = A0; g.lda0 = lda0; g.K0 = K0; g.A1 = A1; g.lda1 = lda1; g.K1 = K1; g.W = W; g.bias = bias;
+  g.R = R; g.ldr = ldr; g.Y = Y; g.ldy = ldy; g.N = N; g.relu = relu; g.segs = one_seg(rows_max, rows_dev);
+  if (mode == GIMS_GEMM_TC) {
+    if (!W_hi || !W_lo) { set_error("gims_linear: tensor-core mode needs W_hi / W_lo"); return GIMS_ERR_ARG; }
+    return launch_gemm_tc(g, W_hi, W_lo, st);
+  }
+  return launch_gemm(g, st);
+}
+
+extern "C" int gims_split_tf32(const float* x, float* hi, float* lo, size_t n, void* stream) {
+  if (n % 4) { set_error("gims_split_tf32: n must be a multiple of 4"); return GIMS_ERR_ARG; }
+  return launch_split_planes(x, hi, lo, n, static_cast<cudaStream_t>(stream));
 }
 
 // whole pair -----------------------------------------------------------------------------------
@@ -330,7 +375,7 @@ extern "C" int gims_forward_pair(const gims_model* m, const gims_pair_inputs* in
   }
   // a-13 .. a-15
   float* coup = o->couplings ? o->couplings : w.couplings;
-  GIMS_TRY(gims_final_scores(m, w.desc, n0, n1, o->n_kept_dev, o->mdesc, coup, stream));
+  GIMS_TRY(gims_final_scores(m, w.desc, n0, n1, o->n_kept_dev, o->mdesc, coup, w.scratch, stream));
   GIMS_TRY(gims_sinkhorn_match(coup, n0, n1, o->n_kept_dev, m->cfg.sinkhorn_iterations, m->cfg.match_threshold, w.sink,
                                w.sink_bytes, o->u, o->v, o->indices[0], o->indices[1], o->matches[0], o->matches[1],
                                o->mscores[0], o->mscores[1], stream));

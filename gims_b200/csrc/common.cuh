@@ -103,6 +103,14 @@ struct GemmArgs {
 };
 int launch_gemm(const GemmArgs& a, cudaStream_t st);
 
+// tensor-core (tcgen05, 3xTF32) variants — gemm_tc.cu
+int launch_gemm_tc(const GemmArgs& a, const float* w_hi, const float* w_lo, cudaStream_t st);
+int launch_score_gemm_tc(const float* mdesc, int n0_max, int n1_max, const int* n_dev, float* planes, float* couplings,
+                         cudaStream_t st);
+int launch_split_planes(const float* x, float* hi, float* lo, size_t n, cudaStream_t st);
+int launch_score_border(int n0_max, int n1_max, const int* n_dev, const float* bin_score, float* couplings,
+                        cudaStream_t st);
+
 // scores GEMM: couplings[i][j] = scale * <A_i, B_j>, with the dustbin border (gmatcher.py:59-60)
 int launch_score_gemm(const float* mdesc, int n0_max, int n1_max, const int* n_dev, const float* bin_score,
                       float* couplings, cudaStream_t st);

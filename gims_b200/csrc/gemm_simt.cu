@@ -189,8 +189,15 @@ int launch_score_gemm(const float* mdesc, int n0_max, int n1_max, const int* n_d
   ProfScope prof(GIMS_PROF_SCORE, st);
   k_gemm_simt<kModeScore><<<dim3(cdiv(n1_max, BN), g.tiles0), 256, 0, st>>>(g);
   GIMS_LAUNCH_OK();
+  return launch_score_border(n0_max, n1_max, n_dev, bin_score, couplings, st);
+}
+
+int launch_score_border(int n0_max, int n1_max, const int* n_dev, const float* bin_score, float* couplings,
+                        cudaStream_t st) {
+  Segs s;
+  s.base[0] = 0; s.base[1] = n0_max; s.nmax[0] = n0_max; s.nmax[1] = n1_max; s.n_dev = n_dev; s.nseg = 2;
   int m = (n0_max > n1_max ? n0_max : n1_max) + 1;
-  k_score_border<<<cdiv(m, 256), 256, 0, st>>>(couplings, n1_max + 1, g.segs, bin_score);
+  k_score_border<<<cdiv(m, 256), 256, 0, st>>>(couplings, n1_max + 1, s, bin_score);
   GIMS_LAUNCH_OK();
   return GIMS_OK;
 }

@@ -1,0 +1,352 @@
+// fp32-accurate GEMM on the 5th-generation tensor cores (tcgen05 / TMEM / TMA), 3xTF32 error compensation.
+//
+//   Y[r][o] = epi( sum_k A(r,k) * W[o][k] + bias[o] )        A, W K-major — the same contract as gemm_simt.cu
+//
+// (Conv1d(k=1) / Linear of models/gmatcher.py:11-24, 105-125, 273 and the SAGE linears.)  Every fp32 operand x
+// is split x = hi + lo with hi = tf32(x); the accumulator receives A_hi*W_hi + A_lo*W_hi + A_hi*W_lo in fp32
+// (TMEM), i.e. ~2^-21 relative accuracy per product instead of TF32's 2^-11.
+//
+// Structure (one CTA = one 128 x BN output tile, 192 threads):
+//   warp 0      TMA producer: raw A tile, W_hi tile, W_lo tile per k-block (32 floats = one 128-B swizzle row)
+//   warp 1      allocates TMEM, then a single thread issues tcgen05.mma (3 per 8-wide k-step) and commits
+//   warps 2..5  split the raw A tile in shared memory into hi (in place) / lo, then run the epilogue:
+//               tcgen05.ld (32 lanes x 32 columns) -> bias / residual / ReLU -> 128-bit global stores
+// W_hi / W_lo are split once at weight-pack time; activations are split on the fly, so no tensor in HBM
+// changes layout.  Pipeline: full[s] (TMA bytes) -> conv[s] (A split done) -> MMA -> empty[s] (tcgen05.commit).
+#include "common.cuh"
+#include "tc_common.cuh"
+
+namespace gims {
+
+namespace tc {
+
+EncodeTiledFn get_encode_tiled() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+int make_tmap_f32_k32(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return GIMS_ERR_CUDA; }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * sizeof(float)};
+  cuuint32_t box[2] = {32, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d) base=%p rows=%llu cols=%llu ld=%llu box_rows=%u", (int)r, (const void*)base,
+              (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows);
+    return GIMS_ERR_CUDA;
+  }
+  return GIMS_OK;
+}
+
+}  // namespace tc
+
+namespace {
+
+using namespace tc;
+
+constexpr int BM = 128, BK = 32;
+constexpr int kThreadsTc = 192;
+
+template <int BN>
+struct TcCfg {
+  static constexpr int kStages = (BN <= 64) ? 4 : (BN <= 128 ? 3 : 2);
+  static constexpr int kABytes = BM * BK * 4;            // 16 KB
+  static constexpr int kWBytes = BN * BK * 4;
+  static constexpr int kStageBytes = 2 * kABytes + 2 * kWBytes;
+  // The tensor core rounds the fp32 accumulator toward zero on every accumulation, so the error of one long
+  // accumulation chain grows linearly.  The two small correction products go to their own accumulator, and the
+  // hi*hi product alternates over kMainAcc accumulators by k-block; the epilogue adds them in fp32 (RN).
+  static constexpr int kMainAcc = (BN <= 64) ? 4 : (BN <= 128 ? 2 : 1);
+  static constexpr int kAccCols = (kMainAcc + 1) * BN;
+  static constexpr int kTmemCols = (kAccCols <= 128) ? 128 : (kAccCols <= 256 ? 256 : 512);
+  static_assert(kAccCols <= 512, "accumulators exceed TMEM");
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct TcArgs {
+  int K0, K1;                    // k extents served by tensor maps A0 / A1 (multiples of 32)
+  const float* bias;
+  const float* R; int ldr;
+  float* Y; int ldy;
+  int N;                         // live output columns (score mode: from n_dev[1])
+  int relu;
+  float scale;                   // score mode
+  int score;                     // 1: Y is the couplings matrix (row-major, ldy = n1_max+1), W rows = image-1 rows
+  Segs segs;
+  int tiles0;
+};
+
+template <int BN>
+__global__ void __launch_bounds__(kThreadsTc, 1)
+k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+          const __grid_constant__ CUtensorMap mapWhi, const __grid_constant__ CUtensorMap mapWlo, TcArgs g) {
+  using Cfg = TcCfg<BN>;
+  extern __shared__ uint8_t smem_raw[];
+  // ---- tile coordinates (uniform per CTA) -------------------------------------------------------
+  int seg, tile;
+  if (g.score) { seg = 0; tile = blockIdx.y; }
+  else if ((int)blockIdx.y < g.tiles0) { seg = 0; tile = blockIdx.y; }
+  else { seg = 1; tile = blockIdx.y - g.tiles0; }
+  const int rows = seg_count(g.segs, seg);
+  const int ncols = g.score ? seg_count(g.segs, 1) : g.N;
+  const int r0 = tile * BM, c0 = blockIdx.x * BN;
+  if (r0 >= rows || c0 >= ncols) return;
+  const int rbase = g.segs.base[seg];
+  const int wbase = g.score ? g.segs.base[1] : 0;
+
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
+  uint64_t* full = bars;                          // [kStages]
+  uint64_t* conv = bars + Cfg::kStages;           // [kStages]
+  uint64_t* empty = bars + 2 * Cfg::kStages;      // [kStages]
+  uint64_t* accum_full = bars + 3 * Cfg::kStages; // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * Cfg::kStages + 1);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nkb = (g.K0 + g.K1) / BK;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&mapA0);
+    if (g.K1) tma_prefetch_desc(&mapA1);
+    tma_prefetch_desc(&mapWhi);
+    tma_prefetch_desc(&mapWlo);
+    for (int s = 0; s < Cfg::kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&conv[s], 4);        // one arrival per converter warp
+      mbar_init(&empty[s], 1);
+    }
+    mbar_init(accum_full, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  auto stage_ptr = [&](int s) { return smem + (size_t)s * Cfg::kStageBytes; };
+
+  if (warp == 0) {
+    // ===== TMA producer =====
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&empty[s], ph ^ 1);
+        uint8_t* st = stage_ptr(s);
+        mbar_arrive_expect_tx(&full[s], Cfg::kABytes + 2 * Cfg::kWBytes);
+        int k = kb * BK;
+        if (k < g.K0) tma_load_2d(st, &mapA0, &full[s], k, rbase + r0);
+        else          tma_load_2d(st, &mapA1, &full[s], k - g.K0, rbase + r0);
+        tma_load_2d(st + 2 * Cfg::kABytes, &mapWhi, &full[s], k, wbase + c0);
+        tma_load_2d(st + 2 * Cfg::kABytes + Cfg::kWBytes, &mapWlo, &full[s], k, wbase + c0);
+        if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_tf32(BM, BN);
+      int s = 0; uint32_t ph = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full[s], ph);
+        mbar_wait(&conv[s], ph);
+        tcgen05_fence_after();
+        uint32_t a_hi = smem_u32(stage_ptr(s));
+        uint32_t a_lo = a_hi + Cfg::kABytes;
+        uint32_t w_hi = a_hi + 2 * Cfg::kABytes;
+        uint32_t w_lo = w_hi + Cfg::kWBytes;
+#pragma unroll
+        for (int ks = 0; ks < BK / 8; ++ks) {
+          uint32_t koff = ks * 32;                    // 8 tf32 = 32 bytes inside the 128-B swizzle row
+          uint64_t dah = umma_desc_sw128(a_hi + koff), dal = umma_desc_sw128(a_lo + koff);
+          uint64_t dwh = umma_desc_sw128(w_hi + koff), dwl = umma_desc_sw128(w_lo + koff);
+          const uint32_t corr = tmem_base + Cfg::kMainAcc * BN;
+          const uint32_t main_acc = tmem_base + (kb % Cfg::kMainAcc) * BN;
+          umma_tf32_ss(corr, dal, dwh, idesc, (kb | ks) ? 1u : 0u);
+          umma_tf32_ss(corr, dah, dwl, idesc, 1u);
+          umma_tf32_ss(main_acc, dah, dwh, idesc, (kb >= Cfg::kMainAcc || ks) ? 1u : 0u);
+        }
+        umma_commit(&empty[s]);                        // smem slot reusable once these MMAs retire
+        if (kb == nkb - 1) umma_commit(accum_full);    // accumulator complete
+        if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
+      }
+    }
+  } else {
+    // ===== A splitters (warps 2..5), then epilogue =====
+    const int t = threadIdx.x - 64;                    // 0..127
+    {
+      int s = 0; uint32_t ph = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full[s], ph);
+        float4* raw = reinterpret_cast<float4*>(stage_ptr(s));
+        float4* lo = reinterpret_cast<float4*>(stage_ptr(s) + Cfg::kABytes);
+#pragma unroll
+        for (int i = 0; i < Cfg::kABytes / 16 / 128; ++i) {
+          int c = t + 128 * i;
+          float4 x = raw[c], h, l;
+          split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y); split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
+          raw[c] = h;
+          lo[c] = l;
+        }
+        fence_proxy_async_smem();                      // generic-proxy writes -> visible to the tensor core (async proxy)
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&conv[s]);
+        if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
+      }
+    }
+    mbar_wait(accum_full, 0);
+    tcgen05_fence_after();
+    const int q = warp & 3;                            // TMEM lane quarter this warp may access
+    const int r = r0 + 32 * q + lane;
+    const bool row_ok = r < rows;
+#pragma unroll 1
+    const int n_main = nkb < Cfg::kMainAcc ? nkb : Cfg::kMainAcc;
+    for (int cc = 0; cc < BN / 32; ++cc) {
+      uint32_t v[32];
+      const uint32_t lane_col = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(cc * 32);
+      tmem_ld_32x32(lane_col, v);
+      tmem_ld_wait();
+      for (int a = 1; a <= Cfg::kMainAcc; ++a) {
+        if (a < Cfg::kMainAcc && a >= n_main) continue;        // accumulator never written (short K)
+        uint32_t w[32];
+        tmem_ld_32x32(lane_col + (uint32_t)(a * BN), w);       // a == kMainAcc: the correction accumulator
+        tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+      }
+      int c = c0 + cc * 32;
+      if (!row_ok || c >= ncols) continue;
+      if (g.score) {
+        float* y = g.Y + (size_t)r * g.ldy + c;
+#pragma unroll
+        for (int j = 0; j < 32; ++j)
+          if (c + j < ncols) y[j] = __uint_as_float(v[j]) * g.scale;
+      } else {
+        size_t row = (size_t)(rbase + r);
+        float* y = g.Y + row * g.ldy + c;
+        const float* rr = g.R ? g.R + row * g.ldr + c : nullptr;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+          float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                                 __uint_as_float(v[j + 3]));
+          if (g.bias) {
+            float4 b = *reinterpret_cast<const float4*>(g.bias + c + j);
+            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+          }
+          if (rr) {
+            float4 b = *reinterpret_cast<const float4*>(rr + j);
+            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+          }
+          if (g.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
+          *reinterpret_cast<float4*>(y + j) = o;
+        }
+      }
+    }
+    tcgen05_fence_before();
+  }
+  __syncthreads();
+  if (warp == 1) {
+    tcgen05_fence_after();
+    tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+}
+
+// x -> (hi, lo) planes, hi = tf32(x); used for activations that act as the "weight" operand (score GEMM)
+__global__ void k_split_planes(const float* __restrict__ x, float* __restrict__ hi, float* __restrict__ lo, size_t n4) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  float4 v = reinterpret_cast<const float4*>(x)[i], h, l;
+  tc::split_tf32(v.x, h.x, l.x); tc::split_tf32(v.y, h.y, l.y); tc::split_tf32(v.z, h.z, l.z); tc::split_tf32(v.w, h.w, l.w);
+  reinterpret_cast<float4*>(hi)[i] = h;
+  reinterpret_cast<float4*>(lo)[i] = l;
+}
+
+template <int BN>
+int launch_tc(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& whi, const CUtensorMap& wlo,
+              const TcArgs& g, int col_tiles, int row_tiles, int prof_class, cudaStream_t st) {
+  using Cfg = TcCfg<BN>;
+  GIMS_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+  ProfScope prof(prof_class, st);
+  k_gemm_tc<BN><<<dim3(col_tiles, row_tiles), kThreadsTc, Cfg::kSmemBytes, st>>>(a0, a1, whi, wlo, g);
+  GIMS_LAUNCH_OK();
+  return GIMS_OK;
+}
+
+int pick_bn(int n) {
+  if (n >= 768) return 192;
+  if (n >= 512) return 128;
+  return 64;
+}
+
+}  // namespace
+
+// W_hi / W_lo: [N][K] planes produced at pack time (gims_b200/packing.py) — same layout as the fp32 weight.
+int launch_gemm_tc(const GemmArgs& a, const float* w_hi, const float* w_lo, cudaStream_t st) {
+  int K = a.K0 + a.K1;
+  if (a.K0 % BK || a.K1 % BK || K == 0 || a.N % 32 || (a.lda0 % 4) || (a.K1 && (a.lda1 % 4))) {
+    set_error("launch_gemm_tc: unsupported shape K0=%d K1=%d N=%d", a.K0, a.K1, a.N);
+    return GIMS_ERR_ARG;
+  }
+  int total_rows = a.segs.nseg > 1 ? a.segs.base[1] + a.segs.nmax[1] : a.segs.nmax[0];
+  int bn = pick_bn(a.N);
+  CUtensorMap mA0, mA1, mWh, mWl;
+  GIMS_TRY(tc::make_tmap_f32_k32(&mA0, a.A0, total_rows, a.K0, a.lda0, BM));
+  if (a.K1) GIMS_TRY(tc::make_tmap_f32_k32(&mA1, a.A1, total_rows, a.K1, a.lda1, BM));
+  else mA1 = mA0;
+  GIMS_TRY(tc::make_tmap_f32_k32(&mWh, w_hi, a.N, K, K, bn));
+  GIMS_TRY(tc::make_tmap_f32_k32(&mWl, w_lo, a.N, K, K, bn));
+  TcArgs g;
+  g.K0 = a.K0; g.K1 = a.K1; g.bias = a.bias; g.R = a.R; g.ldr = a.ldr; g.Y = a.Y; g.ldy = a.ldy; g.N = a.N;
+  g.relu = a.relu; g.scale = 1.f; g.score = 0; g.segs = a.segs;
+  g.tiles0 = cdiv(a.segs.nmax[0], BM);
+  int tiles = g.tiles0 + (a.segs.nseg > 1 ? cdiv(a.segs.nmax[1], BM) : 0);
+  if (tiles == 0) return GIMS_OK;
+  int ct = cdiv(a.N, bn);
+  switch (bn) {
+    case 192: return launch_tc<192>(mA0, mA1, mWh, mWl, g, ct, tiles, GIMS_PROF_GEMM, st);
+    case 128: return launch_tc<128>(mA0, mA1, mWh, mWl, g, ct, tiles, GIMS_PROF_GEMM, st);
+    default:  return launch_tc<64>(mA0, mA1, mWh, mWl, g, ct, tiles, GIMS_PROF_GEMM, st);
+  }
+}
+
+int launch_split_planes(const float* x, float* hi, float* lo, size_t n, cudaStream_t st) {
+  size_t n4 = n / 4;
+  k_split_planes<<<(unsigned)((n4 + 255) / 256), 256, 0, st>>>(x, hi, lo, n4);
+  GIMS_LAUNCH_OK();
+  return GIMS_OK;
+}
+
+// couplings[i][j] = <mdesc0_i, mdesc1_j> / 16 on tensor cores; `planes` = 2 * (n0_max+n1_max) * 256 floats scratch
+int launch_score_gemm_tc(const float* mdesc, int n0_max, int n1_max, const int* n_dev, float* planes, float* couplings,
+                         cudaStream_t st) {
+  size_t rows = (size_t)n0_max + n1_max;
+  float* hi = planes;
+  float* lo = planes + rows * kD;
+  GIMS_TRY(launch_split_planes(mdesc, hi, lo, rows * kD, st));
+  constexpr int bn = 128;
+  CUtensorMap mA, mWh, mWl;
+  GIMS_TRY(tc::make_tmap_f32_k32(&mA, mdesc, rows, kD, kD, BM));
+  GIMS_TRY(tc::make_tmap_f32_k32(&mWh, hi, rows, kD, kD, bn));
+  GIMS_TRY(tc::make_tmap_f32_k32(&mWl, lo, rows, kD, kD, bn));
+  TcArgs g;
+  g.K0 = kD; g.K1 = 0; g.bias = nullptr; g.R = nullptr; g.ldr = 0; g.Y = couplings; g.ldy = n1_max + 1; g.N = n1_max;
+  g.relu = 0; g.scale = 0.0625f; g.score = 1;
+  g.segs.base[0] = 0; g.segs.base[1] = n0_max; g.segs.nmax[0] = n0_max; g.segs.nmax[1] = n1_max; g.segs.n_dev = n_dev;
+  g.segs.nseg = 2;
+  g.tiles0 = cdiv(n0_max, BM);
+  return launch_tc<bn>(mA, mA, mWh, mWl, g, cdiv(n1_max, bn), g.tiles0, GIMS_PROF_SCORE, st);
+}
+
+}  // namespace gims

@@ -11,7 +11,10 @@ Done once at load time, in float64 then rounded to fp32:
     layers 1, 2 stacked along K as [fc_self | fc_neigh] acting on cat[h, mean_neigh(h)]
   * Conv1d weights (out, in, 1) -> (out, in)
 
-Blob order (== offsets passed to gims_model_create):
+  * every weight matrix W is followed by its tensor-core planes W_hi = tf32(W) (round-to-nearest, ties away,
+    like cvt.rna.tf32.f32) and W_lo = W - W_hi (exact in fp32), consumed by the 3xTF32 tcgen05 GEMM
+
+Blob order (== offsets passed to gims_model_create); each matrix W stands for three blobs W, W_hi, W_lo:
   bin_score, (kenc W_i, b_i) for every kenc conv, (sage W_l, b_l) l=0..2,
   per attention layer: Wqkv, bqkv, Wmerge, bmerge, W1, b1, W2, b2; final_proj W, b.
 """
@@ -36,6 +39,14 @@ def head_permutation(d):
     return (cp % hd) * NUM_HEADS + cp // hd
 
 
+def split_tf32(w32):
+    """fp32 tensor -> (hi, lo): hi = w rounded to a 10-bit mantissa (ties away from zero), lo = w - hi."""
+    bits = w32.contiguous().view(torch.int32)
+    hi_bits = (bits + 0x1000) & ~0x1FFF          # sign-magnitude encoding: adding half an ulp rounds |w| away on ties
+    hi = hi_bits.view(torch.float32)
+    return hi, w32 - hi
+
+
 def pack_state_dict(sd, config=None):
     """Returns (flat fp32 CPU tensor, list of float offsets, list of blob names)."""
     cfg = {**DEFAULT_CONFIG, **(config or {})}
@@ -44,7 +55,12 @@ def pack_state_dict(sd, config=None):
     blobs = []
 
     def add(name, t):
-        blobs.append((name, t.double().contiguous()))
+        t = t.double().contiguous()
+        blobs.append((name, t))
+        if t.dim() == 2:                          # weight matrix: append the tensor-core planes
+            hi, lo = split_tf32(t.float())
+            blobs.append((name + '.hi', hi.double()))
+            blobs.append((name + '.lo', lo.double()))
 
     add('bin_score', sd['bin_score'].reshape(1))
     ch = kenc_channels(cfg)

@@ -70,6 +70,21 @@ GIMS_API const char* gims_last_error(void);
 /* number of kernels this library has launched in the calling process (for bench `gpu_launches`) */
 GIMS_API long long   gims_launch_count(void);
 
+/* GEMM arithmetic of the dense contractions (process-wide):
+ *   GIMS_GEMM_TC   tcgen05/TMEM/TMA tensor-core kernels, 3xTF32 error-compensated fp32 (default)
+ *   GIMS_GEMM_SIMT fp32 FMA CUDA-core kernels (bit-for-bit fp32 products; used to validate the former) */
+#define GIMS_GEMM_SIMT 0
+#define GIMS_GEMM_TC   1
+GIMS_API int gims_set_gemm_mode(int mode);
+GIMS_API int gims_get_gemm_mode(void);
+
+/* Bring-up / test entry points for the GEMM kernels: Y[r][o] = act(sum_k A(r,k) W[o][k] + bias[o] + R[r][o]),
+ * A = [A0 | A1] along K (K0 + K1), W [N][K0+K1]; W_hi/W_lo = planes from gims_split_tf32 (TC mode). */
+GIMS_API int gims_linear(const float* A0, int lda0, int K0, const float* A1, int lda1, int K1, const float* W,
+                const float* W_hi, const float* W_lo, const float* bias, const float* R, int ldr, float* Y, int ldy,
+                int N, int relu, int rows_max, const int* rows_dev, int mode, void* stream);
+GIMS_API int gims_split_tf32(const float* x, float* hi, float* lo, size_t n, void* stream);
+
 /* ---- profiling hooks (bench.py roofline): CUDA-event timing of ONE kernel class, recorded on the
  * stream each launch goes to.  begin() arms it for at most max_launches launches; end() waits for
  * the recorded events and returns the summed device time and the number of launches timed. */
@@ -141,9 +156,10 @@ GIMS_API int gims_attn_layer_forward(const gims_model* m, int layer, float* desc
 /* ---- a-13: final_proj + score matrix (gmatcher.py:273-275) ----------------------------------
  * mdesc [rows][256] = final_proj(desc); couplings (n0_max+1) x ld, ld = n1_max+1:
  *   Z0[i][j] = <mdesc0_i, mdesc1_j>/16 for i<N0', j<N1'; bin_score on row N0' and column N1'
- *   (the torch.cat of gmatcher.py:59-60). */
+ *   (the torch.cat of gmatcher.py:59-60).  scratch: 2*(n0_max+n1_max)*256 floats (tf32 planes of mdesc for the
+ *   tensor-core score GEMM) or NULL (CUDA-core score GEMM). */
 GIMS_API int gims_final_scores(const gims_model* m, const float* desc, int n0_max, int n1_max, const int* n_dev,
-                      float* mdesc, float* couplings, void* stream);
+                      float* mdesc, float* couplings, float* scratch, void* stream);
 
 /* ---- a-14 + a-15: log-domain Sinkhorn + mutual-NN matches (gmatcher.py:41-69, 284-294) ------
  * couplings as written by gims_final_scores.  Outputs (capacities n0_max / n1_max):

@@ -37,7 +37,7 @@ def test_host_queries(lib):
     from gims_b200 import GMatcher
     m = GMatcher({})
     c = m.c_config()
-    assert lib.gims_packed_blob_count(C.byref(c)) == 1 + 10 + 6 + 18 * 8 + 2
+    assert lib.gims_packed_blob_count(C.byref(c)) == 1 + 4 * 5 + 4 * 3 + 16 * 18 + 4
     assert [c.layer_is_cross[i] for i in range(4)] == [0, 1, 0, 1]
     assert [c.kenc_dims[i] for i in range(6)] == [2, 32, 64, 128, 256, 256]
 

@@ -8,6 +8,8 @@ python -c "import os;print('cpus',os.cpu_count())" >> gpurun_out/gpu.txt
 grep -m1 "model name" /proc/cpuinfo >> gpurun_out/gpu.txt
 for s in $STAGES; do
   case $s in
+    tc)    timeout 300 python -m pytest tests/test_gpu_gemm.py -m gpu -q --tb=short -s > gpurun_out/test_tc.log 2>&1; echo "tc rc=$?" ;;
+    fwd_simt) GIMS_GEMM_MODE=simt timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q --tb=short -k "not agc and not sinkhorn" -s > gpurun_out/test_fwd_simt.log 2>&1; echo "fwd_simt rc=$?" ;;
     agc)   timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q --tb=short -k "agc" -s > gpurun_out/test_agc.log 2>&1; echo "agc rc=$?" ;;
     sink)  timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q --tb=short -k "sinkhorn" -s > gpurun_out/test_sink.log 2>&1; echo "sink rc=$?" ;;
     fwd)   timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q --tb=short -k "not agc and not sinkhorn" -s > gpurun_out/test_fwd.log 2>&1; echo "fwd rc=$?" ;;
