@@ -277,7 +277,7 @@ def main():
                 flops = 2.0 * 256 * (n0k + n1k) ** 2
                 ach = flops / avg_s / 1e12
                 peak = peaks['bf16_tflops_sustained']
-                roof = {'kernel': 'k_attention_simt', 'bound': 'tensor', 'achieved': ach, 'peak': peak,
+                roof = {'kernel': 'k_attention_tc', 'bound': 'tensor', 'achieved': ach, 'peak': peak,
                         'unit': 'TFLOP/s', 'frac': ach / peak, 'traffic': None,
                         'peak_source': peaks['_source'] + ' bf16 sustained', 'launches_timed': cnt.value,
                         'avg_launch_ms': avg_s * 1e3, 'flops_per_launch': flops}

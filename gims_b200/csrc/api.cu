@@ -245,20 +245,33 @@ extern "C" int gims_kenc_forward(const gims_model* m, const float* kpts, int n_m
 }
 
 // a-11 + a-12 ----------------------------------------------------------------------------------
-extern "C" size_t gims_attn_scratch_floats(int rows) { return (size_t)rows * (3 * kD + kD + kD + 2 * kD); }
+// qkv (or its tf32 planes: 6 * rows * 256 + padding of the transposed V rows) | att | msg | hid
+extern "C" size_t gims_attn_scratch_floats(int rows) { return (size_t)rows * (6 * kD + kD + kD + 2 * kD) + 2 * 128 * kD; }
 
 extern "C" int gims_attn_layer_forward(const gims_model* m, int layer, float* desc, int n0_max, int n1_max,
                                        const int* n_dev, float* scratch, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (!m || layer < 0 || layer >= m->cfg.num_layers) { set_error("gims_attn_layer_forward: bad layer %d", layer); return GIMS_ERR_ARG; }
   size_t rows = (size_t)n0_max + n1_max;
-  float* qkv = scratch;                    // [rows][768]
-  float* att = qkv + rows * 3 * kD;        // [rows][256]
+  int ldv = attn_ldv(n0_max, n1_max);      // <= rows + 126
+  float* qkv = scratch;                    // [rows][768]  (SIMT)  |  Qp, Kp, Vt planes (tensor cores)
+  float* att = qkv + rows * 6 * kD + 2 * 128 * kD;   // [rows][256]
   float* msg = att + rows * kD;            // [rows][256]
   float* hid = msg + rows * kD;            // [rows][512]
   Segs s = two_segs(n0_max, n1_max, n_dev);
-  GIMS_TRY(gemm(desc, kD, kD, nullptr, 0, 0, m->wqkv[layer], m->bqkv[layer], nullptr, 0, qkv, 3 * kD, 3 * kD, 0, s, st));
-  GIMS_TRY(launch_attention(qkv, att, n0_max, n1_max, n_dev, m->cfg.layer_is_cross[layer], st));
+  if (g_gemm_mode.load() == GIMS_GEMM_TC) {
+    QkvPlanes pl;
+    pl.qp = qkv; pl.kp = pl.qp + 2 * rows * kD; pl.vt = pl.kp + 2 * rows * kD; pl.ldv = ldv;
+    pl.vbase1 = attn_vbase1(n0_max);
+    GemmArgs g;
+    g.A0 = desc; g.lda0 = kD; g.K0 = kD; g.A1 = nullptr; g.lda1 = 0; g.K1 = 0; g.W = m->wqkv[layer].w;
+    g.bias = m->bqkv[layer]; g.R = nullptr; g.ldr = 0; g.Y = nullptr; g.ldy = 0; g.N = 3 * kD; g.relu = 0; g.segs = s;
+    GIMS_TRY(launch_gemm_tc(g, m->wqkv[layer].hi, m->wqkv[layer].lo, st, &pl));
+    GIMS_TRY(launch_attention_tc(pl, att, n0_max, n1_max, n_dev, m->cfg.layer_is_cross[layer], st));
+  } else {
+    GIMS_TRY(gemm(desc, kD, kD, nullptr, 0, 0, m->wqkv[layer], m->bqkv[layer], nullptr, 0, qkv, 3 * kD, 3 * kD, 0, s, st));
+    GIMS_TRY(launch_attention(qkv, att, n0_max, n1_max, n_dev, m->cfg.layer_is_cross[layer], st));
+  }
   GIMS_TRY(gemm(att, kD, kD, nullptr, 0, 0, m->wmerge[layer], m->bmerge[layer], nullptr, 0, msg, kD, kD, 0, s, st));
   GIMS_TRY(gemm(desc, kD, kD, msg, kD, kD, m->w1[layer], m->b1[layer], nullptr, 0, hid, 2 * kD, 2 * kD, 1, s, st));
   GIMS_TRY(gemm(hid, 2 * kD, 2 * kD, nullptr, 0, 0, m->w2[layer], m->b2[layer], desc, kD, desc, kD, kD, 0, s, st));

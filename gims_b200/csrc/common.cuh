@@ -104,7 +104,19 @@ struct GemmArgs {
 int launch_gemm(const GemmArgs& a, cudaStream_t st);
 
 // tensor-core (tcgen05, 3xTF32) variants — gemm_tc.cu
-int launch_gemm_tc(const GemmArgs& a, const float* w_hi, const float* w_lo, cudaStream_t st);
+struct QkvPlanes {            // outputs of the QKV projection in the layout attention_tc.cu consumes
+  float* qp;                  // [2][rows_total][256]
+  float* kp;                  // [2][rows_total][256]
+  float* vt;                  // [2][256][ldv]; key columns: image 0 at [0, n0), image 1 at [vbase1, vbase1 + n1)
+  int ldv;                    // multiple of 4
+  int vbase1;                 // round_up(n0_max, 64)
+};
+int launch_gemm_tc(const GemmArgs& a, const float* w_hi, const float* w_lo, cudaStream_t st,
+                   const QkvPlanes* qkv = nullptr);
+int launch_attention_tc(const QkvPlanes& pl, float* out, int n0_max, int n1_max, const int* n_dev, int cross,
+                        cudaStream_t st);
+static inline int attn_vbase1(int n0_max) { return (n0_max + 63) & ~63; }
+static inline int attn_ldv(int n0_max, int n1_max) { return attn_vbase1(n0_max) + ((n1_max + 63) & ~63); }
 int launch_score_gemm_tc(const float* mdesc, int n0_max, int n1_max, const int* n_dev, float* planes, float* couplings,
                          cudaStream_t st);
 int launch_split_planes(const float* x, float* hi, float* lo, size_t n, cudaStream_t st);

@@ -86,6 +86,12 @@ struct TcArgs {
   int score;                     // 1: Y is the couplings matrix (row-major, ldy = n1_max+1), W rows = image-1 rows
   Segs segs;
   int tiles0;
+  // qkv mode (N = 768): instead of Y the epilogue writes the tf32 planes the attention kernel consumes:
+  //   columns [0,256)   -> Qp [2][rows_total][256]  (hi, lo) of (acc + bias) * 1/8
+  //   columns [256,512) -> Kp [2][rows_total][256]
+  //   columns [512,768) -> Vt [2][256][ldv]          transposed; rows beyond the live count are zero-filled
+  int qkv;
+  float* qp; float* kp; float* vt; int ldv; int rows_total; int vbase1;
 };
 
 template <int BN>
@@ -227,6 +233,43 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
         for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
       }
       int c = c0 + cc * 32;
+      if (g.qkv) {
+        if (c >= ncols) continue;
+        const size_t grow = (size_t)(rbase + r);
+        const bool in_buf = r < g.segs.nmax[seg];              // never touch the other image's rows
+        float x[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + g.bias[c + j];
+        const int part = c >> 8, cc256 = c & 255;
+        if (part < 2) {
+          if (!row_ok) continue;
+          float* hi = (part == 0 ? g.qp : g.kp) + grow * kD + cc256;
+          float* lo = hi + (size_t)g.rows_total * kD;
+          const float sc = part == 0 ? 0.125f : 1.f;              // 1/sqrt(64), exact
+#pragma unroll
+          for (int j = 0; j < 32; j += 4) {
+            float4 h, l;
+            split_tf32(x[j] * sc, h.x, l.x); split_tf32(x[j + 1] * sc, h.y, l.y);
+            split_tf32(x[j + 2] * sc, h.z, l.z); split_tf32(x[j + 3] * sc, h.w, l.w);
+            *reinterpret_cast<float4*>(hi + j) = h;
+            *reinterpret_cast<float4*>(lo + j) = l;
+          }
+        } else if (in_buf) {
+          // key column of this row in Vt: image 1 starts at a 64-aligned column (TMA box starts must be
+          // 16-byte aligned in global memory, so the inner coordinate has to be a multiple of 4 floats)
+          const size_t kcol = (size_t)(seg ? g.vbase1 : 0) + r;
+          float* hi = g.vt + (size_t)cc256 * g.ldv + kcol;       // lanes = consecutive rows: coalesced
+          float* lo = hi + (size_t)kD * g.ldv;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float h, l;
+            split_tf32(row_ok ? x[j] : 0.f, h, l);
+            hi[(size_t)j * g.ldv] = h;
+            lo[(size_t)j * g.ldv] = l;
+          }
+        }
+        continue;
+      }
       if (!row_ok || c >= ncols) continue;
       if (g.score) {
         float* y = g.Y + (size_t)r * g.ldy + c;
@@ -293,7 +336,7 @@ int pick_bn(int n) {
 }  // namespace
 
 // W_hi / W_lo: [N][K] planes produced at pack time (gims_b200/packing.py) — same layout as the fp32 weight.
-int launch_gemm_tc(const GemmArgs& a, const float* w_hi, const float* w_lo, cudaStream_t st) {
+int launch_gemm_tc(const GemmArgs& a, const float* w_hi, const float* w_lo, cudaStream_t st, const QkvPlanes* qkv) {
   int K = a.K0 + a.K1;
   if (a.K0 % BK || a.K1 % BK || K == 0 || a.N % 32 || (a.lda0 % 4) || (a.K1 && (a.lda1 % 4))) {
     set_error("launch_gemm_tc: unsupported shape K0=%d K1=%d N=%d", a.K0, a.K1, a.N);
@@ -310,6 +353,11 @@ int launch_gemm_tc(const GemmArgs& a, const float* w_hi, const float* w_lo, cuda
   TcArgs g;
   g.K0 = a.K0; g.K1 = a.K1; g.bias = a.bias; g.R = a.R; g.ldr = a.ldr; g.Y = a.Y; g.ldy = a.ldy; g.N = a.N;
   g.relu = a.relu; g.scale = 1.f; g.score = 0; g.segs = a.segs;
+  g.qkv = 0; g.qp = g.kp = g.vt = nullptr; g.ldv = 0; g.rows_total = total_rows; g.vbase1 = 0;
+  if (qkv) {
+    if (a.N != 3 * kD || !a.bias) { set_error("launch_gemm_tc: qkv mode needs N = 768 and a bias"); return GIMS_ERR_ARG; }
+    g.qkv = 1; g.qp = qkv->qp; g.kp = qkv->kp; g.vt = qkv->vt; g.ldv = qkv->ldv; g.vbase1 = qkv->vbase1;
+  }
   g.tiles0 = cdiv(a.segs.nmax[0], BM);
   int tiles = g.tiles0 + (a.segs.nseg > 1 ? cdiv(a.segs.nmax[1], BM) : 0);
   if (tiles == 0) return GIMS_OK;
@@ -343,6 +391,7 @@ int launch_score_gemm_tc(const float* mdesc, int n0_max, int n1_max, const int* 
   TcArgs g;
   g.K0 = kD; g.K1 = 0; g.bias = nullptr; g.R = nullptr; g.ldr = 0; g.Y = couplings; g.ldy = n1_max + 1; g.N = n1_max;
   g.relu = 0; g.scale = 0.0625f; g.score = 1;
+  g.qkv = 0; g.qp = g.kp = g.vt = nullptr; g.ldv = 0; g.rows_total = (int)rows; g.vbase1 = 0;
   g.segs.base[0] = 0; g.segs.base[1] = n0_max; g.segs.nmax[0] = n0_max; g.segs.nmax[1] = n1_max; g.segs.n_dev = n_dev;
   g.segs.nseg = 2;
   g.tiles0 = cdiv(n0_max, BM);

@@ -22,11 +22,15 @@ __device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
-// Bounded wait: a lost arrival must trap (and surface as a CUDA error), never hang the GPU.
+// Bounded wait: a lost arrival must never hang the GPU.  On timeout the waiter reports (printf + the
+// device-global flag below, which the host turns into an error) and gives up waiting; every later wait
+// in the grid then falls through at once so that the kernel terminates and the report is flushed.
+static __device__ unsigned g_tc_timeout_flag;
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   uint32_t addr = smem_u32(bar);
   long long t0 = clock64();
   while (true) {
+    if (*(volatile unsigned*)&g_tc_timeout_flag) return;
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
@@ -36,10 +40,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         : "r"(addr), "r"(parity)
         : "memory");
     if (ok) return;
-    if (clock64() - t0 > 4000000000LL) {
-      printf("gims: mbarrier timeout block (%d,%d) thread %d bar %u parity %u\n", blockIdx.x, blockIdx.y, threadIdx.x, addr,
-             parity);
-      __trap();
+    if (clock64() - t0 > 400000000LL) {
+      printf("gims: mbarrier timeout block (%d,%d,%d) thread %d bar@%u parity %u\n", blockIdx.x, blockIdx.y, blockIdx.z,
+             threadIdx.x, addr, parity);
+      atomicExch(&g_tc_timeout_flag, 1u);
+      return;
     }
   }
 }

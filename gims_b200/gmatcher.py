@@ -205,7 +205,7 @@ class GMatcher(nn.Module):
             if len(self._ws) > 16:
                 self._ws.clear()
             nbytes = _lib.lib().gims_pair_workspace_bytes(self._model, n0, n1, edge_cap)
-            ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+            ws = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
             self._ws[key] = ws
         return ws
 

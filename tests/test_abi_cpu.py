@@ -33,7 +33,7 @@ def test_host_queries(lib):
     assert lib.gims_version() >= 100
     assert lib.gims_agc_workspace_bytes(2048, 131072) > 2048 * 2048 * 4
     assert lib.gims_sinkhorn_workspace_bytes(2048, 2048) > 0
-    assert lib.gims_attn_scratch_floats(4096) == 4096 * 256 * 7
+    assert lib.gims_attn_scratch_floats(4096) == 4096 * 256 * 10 + 256 * 256
     from gims_b200 import GMatcher
     m = GMatcher({})
     c = m.c_config()

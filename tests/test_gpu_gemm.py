@@ -68,3 +68,44 @@ def test_tc_gemm(shape):
     e = _run(_lib.GEMM_TC, *shape)
     print('\n[tc gemm %s] rel err %.2e' % (shape[:5], e))
     assert e < 4e-6
+
+
+@pytest.mark.parametrize('n0,n1,layer', [(512, 470, 0), (512, 470, 1), (2048, 2048, 3), (130, 64, 1), (1000, 1337, 0)])
+def test_attention_layer_tc_vs_simt(n0, n1, layer):
+    """One AttentionalPropagation layer (QKV GEMM -> attention -> merge -> MLP, a-11/a-12) through the C ABI:
+    tcgen05 path against the fp32 CUDA-core path and the oracle on the same descriptors, ragged live counts."""
+    from gims_b200 import GMatcher, _lib
+    from gims_b200.synth import make_state_dict
+    from oracle import gims_oracle as orc
+    L = _lib.lib()
+    dev = torch.device('cuda')
+    sd = make_state_dict(7)
+    gm = GMatcher({})
+    gm.load_state_dict(sd)
+    gm = gm.cuda().eval()
+    model = gm.handle()
+    g = torch.Generator().manual_seed(n0 + n1 + layer)
+    live0, live1 = n0 - 5, n1 - 3
+    desc = torch.randn(n0 + n1, 256, generator=g)
+    nd = torch.tensor([live0, live1], dtype=torch.int32, device=dev)
+    scratch = torch.zeros(L.gims_attn_scratch_floats(n0 + n1), device=dev)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    outs = {}
+    for mode in (_lib.GEMM_SIMT, _lib.GEMM_TC):
+        L.gims_set_gemm_mode(mode)
+        d = desc.to(dev).clone()
+        _lib.check(L.gims_attn_layer_forward(model, layer, _lib.ptr(d), n0, n1, _lib.ptr(nd), _lib.ptr(scratch), st), 'attn layer')
+        torch.cuda.synchronize()
+        outs[mode] = d.cpu()
+    L.gims_set_gemm_mode(_lib.GEMM_TC)
+    x0, x1 = desc[:live0].t()[None], desc[n0:n0 + live1].t()[None]
+    cross = layer % 2 == 1
+    with torch.no_grad():
+        d0 = orc.attn_propagation(sd, layer, x0, x1 if cross else x0)
+        d1 = orc.attn_propagation(sd, layer, x1, x0 if cross else x1)
+    want = torch.cat([(x0 + d0)[0].t(), (x1 + d1)[0].t()])
+    for mode, name in ((_lib.GEMM_SIMT, 'simt'), (_lib.GEMM_TC, 'tc')):
+        got = torch.cat([outs[mode][:live0], outs[mode][n0:n0 + live1]])
+        err = ((got - want).abs().max() / want.abs().max()).item()
+        print('\n[attn layer %s n=(%d,%d) layer %d] rel err %.2e' % (name, n0, n1, layer, err))
+        assert err < 5e-6, name
