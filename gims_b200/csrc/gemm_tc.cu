@@ -217,8 +217,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
     const int q = warp & 3;                            // TMEM lane quarter this warp may access
     const int r = r0 + 32 * q + lane;
     const bool row_ok = r < rows;
-#pragma unroll 1
     const int n_main = nkb < Cfg::kMainAcc ? nkb : Cfg::kMainAcc;
+#pragma unroll 1
     for (int cc = 0; cc < BN / 32; ++cc) {
       uint32_t v[32];
       const uint32_t lane_col = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(cc * 32);
