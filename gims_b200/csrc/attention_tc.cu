@@ -28,16 +28,17 @@ using namespace tc;
 constexpr int TQ = 128;        // queries per CTA (UMMA M)
 constexpr int TKV = 64;        // keys per tile (UMMA N of S, K of PV)
 constexpr int HD = 64;         // head dim
-constexpr int kStagesKV = 2;
+constexpr int kStagesKV = 2;   // K and Vt travel through separate 2-stage rings (K is released right after S = QK^T)
 constexpr int kBoxBytesQ = TQ * 32 * 4;       // 16 KB: 128 rows x 32 floats
 constexpr int kBoxBytesKV = TKV * 32 * 4;     // 8 KB: 64 rows x 32 floats
 constexpr int kQBytes = 4 * kBoxBytesQ;       // hi{d0-31,d32-63}, lo{...}
-constexpr int kKVStageBytes = 8 * kBoxBytesKV;  // K hi(2) lo(2), Vt hi(2) lo(2)
-constexpr int kAttnSmem = kQBytes + kStagesKV * kKVStageBytes + 1024 + 256;
+constexpr int kKStageBytes = 4 * kBoxBytesKV;   // K hi(2) lo(2)   (same size for Vt)
+constexpr int kAttnSmem = kQBytes + 2 * kStagesKV * kKStageBytes + 1024 + 256;
 constexpr int kAttnThreads = 192;
 
-// TMEM column offsets
-constexpr int cS = 0, cSc = 64, cPh = 128, cPl = 192, cO = 256, cOc = 320;
+// TMEM column offsets: two S buffers (main + corr each), P planes, PV (main + corr)
+constexpr int cS0 = 0, cPh = 256, cPl = 320, cO = 384, cOc = 448;
+__device__ __forceinline__ constexpr int cS(int buf) { return cS0 + buf * 128; }       // main; corr at +64
 
 struct AttnTcArgs {
   float* out;                 // [rows][256]
@@ -71,6 +72,10 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
       : "memory");
 }
 
+// Pipeline (per 64-key tile j):  QK(j+1) is issued before PV(j), so the tensor core computes the next score tile
+// while the softmax warps work on tile j; the softmax warps fold PV(j-1) into their register accumulators while
+// PV(j) / QK(j+1) run.  S is double-buffered in TMEM, P and PV are single-buffered (their reuse is ordered by
+// p_full / o_full).
 __global__ void __launch_bounds__(kAttnThreads, 1)
 k_attention_tc(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                const __grid_constant__ CUtensorMap mapVt, AttnTcArgs a) {
@@ -86,16 +91,19 @@ k_attention_tc(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* q_smem = smem;
-  uint8_t* kv_smem = smem + kQBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(kv_smem + kStagesKV * kKVStageBytes);
+  uint8_t* k_smem = smem + kQBytes;
+  uint8_t* v_smem = k_smem + kStagesKV * kKStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(v_smem + kStagesKV * kKStageBytes);
   uint64_t* q_full = bars;                 // 1
-  uint64_t* kv_full = bars + 1;            // [2]
-  uint64_t* kv_empty = bars + 3;           // [2]
-  uint64_t* s_full = bars + 5;             // S ready (MMA commit)
-  uint64_t* p_full = bars + 6;             // P written by the softmax warps (4 arrivals)
-  uint64_t* o_full = bars + 7;             // PV ready (MMA commit)
-  uint64_t* o_done = bars + 8;             // PV consumed by the softmax warps (4 arrivals)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 9);
+  uint64_t* k_full = bars + 1;             // [2] TMA -> MMA
+  uint64_t* k_empty = bars + 3;            // [2] QK MMAs retired (tcgen05.commit)
+  uint64_t* v_full = bars + 5;             // [2]
+  uint64_t* v_empty = bars + 7;            // [2] PV MMAs retired
+  uint64_t* s_full = bars + 9;             // [2] S buffer written (commit)
+  uint64_t* s_free = bars + 11;            // [2] S buffer read by the softmax warps (4 arrivals)
+  uint64_t* p_full = bars + 13;            // P written, PV(j-1) folded (4 arrivals)
+  uint64_t* o_full = bars + 14;            // PV written (commit)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -103,11 +111,13 @@ k_attention_tc(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     tma_prefetch_desc(&mapK);
     tma_prefetch_desc(&mapVt);
     mbar_init(q_full, 1);
-    for (int s = 0; s < kStagesKV; ++s) { mbar_init(&kv_full[s], 1); mbar_init(&kv_empty[s], 1); }
-    mbar_init(s_full, 1);
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1);
+      mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
+      mbar_init(&s_full[s], 1); mbar_init(&s_free[s], 4);
+    }
     mbar_init(p_full, 4);
     mbar_init(o_full, 1);
-    mbar_init(o_done, 4);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -123,60 +133,70 @@ k_attention_tc(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
       for (int pl = 0; pl < 2; ++pl)
         for (int hf = 0; hf < 2; ++hf)
           tma_load_2d(q_smem + (pl * 2 + hf) * kBoxBytesQ, &mapQ, q_full, head * HD + hf * 32, pl * a.rows_total + qrow0);
-      int s = 0; uint32_t ph = 0;
       for (int j = 0; j < ntiles; ++j) {
-        mbar_wait(&kv_empty[s], ph ^ 1);
-        uint8_t* st = kv_smem + s * kKVStageBytes;
-        mbar_arrive_expect_tx(&kv_full[s], kKVStageBytes);
-        int key0 = krow0 + j * TKV;                       // row in the K planes
-        int vcol0 = (src ? a.vbase1 : 0) + j * TKV;       // key column in the Vt planes (multiple of 64)
+        const int s = j & 1;
+        const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+        const int key0 = krow0 + j * TKV;                       // row in the K planes
+        const int vcol0 = (src ? a.vbase1 : 0) + j * TKV;       // key column in the Vt planes (multiple of 64)
+        mbar_wait(&k_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&k_full[s], kKStageBytes);
         for (int pl = 0; pl < 2; ++pl)
-          for (int hf = 0; hf < 2; ++hf) {
-            // K box: 64 keys x 32 channels;  Vt box: 64 channels x 32 keys
-            tma_load_2d(st + (pl * 2 + hf) * kBoxBytesKV, &mapK, &kv_full[s], head * HD + hf * 32, pl * a.rows_total + key0);
-            tma_load_2d(st + (4 + pl * 2 + hf) * kBoxBytesKV, &mapVt, &kv_full[s], vcol0 + hf * 32, pl * kD + head * HD);
-          }
-        if (++s == kStagesKV) { s = 0; ph ^= 1; }
+          for (int hf = 0; hf < 2; ++hf)      // K box: 64 keys x 32 channels
+            tma_load_2d(k_smem + s * kKStageBytes + (pl * 2 + hf) * kBoxBytesKV, &mapK, &k_full[s], head * HD + hf * 32,
+                        pl * a.rows_total + key0);
+        mbar_wait(&v_empty[s], ph ^ 1);
+        mbar_arrive_expect_tx(&v_full[s], kKStageBytes);
+        for (int pl = 0; pl < 2; ++pl)
+          for (int hf = 0; hf < 2; ++hf)      // Vt box: 64 channels x 32 keys
+            tma_load_2d(v_smem + s * kKStageBytes + (pl * 2 + hf) * kBoxBytesKV, &mapVt, &v_full[s], vcol0 + hf * 32,
+                        pl * kD + head * HD);
       }
     }
   } else if (warp == 1) {
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_tf32(TQ, TKV);      // M=128, N=64 for both S and PV
-      mbar_wait(q_full, 0);
       const uint32_t qh = smem_u32(q_smem), ql = qh + 2 * kBoxBytesQ;
-      int s = 0; uint32_t ph = 0;
-      for (int j = 0; j < ntiles; ++j) {
-        mbar_wait(&kv_full[s], ph);
-        if (j > 0) mbar_wait(o_done, (j - 1) & 1);             // softmax warps are done with S / P / PV of tile j-1
+      auto issue_qk = [&](int j) {
+        const int s = j & 1;
+        const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+        mbar_wait(&k_full[s], ph);
+        if (j >= 2) mbar_wait(&s_free[s], ph ^ 1);             // softmax warps have read S(j-2) out of this buffer
         tcgen05_fence_after();
-        const uint32_t kh = smem_u32(kv_smem + s * kKVStageBytes), kl = kh + 2 * kBoxBytesKV;
-        const uint32_t vh = kh + 4 * kBoxBytesKV, vl = kh + 6 * kBoxBytesKV;
-        // S = Q K^T : K-dim = 64 channels = 2 boxes x 4 k-steps
+        const uint32_t kh = smem_u32(k_smem + s * kKStageBytes), kl = kh + 2 * kBoxBytesKV;
+        const uint32_t sm = tmem + cS(s), sc = sm + 64;
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
+        for (int ks = 0; ks < 8; ++ks) {                       // K-dim = 64 channels = 2 boxes x 4 k-steps
           uint32_t qoff = (ks >> 2) * kBoxBytesQ + (ks & 3) * 32;
           uint32_t koff = (ks >> 2) * kBoxBytesKV + (ks & 3) * 32;
           uint64_t dqh = umma_desc_sw128(qh + qoff), dql = umma_desc_sw128(ql + qoff);
           uint64_t dkh = umma_desc_sw128(kh + koff), dkl = umma_desc_sw128(kl + koff);
-          umma_tf32_ss(tmem + cSc, dql, dkh, idesc, ks ? 1u : 0u);
-          umma_tf32_ss(tmem + cSc, dqh, dkl, idesc, 1u);
-          umma_tf32_ss(tmem + cS, dqh, dkh, idesc, ks ? 1u : 0u);
+          umma_tf32_ss(sc, dql, dkh, idesc, ks ? 1u : 0u);
+          umma_tf32_ss(sc, dqh, dkl, idesc, 1u);
+          umma_tf32_ss(sm, dqh, dkh, idesc, ks ? 1u : 0u);
         }
-        umma_commit(s_full);
-        // PV = P V : K-dim = 64 keys = 2 Vt boxes x 4 k-steps; A (P planes) from TMEM, 8 columns per k-step
-        mbar_wait(p_full, j & 1);
+        umma_commit(&k_empty[s]);
+        umma_commit(&s_full[s]);
+      };
+      mbar_wait(q_full, 0);
+      issue_qk(0);
+      for (int j = 0; j < ntiles; ++j) {
+        if (j + 1 < ntiles) issue_qk(j + 1);
+        const int s = j & 1;
+        const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+        mbar_wait(&v_full[s], ph);
+        mbar_wait(p_full, j & 1);                              // P(j) in TMEM, PV(j-1) already folded away
         tcgen05_fence_after();
+        const uint32_t vh = smem_u32(v_smem + s * kKStageBytes), vl = vh + 2 * kBoxBytesKV;
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
+        for (int ks = 0; ks < 8; ++ks) {                       // K-dim = 64 keys = 2 Vt boxes x 4 k-steps; A from TMEM
           uint32_t voff = (ks >> 2) * kBoxBytesKV + (ks & 3) * 32;
           uint64_t dvh = umma_desc_sw128(vh + voff), dvl = umma_desc_sw128(vl + voff);
           umma_tf32_ts(tmem + cOc, tmem + cPl + ks * 8, dvh, idesc, ks ? 1u : 0u);
           umma_tf32_ts(tmem + cOc, tmem + cPh + ks * 8, dvl, idesc, 1u);
           umma_tf32_ts(tmem + cO, tmem + cPh + ks * 8, dvh, idesc, ks ? 1u : 0u);
         }
-        umma_commit(&kv_empty[s]);
+        umma_commit(&v_empty[s]);
         umma_commit(o_full);
-        if (++s == kStagesKV) { s = 0; ph ^= 1; }
       }
     }
   } else {
@@ -187,21 +207,37 @@ k_attention_tc(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     float o[HD];
 #pragma unroll
     for (int d = 0; d < HD; ++d) o[d] = 0.f;
-    float m_run = -CUDART_INF_F, l_run = 0.f;
+    float m_run = -CUDART_INF_F, l_run = 0.f, alpha_prev = 0.f;
     const float kLog2e = 1.4426950408889634f;
+    auto fold_pv = [&](float alpha) {                          // O = O * alpha + PV
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        uint32_t v[32], c[32];
+        tmem_ld_32x32(lane_base + cO + h * 32, v);
+        tmem_ld_32x32(lane_base + cOc + h * 32, c);
+        tmem_ld_wait();
+#pragma unroll
+        for (int i = 0; i < 32; ++i)
+          o[h * 32 + i] = fmaf(o[h * 32 + i], alpha, __uint_as_float(v[i]) + __uint_as_float(c[i]));
+      }
+    };
     for (int j = 0; j < ntiles; ++j) {
-      mbar_wait(s_full, j & 1);
+      const int sb = j & 1;
+      mbar_wait(&s_full[sb], (uint32_t)(j >> 1) & 1u);
       tcgen05_fence_after();
       float s[TKV];
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         uint32_t v[32], c[32];
-        tmem_ld_32x32(lane_base + cS + h * 32, v);
-        tmem_ld_32x32(lane_base + cSc + h * 32, c);
+        tmem_ld_32x32(lane_base + cS(sb) + h * 32, v);
+        tmem_ld_32x32(lane_base + cS(sb) + 64 + h * 32, c);
         tmem_ld_wait();
 #pragma unroll
         for (int i = 0; i < 32; ++i) s[h * 32 + i] = (__uint_as_float(v[i]) + __uint_as_float(c[i])) * kLog2e;
       }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&s_free[sb]);           // the tensor core may overwrite this S buffer (tile j+2)
       const int valid = nk - j * TKV;                    // keys of this tile that exist
       float mx = -CUDART_INF_F;
 #pragma unroll
@@ -213,14 +249,22 @@ k_attention_tc(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
       const float alpha = exp2f(m_run - m_new);
       float rs = 0.f;
 #pragma unroll
+      for (int i = 0; i < TKV; ++i) { s[i] = exp2f(s[i] - m_new); rs += s[i]; }
+      l_run = l_run * alpha + rs;
+      m_run = m_new;
+      if (j > 0) {                                       // PV(j-1) has to be out of TMEM before P(j) goes in
+        mbar_wait(o_full, (j - 1) & 1);
+        tcgen05_fence_after();
+        fold_pv(alpha_prev);
+      }
+      alpha_prev = alpha;
+#pragma unroll
       for (int h = 0; h < 2; ++h) {
         uint32_t ph_[32], pl_[32];
 #pragma unroll
         for (int i = 0; i < 32; ++i) {
-          float p = exp2f(s[h * 32 + i] - m_new);
-          rs += p;
           float hi, lo;
-          split_tf32(p, hi, lo);
+          split_tf32(s[h * 32 + i], hi, lo);
           ph_[i] = __float_as_uint(hi);
           pl_[i] = __float_as_uint(lo);
         }
@@ -231,24 +275,10 @@ k_attention_tc(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(p_full);
-      l_run = l_run * alpha + rs;
-      m_run = m_new;
-      mbar_wait(o_full, j & 1);
-      tcgen05_fence_after();
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t v[32], c[32];
-        tmem_ld_32x32(lane_base + cO + h * 32, v);
-        tmem_ld_32x32(lane_base + cOc + h * 32, c);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i)
-          o[h * 32 + i] = fmaf(o[h * 32 + i], alpha, __uint_as_float(v[i]) + __uint_as_float(c[i]));
-      }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(o_done);
     }
+    mbar_wait(o_full, (ntiles - 1) & 1);
+    tcgen05_fence_after();
+    fold_pv(alpha_prev);
     if (row < nq) {
       const float inv = 1.f / l_run;
       float4* dst = reinterpret_cast<float4*>(a.out + (size_t)(a.segs.base[img] + row) * kD + head * HD);
