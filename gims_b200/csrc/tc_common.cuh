@@ -26,27 +26,37 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t by
 // device-global flag below, which the host turns into an error) and gives up waiting; every later wait
 // in the grid then falls through at once so that the kernel terminates and the report is flushed.
 static __device__ unsigned g_tc_timeout_flag;
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t addr = smem_u32(bar);
+__device__ __forceinline__ bool mbar_try_wait(uint32_t addr, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(addr), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+static __device__ __noinline__ void mbar_wait_slow(uint32_t addr, uint32_t parity) {
   long long t0 = clock64();
-  while (true) {
-    if (*(volatile unsigned*)&g_tc_timeout_flag) return;
-    uint32_t ok;
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-        "selp.u32 %0, 1, 0, p;\n\t}"
-        : "=r"(ok)
-        : "r"(addr), "r"(parity)
-        : "memory");
-    if (ok) return;
-    if (clock64() - t0 > 400000000LL) {
-      printf("gims: mbarrier timeout block (%d,%d,%d) thread %d bar@%u parity %u\n", blockIdx.x, blockIdx.y, blockIdx.z,
-             threadIdx.x, addr, parity);
-      atomicExch(&g_tc_timeout_flag, 1u);
-      return;
+  unsigned spins = 0;
+  while (!mbar_try_wait(addr, parity)) {
+    if ((++spins & 63u) == 0) {
+      if (*(volatile unsigned*)&g_tc_timeout_flag) return;
+      if (clock64() - t0 > 400000000LL) {
+        printf("gims: mbarrier timeout block (%d,%d,%d) thread %d bar@%u parity %u\n", blockIdx.x, blockIdx.y, blockIdx.z,
+               threadIdx.x, addr, parity);
+        atomicExch(&g_tc_timeout_flag, 1u);
+        return;
+      }
     }
   }
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t addr = smem_u32(bar);
+  if (mbar_try_wait(addr, parity)) return;     // fast path: no global traffic, no timers
+  if (mbar_try_wait(addr, parity)) return;
+  mbar_wait_slow(addr, parity);
 }
 
 // ---- proxies / fences ---------------------------------------------------------------------------
