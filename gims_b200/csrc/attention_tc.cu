@@ -4,7 +4,7 @@
 // head_dim 64:  out = softmax(q^T k / 8) v  per head, without materialising the (4, N, M) probabilities.
 //
 // Operands arrive as tf32 planes written by the QKV projection epilogue (gemm_tc.cu, qkv mode):
-//   Qp [2][rows][256]   hi / lo planes of q * 1/8 (exact scaling), head-major channels h*64+d
+//   Qp [2][rows][256]   hi / lo planes of q * log2(e)/8 (scores land in the log2 domain), channels h*64+d
 //   Kp [2][rows][256]   hi / lo planes of k
 //   Vt [2][256][ldv]    hi / lo planes of v, TRANSPOSED (channel-major) so that PV's B operand is K-major
 // One CTA = 128 queries of one head of one image; 192 threads:
@@ -12,8 +12,6 @@
 //   warp 1      one thread issues tcgen05.mma:  S = Q K^T (SS, 3 products),  PV = P V (TS: P read from TMEM)
 //   warps 2..5  softmax: tcgen05.ld S -> online max / exp2 / sum in fp32 -> P split into tf32 hi / lo ->
 //               tcgen05.st into TMEM -> after the PV MMAs: O = O * alpha + PV in registers (fp32, RN)
-// TMEM columns: S_main 64 | S_corr 64 | P_hi 64 | P_lo 64 | PV_main 64 | PV_corr 64  (corr = the two small
-// 3xTF32 products, kept apart because the tensor core rounds its accumulator toward zero).
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -36,9 +34,24 @@ constexpr int kKStageBytes = 4 * kBoxBytesKV;   // K hi(2) lo(2)   (same size fo
 constexpr int kAttnSmem = kQBytes + 2 * kStagesKV * kKStageBytes + 1024 + 256;
 constexpr int kAttnThreads = 192;
 
-// TMEM column offsets: two S buffers (main + corr each), P planes, PV (main + corr)
-constexpr int cS0 = 0, cPh = 256, cPl = 320, cO = 384, cOc = 448;
-__device__ __forceinline__ constexpr int cS(int buf) { return cS0 + buf * 128; }       // main; corr at +64
+// TMEM columns (all 512 in use): S[2] 64 each | P[2] = (hi 64 | lo 64) each | PV[2] 64 each.
+// Each S / PV accumulator receives the 16 small correction products of its tile FIRST and the 8 hi*hi products
+// last: the tensor core rounds the accumulator toward zero at every step, and this order keeps those roundings at
+// the magnitude of the small terms for as long as possible (same error as a separate correction accumulator,
+// without its TMEM columns and the extra add).
+__device__ __forceinline__ constexpr int cS(int b) { return b * 64; }
+__device__ __forceinline__ constexpr int cPh(int b) { return 128 + b * 128; }
+__device__ __forceinline__ constexpr int cPl(int b) { return 192 + b * 128; }
+__device__ __forceinline__ constexpr int cO(int b) { return 384 + b * 64; }
+
+// Optional pipeline trace (bring-up / profiling): CTA (0,0,0) stores clock64() stamps per tile.
+//   [j*8+0] MMA: QK(j+1) issue start   [j*8+1] MMA: PV(j) operands ready   [j*8+2] MMA: PV(j) issued
+//   [j*8+4] softmax warp 2: S(j) observed   [j*8+5] P(j) handed over   [j*8+6] fold of PV(j-1) done
+__device__ long long* g_attn_trace = nullptr;
+#define ATTN_TRACE(slot)                                                                       \
+  do {                                                                                         \
+    if (trace) trace[j * 8 + (slot)] = clock64();                                              \
+  } while (0)
 
 struct AttnTcArgs {
   float* out;                 // [rows][256]
@@ -71,11 +84,16 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
       "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// 2^x for x <= 0 (softmax arguments): one MUFU, flushes results below 2^-126 to zero
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 
 // Pipeline (per 64-key tile j):  QK(j+1) is issued before PV(j), so the tensor core computes the next score tile
-// while the softmax warps work on tile j; the softmax warps fold PV(j-1) into their register accumulators while
-// PV(j) / QK(j+1) run.  S is double-buffered in TMEM, P and PV are single-buffered (their reuse is ordered by
-// p_full / o_full).
+// while the softmax warps work on tile j; the softmax warps fold PV(j-1) into their register accumulators after
+// they have handed P(j) to the tensor core.  S, P and PV are all double-buffered in TMEM.
 __global__ void __launch_bounds__(kAttnThreads, 1)
 k_attention_tc(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
                const __grid_constant__ CUtensorMap mapVt, AttnTcArgs a) {
@@ -101,9 +119,10 @@ k_attention_tc(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
   uint64_t* v_empty = bars + 7;            // [2] PV MMAs retired
   uint64_t* s_full = bars + 9;             // [2] S buffer written (commit)
   uint64_t* s_free = bars + 11;            // [2] S buffer read by the softmax warps (4 arrivals)
-  uint64_t* p_full = bars + 13;            // P written, PV(j-1) folded (4 arrivals)
-  uint64_t* o_full = bars + 14;            // PV written (commit)
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 15);
+  uint64_t* p_full = bars + 13;            // [2] P buffer written by the softmax warps (4 arrivals)
+  uint64_t* o_full = bars + 15;            // [2] PV buffer written (commit); also: P buffer consumed
+  uint64_t* o_free = bars + 17;            // [2] PV buffer folded by the softmax warps (4 arrivals)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -115,9 +134,8 @@ k_attention_tc(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
       mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1);
       mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
       mbar_init(&s_full[s], 1); mbar_init(&s_free[s], 4);
+      mbar_init(&p_full[s], 4); mbar_init(&o_full[s], 1); mbar_init(&o_free[s], 4);
     }
-    mbar_init(p_full, 4);
-    mbar_init(o_full, 1);
     fence_barrier_init();
   }
   if (warp == 1) tmem_alloc<512>(tmem_slot);
@@ -156,47 +174,69 @@ k_attention_tc(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_tf32(TQ, TKV);      // M=128, N=64 for both S and PV
       const uint32_t qh = smem_u32(q_smem), ql = qh + 2 * kBoxBytesQ;
+      // Descriptors are built once; inside the loops an operand advance is one 64-bit add of (bytes >> 4) —
+      // the single issuing thread must not spend its time on descriptor arithmetic.
+      const uint64_t dq_hi = umma_desc_sw128(qh), dq_lo = umma_desc_sw128(ql);
+      uint64_t dk_hi[2], dk_lo[2], dv_hi[2], dv_lo[2];
+#pragma unroll
+      for (int s = 0; s < 2; ++s) {
+        const uint32_t kb = smem_u32(k_smem + s * kKStageBytes), vb = smem_u32(v_smem + s * kKStageBytes);
+        dk_hi[s] = umma_desc_sw128(kb); dk_lo[s] = umma_desc_sw128(kb + 2 * kBoxBytesKV);
+        dv_hi[s] = umma_desc_sw128(vb); dv_lo[s] = umma_desc_sw128(vb + 2 * kBoxBytesKV);
+      }
       auto issue_qk = [&](int j) {
         const int s = j & 1;
         const uint32_t ph = (uint32_t)(j >> 1) & 1u;
         mbar_wait(&k_full[s], ph);
         if (j >= 2) mbar_wait(&s_free[s], ph ^ 1);             // softmax warps have read S(j-2) out of this buffer
         tcgen05_fence_after();
-        const uint32_t kh = smem_u32(k_smem + s * kKStageBytes), kl = kh + 2 * kBoxBytesKV;
-        const uint32_t sm = tmem + cS(s), sc = sm + 64;
+        const uint64_t kh = dk_hi[s], kl = dk_lo[s];
+        const uint32_t sacc = tmem + cS(s);
+        // K-dim = 64 channels = 2 boxes x 4 k-steps; corrections first, hi*hi last
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {                       // K-dim = 64 channels = 2 boxes x 4 k-steps
-          uint32_t qoff = (ks >> 2) * kBoxBytesQ + (ks & 3) * 32;
-          uint32_t koff = (ks >> 2) * kBoxBytesKV + (ks & 3) * 32;
-          uint64_t dqh = umma_desc_sw128(qh + qoff), dql = umma_desc_sw128(ql + qoff);
-          uint64_t dkh = umma_desc_sw128(kh + koff), dkl = umma_desc_sw128(kl + koff);
-          umma_tf32_ss(sc, dql, dkh, idesc, ks ? 1u : 0u);
-          umma_tf32_ss(sc, dqh, dkl, idesc, 1u);
-          umma_tf32_ss(sm, dqh, dkh, idesc, ks ? 1u : 0u);
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t qoff = ((ks >> 2) * kBoxBytesQ + (ks & 3) * 32) >> 4, koff = ((ks >> 2) * kBoxBytesKV + (ks & 3) * 32) >> 4;
+          umma_tf32_ss(sacc, dq_lo + qoff, kh + koff, idesc, ks ? 1u : 0u);
+          umma_tf32_ss(sacc, dq_hi + qoff, kl + koff, idesc, 1u);
+        }
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t qoff = ((ks >> 2) * kBoxBytesQ + (ks & 3) * 32) >> 4, koff = ((ks >> 2) * kBoxBytesKV + (ks & 3) * 32) >> 4;
+          umma_tf32_ss(sacc, dq_hi + qoff, kh + koff, idesc, 1u);
         }
         umma_commit(&k_empty[s]);
         umma_commit(&s_full[s]);
       };
+      long long* trace = (blockIdx.x | blockIdx.y | blockIdx.z) == 0 ? g_attn_trace : nullptr;
       mbar_wait(q_full, 0);
       issue_qk(0);
       for (int j = 0; j < ntiles; ++j) {
+        ATTN_TRACE(0);
         if (j + 1 < ntiles) issue_qk(j + 1);
         const int s = j & 1;
         const uint32_t ph = (uint32_t)(j >> 1) & 1u;
         mbar_wait(&v_full[s], ph);
-        mbar_wait(p_full, j & 1);                              // P(j) in TMEM, PV(j-1) already folded away
+        mbar_wait(&p_full[s], ph);                             // P(j) is in TMEM
+        if (j >= 2) mbar_wait(&o_free[s], ph ^ 1);             // PV(j-2) has been folded out of this buffer
         tcgen05_fence_after();
-        const uint32_t vh = smem_u32(v_smem + s * kKStageBytes), vl = vh + 2 * kBoxBytesKV;
+        ATTN_TRACE(1);
+        const uint64_t vh = dv_hi[s], vl = dv_lo[s];
+        const uint32_t oacc = tmem + cO(s), p_hi = tmem + cPh(s), p_lo = tmem + cPl(s);
+        // K-dim = 64 keys = 2 Vt boxes x 4 k-steps; A (P planes) from TMEM, 8 columns per k-step
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {                       // K-dim = 64 keys = 2 Vt boxes x 4 k-steps; A from TMEM
-          uint32_t voff = (ks >> 2) * kBoxBytesKV + (ks & 3) * 32;
-          uint64_t dvh = umma_desc_sw128(vh + voff), dvl = umma_desc_sw128(vl + voff);
-          umma_tf32_ts(tmem + cOc, tmem + cPl + ks * 8, dvh, idesc, ks ? 1u : 0u);
-          umma_tf32_ts(tmem + cOc, tmem + cPh + ks * 8, dvl, idesc, 1u);
-          umma_tf32_ts(tmem + cO, tmem + cPh + ks * 8, dvh, idesc, ks ? 1u : 0u);
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t voff = ((ks >> 2) * kBoxBytesKV + (ks & 3) * 32) >> 4;
+          umma_tf32_ts(oacc, p_lo + ks * 8, vh + voff, idesc, ks ? 1u : 0u);
+          umma_tf32_ts(oacc, p_hi + ks * 8, vl + voff, idesc, 1u);
+        }
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) {
+          const uint64_t voff = ((ks >> 2) * kBoxBytesKV + (ks & 3) * 32) >> 4;
+          umma_tf32_ts(oacc, p_hi + ks * 8, vh + voff, idesc, 1u);
         }
         umma_commit(&v_empty[s]);
-        umma_commit(o_full);
+        umma_commit(&o_full[s]);
+        ATTN_TRACE(2);
       }
     }
   } else {
@@ -208,56 +248,63 @@ k_attention_tc(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
 #pragma unroll
     for (int d = 0; d < HD; ++d) o[d] = 0.f;
     float m_run = -CUDART_INF_F, l_run = 0.f, alpha_prev = 0.f;
-    const float kLog2e = 1.4426950408889634f;
-    auto fold_pv = [&](float alpha) {                          // O = O * alpha + PV
+    auto fold_pv = [&](int jj, float alpha) {                  // O = O * alpha + PV(jj)
+      const int b = jj & 1;
+      mbar_wait(&o_full[b], (uint32_t)(jj >> 1) & 1u);
+      tcgen05_fence_after();
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        uint32_t v[32], c[32];
-        tmem_ld_32x32(lane_base + cO + h * 32, v);
-        tmem_ld_32x32(lane_base + cOc + h * 32, c);
+        uint32_t v[32];
+        tmem_ld_32x32(lane_base + cO(b) + h * 32, v);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i)
-          o[h * 32 + i] = fmaf(o[h * 32 + i], alpha, __uint_as_float(v[i]) + __uint_as_float(c[i]));
+        for (int i = 0; i < 32; ++i) o[h * 32 + i] = fmaf(o[h * 32 + i], alpha, __uint_as_float(v[i]));
       }
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&o_free[b]);
     };
+    long long* trace = ((blockIdx.x | blockIdx.y | blockIdx.z) == 0 && threadIdx.x == 64) ? g_attn_trace : nullptr;
     for (int j = 0; j < ntiles; ++j) {
       const int sb = j & 1;
-      mbar_wait(&s_full[sb], (uint32_t)(j >> 1) & 1u);
+      const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+      mbar_wait(&s_full[sb], ph);
       tcgen05_fence_after();
-      float s[TKV];
+      ATTN_TRACE(4);
+      float s[TKV];                                      // scores in the log2 domain (Q was scaled by log2(e)/8)
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
-        uint32_t v[32], c[32];
+        uint32_t v[32];
         tmem_ld_32x32(lane_base + cS(sb) + h * 32, v);
-        tmem_ld_32x32(lane_base + cS(sb) + 64 + h * 32, c);
         tmem_ld_wait();
 #pragma unroll
-        for (int i = 0; i < 32; ++i) s[h * 32 + i] = (__uint_as_float(v[i]) + __uint_as_float(c[i])) * kLog2e;
+        for (int i = 0; i < 32; ++i) s[h * 32 + i] = __uint_as_float(v[i]);
       }
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&s_free[sb]);           // the tensor core may overwrite this S buffer (tile j+2)
       const int valid = nk - j * TKV;                    // keys of this tile that exist
-      float mx = -CUDART_INF_F;
+      if (valid < TKV) {
 #pragma unroll
-      for (int i = 0; i < TKV; ++i) {
-        if (i >= valid) s[i] = -CUDART_INF_F;
-        mx = fmaxf(mx, s[i]);
+        for (int i = 0; i < TKV; ++i)
+          if (i >= valid) s[i] = -CUDART_INF_F;
       }
+      float mx = s[0];
+#pragma unroll
+      for (int i = 1; i < TKV; ++i) mx = fmaxf(mx, s[i]);
       const float m_new = fmaxf(m_run, mx);
-      const float alpha = exp2f(m_run - m_new);
-      float rs = 0.f;
+      const float alpha = ex2_approx(m_run - m_new);
+      float rs0 = 0.f, rs1 = 0.f;
 #pragma unroll
-      for (int i = 0; i < TKV; ++i) { s[i] = exp2f(s[i] - m_new); rs += s[i]; }
-      l_run = l_run * alpha + rs;
-      m_run = m_new;
-      if (j > 0) {                                       // PV(j-1) has to be out of TMEM before P(j) goes in
-        mbar_wait(o_full, (j - 1) & 1);
-        tcgen05_fence_after();
-        fold_pv(alpha_prev);
+      for (int i = 0; i < TKV; i += 2) {
+        s[i] = ex2_approx(s[i] - m_new);
+        s[i + 1] = ex2_approx(s[i + 1] - m_new);
+        rs0 += s[i];
+        rs1 += s[i + 1];
       }
-      alpha_prev = alpha;
+      l_run = l_run * alpha + (rs0 + rs1);
+      m_run = m_new;
+      // P(j) -> TMEM buffer sb; that buffer was last read by PV(j-2), whose completion we observed when folding it
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
         uint32_t ph_[32], pl_[32];
@@ -268,17 +315,19 @@ k_attention_tc(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
           ph_[i] = __float_as_uint(hi);
           pl_[i] = __float_as_uint(lo);
         }
-        tmem_st_32x32(lane_base + cPh + h * 32, ph_);
-        tmem_st_32x32(lane_base + cPl + h * 32, pl_);
+        tmem_st_32x32(lane_base + cPh(sb) + h * 32, ph_);
+        tmem_st_32x32(lane_base + cPl(sb) + h * 32, pl_);
       }
       tmem_st_wait();
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(p_full);
+      if (lane == 0) mbar_arrive(&p_full[sb]);
+      ATTN_TRACE(5);
+      if (j > 0) fold_pv(j - 1, alpha_prev);             // overlaps PV(j) / QK(j+1) on the tensor core
+      ATTN_TRACE(6);
+      alpha_prev = alpha;
     }
-    mbar_wait(o_full, (ntiles - 1) & 1);
-    tcgen05_fence_after();
-    fold_pv(alpha_prev);
+    fold_pv(ntiles - 1, alpha_prev);
     if (row < nq) {
       const float inv = 1.f / l_run;
       float4* dst = reinterpret_cast<float4*>(a.out + (size_t)(a.segs.base[img] + row) * kD + head * HD);
@@ -297,6 +346,11 @@ k_attention_tc(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
 }  // namespace
 
 // planes as written by the qkv-mode GEMM epilogue (QkvPlanes, common.cuh)
+int set_attention_trace(long long* dev_buf) {
+  GIMS_CUDA_OK(cudaMemcpyToSymbol(g_attn_trace, &dev_buf, sizeof(dev_buf)));
+  return GIMS_OK;
+}
+
 int launch_attention_tc(const QkvPlanes& pl, float* out, int n0_max, int n1_max, const int* n_dev, int cross,
                         cudaStream_t st) {
   int rows = n0_max + n1_max;

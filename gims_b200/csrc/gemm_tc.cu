@@ -87,7 +87,7 @@ struct TcArgs {
   Segs segs;
   int tiles0;
   // qkv mode (N = 768): instead of Y the epilogue writes the tf32 planes the attention kernel consumes:
-  //   columns [0,256)   -> Qp [2][rows_total][256]  (hi, lo) of (acc + bias) * 1/8
+  //   columns [0,256)   -> Qp [2][rows_total][256]  (hi, lo) of (acc + bias) * log2(e)/8
   //   columns [256,512) -> Kp [2][rows_total][256]
   //   columns [512,768) -> Vt [2][256][ldv]          transposed; rows beyond the live count are zero-filled
   int qkv;
@@ -164,20 +164,21 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
     // ===== MMA issuer =====
     if (lane == 0) {
       constexpr uint32_t idesc = umma_idesc_tf32(BM, BN);
+      // one descriptor per stage, built once: inside the loop an operand advance is a single 64-bit add
+      const uint64_t d_stage0 = umma_desc_sw128(smem_u32(stage_ptr(0)));
       int s = 0; uint32_t ph = 0;
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&full[s], ph);
         mbar_wait(&conv[s], ph);
         tcgen05_fence_after();
-        uint32_t a_hi = smem_u32(stage_ptr(s));
-        uint32_t a_lo = a_hi + Cfg::kABytes;
-        uint32_t w_hi = a_hi + 2 * Cfg::kABytes;
-        uint32_t w_lo = w_hi + Cfg::kWBytes;
+        const uint64_t a_hi = d_stage0 + (uint64_t)((s * Cfg::kStageBytes) >> 4);
+        const uint64_t a_lo = a_hi + (Cfg::kABytes >> 4);
+        const uint64_t w_hi = a_hi + ((2 * Cfg::kABytes) >> 4);
+        const uint64_t w_lo = w_hi + (Cfg::kWBytes >> 4);
 #pragma unroll
         for (int ks = 0; ks < BK / 8; ++ks) {
-          uint32_t koff = ks * 32;                    // 8 tf32 = 32 bytes inside the 128-B swizzle row
-          uint64_t dah = umma_desc_sw128(a_hi + koff), dal = umma_desc_sw128(a_lo + koff);
-          uint64_t dwh = umma_desc_sw128(w_hi + koff), dwl = umma_desc_sw128(w_lo + koff);
+          const uint64_t koff = (ks * 32) >> 4;       // 8 tf32 = 32 bytes inside the 128-B swizzle row
+          const uint64_t dah = a_hi + koff, dal = a_lo + koff, dwh = w_hi + koff, dwl = w_lo + koff;
           const uint32_t corr = tmem_base + Cfg::kMainAcc * BN;
           const uint32_t main_acc = tmem_base + (kb % Cfg::kMainAcc) * BN;
           umma_tf32_ss(corr, dal, dwh, idesc, (kb | ks) ? 1u : 0u);
@@ -245,7 +246,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
           if (!row_ok) continue;
           float* hi = (part == 0 ? g.qp : g.kp) + grow * kD + cc256;
           float* lo = hi + (size_t)g.rows_total * kD;
-          const float sc = part == 0 ? 0.125f : 1.f;              // 1/sqrt(64), exact
+          const float sc = part == 0 ? 0.18033688011112042f : 1.f;   // log2(e)/sqrt(64): scores in the log2 domain
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             float4 h, l;

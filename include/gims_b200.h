@@ -84,6 +84,9 @@ GIMS_API int gims_linear(const float* A0, int lda0, int K0, const float* A1, int
                 const float* W_hi, const float* W_lo, const float* bias, const float* R, int ldr, float* Y, int ldy,
                 int N, int relu, int rows_max, const int* rows_dev, int mode, void* stream);
 GIMS_API int gims_split_tf32(const float* x, float* hi, float* lo, size_t n, void* stream);
+/* Profiling aid: CTA (0,0,0) of every following attention launch stores clock64() stamps of its pipeline
+ * (8 int64 per 64-key tile, see attention_tc.cu) into dev_buf; pass NULL to switch the trace off. */
+GIMS_API int gims_debug_attention_trace(long long* dev_buf);
 
 /* ---- profiling hooks (bench.py roofline): CUDA-event timing of ONE kernel class, recorded on the
  * stream each launch goes to.  begin() arms it for at most max_launches launches; end() waits for

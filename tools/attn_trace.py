@@ -1,0 +1,34 @@
+"""Dump the pipeline timeline of one attention CTA (gims_debug_attention_trace) for a 2048x2048 layer."""
+import ctypes as C
+import sys, os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from gims_b200 import GMatcher, _lib
+from gims_b200.synth import make_state_dict
+
+L = _lib.lib()
+dev = torch.device('cuda')
+gm = GMatcher({}); gm.load_state_dict(make_state_dict(7)); gm = gm.cuda().eval()
+model = gm.handle()
+n0 = n1 = 2048
+desc = torch.randn(n0 + n1, 256, device=dev)
+nd = torch.tensor([n0, n1], dtype=torch.int32, device=dev)
+scratch = torch.zeros(L.gims_attn_scratch_floats(n0 + n1), device=dev)
+st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+trace = torch.zeros(64 * 8, dtype=torch.int64, device=dev)
+for it in range(3):
+    _lib.check(L.gims_attn_layer_forward(model, 0, _lib.ptr(desc), n0, n1, _lib.ptr(nd), _lib.ptr(scratch), st), 'warm')
+torch.cuda.synchronize()
+L.gims_debug_attention_trace(C.c_void_p(trace.data_ptr()))
+_lib.check(L.gims_attn_layer_forward(model, 0, _lib.ptr(desc), n0, n1, _lib.ptr(nd), _lib.ptr(scratch), st), 'trace')
+torch.cuda.synchronize()
+L.gims_debug_attention_trace(None)
+t = trace.cpu().view(64, 8)
+t0 = int(t[0, 0])
+print('tile  qk_issue  pv_ready  pv_issued | s_seen  p_given  fold_done   (cycles since first stamp; deltas to previous tile)')
+prev = None
+for j in range(32):
+    r = [int(x) - t0 if int(x) else -1 for x in t[j]]
+    d = '' if prev is None else '  d_pv_issued=%d d_p_given=%d' % (r[2] - prev[2], r[5] - prev[5])
+    print('%3d  %8d %8d %8d | %8d %8d %8d%s' % (j, r[0], r[1], r[2], r[4], r[5], r[6], d))
+    prev = r
