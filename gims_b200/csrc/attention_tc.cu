@@ -100,7 +100,10 @@ k_attention_tc(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
   extern __shared__ uint8_t smem_raw[];
   const int img = blockIdx.z, head = blockIdx.y;
   const int src = a.cross ? 1 - img : img;
-  const int nq = seg_count(a.segs, img), nk = seg_count(a.segs, src);
+  // counts come from device memory; the shuffle makes them provably warp-uniform for the compiler, so that the
+  // single-thread TMA / MMA loops below compile to uniform-datapath code (no per-operand R2UR moves)
+  const int nq = __shfl_sync(0xffffffffu, seg_count(a.segs, img), 0);
+  const int nk = __shfl_sync(0xffffffffu, seg_count(a.segs, src), 0);
   const int q0 = blockIdx.x * TQ;
   if (q0 >= nq || nk <= 0) return;
   const int qrow0 = a.segs.base[img] + q0;       // global row of the first query
@@ -124,8 +127,11 @@ k_attention_tc(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
   uint64_t* o_free = bars + 17;            // [2] PV buffer folded by the softmax warps (4 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
 
+  // Warp roles: 0..3 = data warps (TMEM lane quarter = warp), 4 = TMA producer, 5 = MMA issuer.  The issuer gets
+  // the highest warp id on its scheduler: the arbiter favours high warp ids, and a starved issuer starves the tensor pipe.
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0 && lane == 0) {
+  constexpr int kWarpTma = 4, kWarpMma = 5;
+  if (warp == kWarpTma && lane == 0) {
     tma_prefetch_desc(&mapQ);
     tma_prefetch_desc(&mapK);
     tma_prefetch_desc(&mapVt);
@@ -138,14 +144,14 @@ k_attention_tc(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     }
     fence_barrier_init();
   }
-  if (warp == 1) tmem_alloc<512>(tmem_slot);
+  if (warp == kWarpMma) tmem_alloc<512>(tmem_slot);
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
-  const uint32_t tmem = *tmem_slot;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);      // warp-uniform for the compiler
 
-  if (warp == 0) {
-    if (lane == 0) {
+  if (threadIdx.x == kWarpTma * 32) {
+    {
       // Q planes: rows [qrow0, +128) of plane 0 (hi) and plane 1 (lo, row offset rows_total), channels head*64..+64
       mbar_arrive_expect_tx(q_full, kQBytes);
       for (int pl = 0; pl < 2; ++pl)
@@ -170,28 +176,27 @@ k_attention_tc(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
                         pl * kD + head * HD);
       }
     }
-  } else if (warp == 1) {
-    if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_tf32(TQ, TKV);      // M=128, N=64 for both S and PV
-      const uint32_t qh = smem_u32(q_smem), ql = qh + 2 * kBoxBytesQ;
-      // Descriptors are built once; inside the loops an operand advance is one 64-bit add of (bytes >> 4) —
-      // the single issuing thread must not spend its time on descriptor arithmetic.
-      const uint64_t dq_hi = umma_desc_sw128(qh), dq_lo = umma_desc_sw128(ql);
-      uint64_t dk_hi[2], dk_lo[2], dv_hi[2], dv_lo[2];
-#pragma unroll
-      for (int s = 0; s < 2; ++s) {
-        const uint32_t kb = smem_u32(k_smem + s * kKStageBytes), vb = smem_u32(v_smem + s * kKStageBytes);
-        dk_hi[s] = umma_desc_sw128(kb); dk_lo[s] = umma_desc_sw128(kb + 2 * kBoxBytesKV);
-        dv_hi[s] = umma_desc_sw128(vb); dv_lo[s] = umma_desc_sw128(vb + 2 * kBoxBytesKV);
-      }
-      auto issue_qk = [&](int j) {
-        const int s = j & 1;
-        const uint32_t ph = (uint32_t)(j >> 1) & 1u;
+  } else if (threadIdx.x == kWarpMma * 32) {
+    // ===== MMA issuer: ONE thread, written so that all operand arithmetic stays in the uniform datapath
+    // (descriptor = base + constant; no arrays, no lambdas) — an issuer that needs R2UR moves per operand
+    // cannot keep the tensor pipe fed.
+    constexpr uint32_t idesc = umma_idesc_tf32(TQ, TKV);      // M=128, N=64 for both S and PV
+    const uint64_t dq_hi = umma_desc_sw128(smem_u32(q_smem)), dq_lo = dq_hi + ((2 * kBoxBytesQ) >> 4);
+    const uint64_t dk0 = umma_desc_sw128(smem_u32(k_smem)), dv0 = umma_desc_sw128(smem_u32(v_smem));
+    long long* trace = (blockIdx.x | blockIdx.y | blockIdx.z) == 0 ? g_attn_trace : nullptr;
+    mbar_wait(q_full, 0);
+    // software pipeline: iteration jq issues QK(jq) and then PV(jq-1)
+    for (int jq = 0; jq <= ntiles; ++jq) {
+      const int j = jq - 1;                                    // tile whose PV is issued in this iteration
+      if (trace && j >= 0) trace[j * 8 + 0] = clock64();
+      if (jq < ntiles) {
+        const int s = jq & 1;
+        const uint32_t ph = (uint32_t)(jq >> 1) & 1u;
         mbar_wait(&k_full[s], ph);
-        if (j >= 2) mbar_wait(&s_free[s], ph ^ 1);             // softmax warps have read S(j-2) out of this buffer
+        if (jq >= 2) mbar_wait(&s_free[s], ph ^ 1);            // softmax warps have read S(jq-2) out of this buffer
         tcgen05_fence_after();
-        const uint64_t kh = dk_hi[s], kl = dk_lo[s];
-        const uint32_t sacc = tmem + cS(s);
+        const uint64_t kh = dk0 + (uint64_t)(s * (kKStageBytes >> 4)), kl = kh + ((2 * kBoxBytesKV) >> 4);
+        const uint32_t sacc = tmem + s * 64;
         // K-dim = 64 channels = 2 boxes x 4 k-steps; corrections first, hi*hi last
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
@@ -206,22 +211,17 @@ k_attention_tc(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
         }
         umma_commit(&k_empty[s]);
         umma_commit(&s_full[s]);
-      };
-      long long* trace = (blockIdx.x | blockIdx.y | blockIdx.z) == 0 ? g_attn_trace : nullptr;
-      mbar_wait(q_full, 0);
-      issue_qk(0);
-      for (int j = 0; j < ntiles; ++j) {
-        ATTN_TRACE(0);
-        if (j + 1 < ntiles) issue_qk(j + 1);
+      }
+      if (j >= 0) {
         const int s = j & 1;
         const uint32_t ph = (uint32_t)(j >> 1) & 1u;
         mbar_wait(&v_full[s], ph);
         mbar_wait(&p_full[s], ph);                             // P(j) is in TMEM
         if (j >= 2) mbar_wait(&o_free[s], ph ^ 1);             // PV(j-2) has been folded out of this buffer
         tcgen05_fence_after();
-        ATTN_TRACE(1);
-        const uint64_t vh = dv_hi[s], vl = dv_lo[s];
-        const uint32_t oacc = tmem + cO(s), p_hi = tmem + cPh(s), p_lo = tmem + cPl(s);
+        if (trace) trace[j * 8 + 1] = clock64();
+        const uint64_t vh = dv0 + (uint64_t)(s * (kKStageBytes >> 4)), vl = vh + ((2 * kBoxBytesKV) >> 4);
+        const uint32_t oacc = tmem + 384 + s * 64, p_hi = tmem + 128 + s * 128, p_lo = p_hi + 64;
         // K-dim = 64 keys = 2 Vt boxes x 4 k-steps; A (P planes) from TMEM, 8 columns per k-step
 #pragma unroll
         for (int ks = 0; ks < 8; ++ks) {
@@ -236,10 +236,10 @@ k_attention_tc(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
         }
         umma_commit(&v_empty[s]);
         umma_commit(&o_full[s]);
-        ATTN_TRACE(2);
+        if (trace) trace[j * 8 + 2] = clock64();
       }
     }
-  } else {
+  } else if (warp < 4) {
     // ===== softmax / accumulate warps: thread <-> query row =====
     const int q = warp & 3;
     const uint32_t lane_base = tmem + ((uint32_t)(32 * q) << 16);
@@ -264,13 +264,14 @@ k_attention_tc(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
       __syncwarp();
       if (lane == 0) mbar_arrive(&o_free[b]);
     };
-    long long* trace = ((blockIdx.x | blockIdx.y | blockIdx.z) == 0 && threadIdx.x == 64) ? g_attn_trace : nullptr;
+    long long* trace = ((blockIdx.x | blockIdx.y | blockIdx.z) == 0 && lane == 0) ? g_attn_trace : nullptr;
+    const int tw = warp;   // trace: slots 4 (S seen, warp 0), 3/5/6/7 (P handed over by warps 0..3)
     for (int j = 0; j < ntiles; ++j) {
       const int sb = j & 1;
       const uint32_t ph = (uint32_t)(j >> 1) & 1u;
       mbar_wait(&s_full[sb], ph);
       tcgen05_fence_after();
-      ATTN_TRACE(4);
+      if (tw == 0) ATTN_TRACE(4);
       float s[TKV];                                      // scores in the log2 domain (Q was scaled by log2(e)/8)
 #pragma unroll
       for (int h = 0; h < 2; ++h) {
@@ -322,9 +323,8 @@ k_attention_tc(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
       tcgen05_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&p_full[sb]);
-      ATTN_TRACE(5);
+      if (tw == 0) ATTN_TRACE(3);
       if (j > 0) fold_pv(j - 1, alpha_prev);             // overlaps PV(j) / QK(j+1) on the tensor core
-      ATTN_TRACE(6);
       alpha_prev = alpha;
     }
     fold_pv(ntiles - 1, alpha_prev);
@@ -337,7 +337,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
     tcgen05_fence_before();
   }
   __syncthreads();
-  if (warp == 1) {
+  if (warp == kWarpMma) {
     tcgen05_fence_after();
     tmem_dealloc<512>(tmem);
   }

@@ -25,10 +25,9 @@ torch.cuda.synchronize()
 L.gims_debug_attention_trace(None)
 t = trace.cpu().view(64, 8)
 t0 = int(t[0, 0])
-print('tile  qk_issue  pv_ready  pv_issued | s_seen  p_given  fold_done   (cycles since first stamp; deltas to previous tile)')
+print('tile  qk_issue  pv_ready  pv_issued | s_seen(w0)  p_given by warp 0,1,2,3   (cycles since first stamp)')
 prev = None
 for j in range(32):
     r = [int(x) - t0 if int(x) else -1 for x in t[j]]
-    d = '' if prev is None else '  d_pv_issued=%d d_p_given=%d' % (r[2] - prev[2], r[5] - prev[5])
-    print('%3d  %8d %8d %8d | %8d %8d %8d%s' % (j, r[0], r[1], r[2], r[4], r[5], r[6], d))
+    print('%3d  top %8d  qk_first_mma %8d  pv_ready %8d  pv_issued %8d | s_seen %8d p_given %8d' % (j, r[0], r[6], r[1], r[2], r[4], r[3]))
     prev = r
