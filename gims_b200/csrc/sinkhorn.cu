@@ -28,6 +28,7 @@ constexpr int kThreads = 512;
 constexpr int kWarps = kThreads / 32;
 constexpr int kMaxGrid = 256;
 constexpr int kRMax = 16;            // rows per CTA handled by the unrolled (register) column pass
+constexpr int kRowChunks = 17;       // float4 chunks per lane of the register row pass (rows up to 2176 columns)
 constexpr float kLog2e = 1.4426950408889634f;
 
 typedef unsigned long long u64;
@@ -38,9 +39,11 @@ struct SinkArgs {
   const int* n_dev;
   int iters;
   float* u; float* v;              // outputs: final potentials
-  u64* part;                       // [grid][ldp]  (m, +-s): per-CTA column partials, sign(s) = iteration tag
-  u64* vx;                         // [ldp]        (v_j, iteration+1)
-  u64* cpart;                      // [grid][ldp]  (best value, row+1): column argmax partials of the last pass
+  float2* part;                    // [grid][ldp]  (m, s): per-CTA column partials; last pass: (best value, row index bits)
+  float* vg;                       // [ldp + 4]    v_j exchange buffer
+  unsigned* pflag;                 // [grid]       iteration number of the partials CTA g has published
+  unsigned* vflag;                 // [grid]       iteration number of the v_j CTA g has published
+  u64* mm;                         // [2*grid]     (zmin | 1<<32), (zmax | 1<<32) of every CTA's slab
   int ldp;
   unsigned* err;                   // set if a poll timed out (never expected; the results are then poisoned)
   int* idx0; int* idx1; float* max0; float* max1;
@@ -78,6 +81,52 @@ __device__ __forceinline__ u64 poll(const u64* p, unsigned* err, Pred ready) {
   }
 }
 
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
+  unsigned v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// Publish: every thread of the CTA has written its data with plain stores; one fence + one flag store makes them
+// visible (the block barrier orders the other threads' stores before thread 0's fence — cumulativity).
+__device__ __forceinline__ void publish_flag(unsigned* flag, unsigned epoch) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(flag), "r"(epoch) : "memory");
+  }
+}
+// Warp 0 waits until flags[0..n) have all reached `epoch`, then the whole CTA proceeds (data is then read with
+// ld.global.cg, which cannot hit a stale L1 line).  Bounded like every other wait in this file.
+__device__ __forceinline__ void wait_flags(const unsigned* flags, int n, unsigned epoch, unsigned* err) {
+  if (threadIdx.x < 32) {
+    const int lane = threadIdx.x;
+    long long t0 = clock64();
+    unsigned spins = 0;
+    while (true) {
+      bool ok = true;
+      for (int g = lane; g < n; g += 32) ok = ok && (ld_acquire_u32(&flags[g]) >= epoch);
+      if (__all_sync(0xffffffffu, ok)) break;
+      if ((++spins & 63u) == 0) {
+        bool bail = *(volatile unsigned*)err != 0u;
+        if (clock64() - t0 > 400000000LL) { atomicExch(err, 1u); bail = true; }
+        if (__any_sync(0xffffffffu, bail)) break;
+      }
+    }
+  }
+  __syncthreads();
+}
+
+// Up to N tagged words: issue every load first (one L2 round trip for all of them), then poll only the stragglers.
+template <int N, typename Addr, typename Pred>
+__device__ __forceinline__ void poll_batch(u64 (&w)[N], int count, Addr addr, unsigned* err, Pred ready) {
+#pragma unroll
+  for (int k = 0; k < N; ++k)
+    if (k < count) w[k] = ld_relaxed(addr(k));
+#pragma unroll
+  for (int k = 0; k < N; ++k)
+    if (k < count && !ready(w[k])) w[k] = poll(addr(k), err, ready);
+}
+
 __device__ __forceinline__ float warp_max(float x) {
 #pragma unroll
   for (int o = 16; o; o >>= 1) x = fmaxf(x, __shfl_xor_sync(0xffffffffu, x, o));
@@ -88,12 +137,25 @@ __device__ __forceinline__ float warp_sum(float x) {
   for (int o = 16; o; o >>= 1) x += __shfl_xor_sync(0xffffffffu, x, o);
   return x;
 }
+// 2^x for x <= 0: one MUFU (results below 2^-126 flush to zero, which is what a log-sum-exp term wants)
+__device__ __forceinline__ float ex2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
 // (m, s) <- combine of two (max, sum-of-exp) partials
 __device__ __forceinline__ void lse_merge(float& m, float& s, float pm, float ps) {
   float mn = fmaxf(m, pm);
-  s = s * exp2f((m - mn) * kLog2e) + ps * exp2f((pm - mn) * kLog2e);
+  s = s * ex2((m - mn) * kLog2e) + ps * ex2((pm - mn) * kLog2e);
   m = mn;
 }
+
+// Optional timeline (profiling): CTA 0 / thread 0 stores clock64() at 6 points of each of the first 16 iterations.
+__device__ long long* g_sink_trace = nullptr;
+#define SINK_TRACE(slot)                                                        \
+  do {                                                                          \
+    if (trace && it < 16) trace[it * 8 + (slot)] = clock64();                   \
+  } while (0)
 
 __global__ void __launch_bounds__(kThreads, 1) k_sinkhorn(SinkArgs a) {
   extern __shared__ __align__(16) float smem[];
@@ -117,132 +179,296 @@ __global__ void __launch_bounds__(kThreads, 1) k_sinkhorn(SinkArgs a) {
   const int c_begin = min(b * cpc, C), c_end = min(c_begin + cpc, C);
 
   const int vlen = (a.n1_max + 1 + 3) & ~3;
+  const int rlen = (a.rpc_max + 3) & ~3;
   float* v_s = smem;                                // [vlen], entries >= C stay 0
-  float* u_s = v_s + vlen;                          // [rpc_max]
-  float* slab = u_s + ((a.rpc_max + 3) & ~3);
+  float* w_s = v_s + vlen;                          // [vlen]  exp(v_j - vmax) (scaled-kernel path), pads 0
+  float* u_s = w_s + vlen;                          // [rlen]  u_r
+  float* ut_s = u_s + rlen;                         // [rlen]  u_r + rowmax_r
+  float* rmax_s = ut_s + rlen;                      // [rlen]  row maxima of my slab
+  float* e_s = rmax_s + rlen;                       // [rlen]  exp(ut_r - max ut)
+  float* slab = e_s + rlen;
+  __shared__ float red_x[kWarps], red_y[kWarps];
   const bool resident = a.slab_rows > 0 && nrows <= a.slab_rows && C <= a.slab_ld;
   const int zs = resident ? a.slab_ld : a.ld;       // row stride used by the passes
   const float* zbase = resident ? slab : a.Z + (size_t)r_begin * a.ld;
   const int C4 = resident ? ((C + 3) & ~3) : C;     // resident rows are padded with -inf up to a multiple of 4
 
+  float zmin_w = CUDART_INF_F, zmax_w = -CUDART_INF_F;
   if (resident) {
     for (int r = warp; r < nrows; r += kWarps) {
       const float* src = a.Z + (size_t)(r_begin + r) * a.ld;
       float* dst = slab + (size_t)r * a.slab_ld;
-      for (int j = lane; j < C4; j += 32) dst[j] = (j < C) ? src[j] : -CUDART_INF_F;
+      float mx = -CUDART_INF_F, mn = CUDART_INF_F;
+      for (int j = lane; j < C4; j += 32) {
+        float z = (j < C) ? src[j] : -CUDART_INF_F;
+        dst[j] = z;
+        if (j < C) { mx = fmaxf(mx, z); mn = fminf(mn, z); }
+      }
+      mx = warp_max(mx);
+      mn = -warp_max(-mn);
+      if (lane == 0) rmax_s[r] = mx;
+      zmax_w = fmaxf(zmax_w, mx); zmin_w = fminf(zmin_w, mn);
     }
   }
-  for (int j = tid; j < vlen; j += kThreads) v_s[j] = 0.f;
+  for (int j = tid; j < vlen; j += kThreads) { v_s[j] = 0.f; w_s[j] = (j < C) ? 1.f : 0.f; }
   if (a.iters == 0) for (int j = c_begin + tid; j < c_end; j += kThreads) a.v[j] = 0.f;
+  if (lane == 0) { red_x[warp] = zmax_w; red_y[warp] = zmin_w; }
   __syncthreads();
+  // ---- scaled-kernel path: decided once, identically by every CTA, from the global range of the couplings.
+  // With R = max Z0 - min Z0 every potential stays within R + 2 log(N+M) of any other (u_r differs between rows by at
+  // most R plus the log-marginals, likewise v_j), also from one iteration to the next.  For R <= 20 the weights
+  // exp(pot - reference) therefore stay inside e^+-70 and every row / column sum contains a term >= e^-70:
+  // nothing overflows, and anything that underflows is < 1e-7 of its sum.  The iteration then needs no exp per
+  // matrix element at all: slab = exp(z - rowmax) once, row pass = sum_j E_rj w_j, column pass = sum_r E_rj e_r.
+  bool fast = false;
+  if (resident && nrows <= kRMax && (C4 >> 2) <= kRowChunks * 32 && a.iters > 0) {
+    if (tid == 0 && b < Ga) {
+      float zx = red_x[0], zn = red_y[0];
+      for (int w = 1; w < kWarps; ++w) { zx = fmaxf(zx, red_x[w]); zn = fminf(zn, red_y[w]); }
+      st_relaxed(&a.mm[2 * b], (u64)__float_as_uint(zn) | (1ull << 32));
+      st_relaxed(&a.mm[2 * b + 1], (u64)__float_as_uint(zx) | (1ull << 32));
+    }
+    float gx = -CUDART_INF_F, gn = CUDART_INF_F;
+    if (warp == 0) {
+      for (int g = lane; g < Ga; g += 32) {
+        u64 w0 = poll(&a.mm[2 * g], a.err, [](u64 x) { return (x >> 32) != 0ull; });
+        u64 w1 = poll(&a.mm[2 * g + 1], a.err, [](u64 x) { return (x >> 32) != 0ull; });
+        gn = fminf(gn, __uint_as_float((unsigned)w0));
+        gx = fmaxf(gx, __uint_as_float((unsigned)w1));
+      }
+      gx = warp_max(gx);
+      gn = -warp_max(-gn);
+      if (lane == 0) red_x[0] = ((gx - gn) <= 20.f) ? 1.f : 0.f;
+    }
+    __syncthreads();
+    fast = red_x[0] != 0.f;
+    __syncthreads();
+    if (fast) {                                     // slab <- E = exp(z - rowmax), pads 0
+      for (int r = warp; r < nrows; r += kWarps) {
+        float* row = slab + (size_t)r * a.slab_ld;
+        const float rm = rmax_s[r];
+        for (int j = lane; j < C4; j += 32) row[j] = (j < C) ? ex2((row[j] - rm) * kLog2e) : 0.f;
+      }
+      __syncthreads();
+    }
+  }
+  float vmax = 0.f;                                 // reference the current w_s was scaled with (scaled-kernel path)
+  float ut_ref = 0.f;                               // reference of the column-pass weights e_s (a recent ut_0)
+  float vmax_next = 0.f;                            // v_0 of the current v: reference for the next gather
 
+  long long* trace = (b == 0 && tid == 0) ? g_sink_trace : nullptr;
+  const bool reg_rows = resident && (C4 >> 2) <= kRowChunks * 32;   // a row's (z + v) fits the lanes' registers
+  const bool reg_cols = resident && nrows <= kRMax;
   for (int it = 0; it < a.iters; ++it) {
+    SINK_TRACE(0);
     // ---- row pass -------------------------------------------------------------------------
-    for (int r = warp; r < nrows; r += kWarps) {
-      const float* z = zbase + (size_t)r * zs;
-      float m = -CUDART_INF_F, s = 0.f;
-      if (resident) {
-        const float4* z4 = reinterpret_cast<const float4*>(z);
+    if (fast) {
+      const int n4 = C4 >> 2;
+      for (int r = warp; r < nrows; r += kWarps) {
+        const float4* e4 = reinterpret_cast<const float4*>(slab + (size_t)r * a.slab_ld);
+        const float4* w4 = reinterpret_cast<const float4*>(w_s);
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int k = 0; k < kRowChunks; ++k) {
+          const int i = lane + 32 * k;
+          if (i < n4) {
+            const float4 ee = e4[i], ww = w4[i];
+            s0 = fmaf(ee.x, ww.x, s0); s1 = fmaf(ee.y, ww.y, s1); s2 = fmaf(ee.z, ww.z, s2); s3 = fmaf(ee.w, ww.w, s3);
+          }
+        }
+        const float sr = warp_sum((s0 + s1) + (s2 + s3));
+        if (lane == 0) {
+          const float lmu = (r_begin + r == n0) ? log_mu_last : norm;
+          const float lse_rel = vmax + logf(sr);               // LSE_j(z + v) - rowmax
+          const float ut = lmu - lse_rel;                      // u_r + rowmax_r
+          ut_s[r] = ut;
+          e_s[r] = ex2((ut - ut_ref) * kLog2e);                // column-pass weight, reference = last iteration's ut_0
+          u_s[r] = lmu - (rmax_s[r] + lse_rel);
+        }
+      }
+    } else if (reg_rows) {
+      const int n4 = C4 >> 2;
+      for (int r = warp; r < nrows; r += kWarps) {
+        const float4* z4 = reinterpret_cast<const float4*>(slab + (size_t)r * a.slab_ld);
         const float4* v4 = reinterpret_cast<const float4*>(v_s);
-        const int n4 = C4 >> 2;
-#pragma unroll 4
-        for (int i = lane; i < n4; i += 32) {
-          float4 zz = z4[i], vv = v4[i];
-          m = fmaxf(m, fmaxf(fmaxf(zz.x + vv.x, zz.y + vv.y), fmaxf(zz.z + vv.z, zz.w + vv.w)));
+        float4 x[kRowChunks];
+        float m = -CUDART_INF_F;
+#pragma unroll
+        for (int k = 0; k < kRowChunks; ++k) {
+          const int i = lane + 32 * k;
+          if (i < n4) {
+            const float4 zz = z4[i], vv = v4[i];
+            x[k] = make_float4(zz.x + vv.x, zz.y + vv.y, zz.z + vv.z, zz.w + vv.w);
+            m = fmaxf(m, fmaxf(fmaxf(x[k].x, x[k].y), fmaxf(x[k].z, x[k].w)));
+          } else {
+            x[k] = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+          }
         }
         m = warp_max(m);
-#pragma unroll 4
-        for (int i = lane; i < n4; i += 32) {
-          float4 zz = z4[i], vv = v4[i];
-          s += exp2f((zz.x + vv.x - m) * kLog2e) + exp2f((zz.y + vv.y - m) * kLog2e) +
-               exp2f((zz.z + vv.z - m) * kLog2e) + exp2f((zz.w + vv.w - m) * kLog2e);
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int k = 0; k < kRowChunks; ++k) {
+          s0 += ex2((x[k].x - m) * kLog2e); s1 += ex2((x[k].y - m) * kLog2e);
+          s2 += ex2((x[k].z - m) * kLog2e); s3 += ex2((x[k].w - m) * kLog2e);
         }
-      } else {
+        const float s = warp_sum((s0 + s1) + (s2 + s3));
+        if (lane == 0) {
+          float lmu = (r_begin + r == n0) ? log_mu_last : norm;
+          u_s[r] = lmu - (m + logf(s));
+        }
+      }
+    } else {
+      for (int r = warp; r < nrows; r += kWarps) {
+        const float* z = zbase + (size_t)r * zs;
+        float m = -CUDART_INF_F, s = 0.f;
 #pragma unroll 4
         for (int j = lane; j < C; j += 32) m = fmaxf(m, z[j] + v_s[j]);
         m = warp_max(m);
 #pragma unroll 4
-        for (int j = lane; j < C; j += 32) s += exp2f((z[j] + v_s[j] - m) * kLog2e);
-      }
-      s = warp_sum(s);
-      if (lane == 0) {
-        float lmu = (r_begin + r == n0) ? log_mu_last : norm;
-        u_s[r] = lmu - (m + logf(s));
+        for (int j = lane; j < C; j += 32) s += ex2((z[j] + v_s[j] - m) * kLog2e);
+        s = warp_sum(s);
+        if (lane == 0) {
+          float lmu = (r_begin + r == n0) ? log_mu_last : norm;
+          u_s[r] = lmu - (m + logf(s));
+        }
       }
     }
     __syncthreads();
+    const float ut_ref_used = ut_ref;
+    if (fast && nrows > 0) ut_ref = ut_s[0];         // reference for the next iteration (read after the barrier)
+    SINK_TRACE(1);
     // ---- column pass: per-CTA partial LSE, published with the iteration tag in sign(s) --------------
-    const unsigned tagbit = ((unsigned)(it + 1) & 1u) << 31;
-    if (b < Ga) {
-      if (nrows <= kRMax) {
-        for (int j = tid; j < C; j += kThreads) {
-          float x[kRMax];
-          float m = -CUDART_INF_F;
+    const unsigned epoch = (unsigned)(it + 1);
+    if (b < Ga && fast) {
+      const float mb = ut_ref_used;                  // e_s[r] = exp(ut_r - mb) was written by the row pass
+      const int Gf = C >> 2;
+      for (int g = tid; g < Gf; g += kThreads) {
+        float4 sm = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int r = 0; r < kRMax; ++r) {
+          if (r < nrows) {
+            const float4 ee = *reinterpret_cast<const float4*>(slab + (size_t)r * a.slab_ld + 4 * g);
+            const float er = e_s[r];
+            sm.x = fmaf(ee.x, er, sm.x); sm.y = fmaf(ee.y, er, sm.y); sm.z = fmaf(ee.z, er, sm.z); sm.w = fmaf(ee.w, er, sm.w);
+          }
+        }
+        float2* dst = &a.part[(size_t)b * a.ldp + 4 * g];
+        dst[0] = make_float2(mb, sm.x); dst[1] = make_float2(mb, sm.y);
+        dst[2] = make_float2(mb, sm.z); dst[3] = make_float2(mb, sm.w);
+      }
+      const int jl = 4 * Gf + warp;
+      if (jl < C) {
+        const float xx = (lane < nrows) ? slab[(size_t)lane * a.slab_ld + jl] * e_s[lane] : 0.f;
+        const float ss = warp_sum(xx);
+        if (lane == 0) a.part[(size_t)b * a.ldp + jl] = make_float2(mb, ss);
+      }
+    } else if (b < Ga) {
+      if (reg_cols) {
+        const int Gf = C >> 2;                               // groups of 4 columns, one 128-bit LDS per row
+        for (int g = tid; g < Gf; g += kThreads) {
+          float4 x[kRMax];
+          float4 m = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
 #pragma unroll
           for (int r = 0; r < kRMax; ++r) {
-            x[r] = (r < nrows) ? zbase[(size_t)r * zs + j] + u_s[r] : -CUDART_INF_F;
-            m = fmaxf(m, x[r]);
+            if (r < nrows) {
+              const float4 zz = *reinterpret_cast<const float4*>(slab + (size_t)r * a.slab_ld + 4 * g);
+              const float ur = u_s[r];
+              x[r] = make_float4(zz.x + ur, zz.y + ur, zz.z + ur, zz.w + ur);
+              m.x = fmaxf(m.x, x[r].x); m.y = fmaxf(m.y, x[r].y); m.z = fmaxf(m.z, x[r].z); m.w = fmaxf(m.w, x[r].w);
+            } else {
+              x[r] = make_float4(-CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F, -CUDART_INF_F);
+            }
           }
-          float s = 0.f;
+          float4 sm = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-          for (int r = 0; r < kRMax; ++r) s += exp2f((x[r] - m) * kLog2e);
-          st_relaxed(&a.part[(size_t)b * a.ldp + j], pack2(m, __uint_as_float(__float_as_uint(s) | tagbit)));
+          for (int r = 0; r < kRMax; ++r) {
+            sm.x += ex2((x[r].x - m.x) * kLog2e); sm.y += ex2((x[r].y - m.y) * kLog2e);
+            sm.z += ex2((x[r].z - m.z) * kLog2e); sm.w += ex2((x[r].w - m.w) * kLog2e);
+          }
+          float2* dst = &a.part[(size_t)b * a.ldp + 4 * g];
+          dst[0] = make_float2(m.x, sm.x); dst[1] = make_float2(m.y, sm.y);
+          dst[2] = make_float2(m.z, sm.z); dst[3] = make_float2(m.w, sm.w);
+        }
+        // the (at most 3) columns left over — among them the dustbin column — are reduced across the lanes of a warp
+        const int jl = 4 * Gf + warp;
+        if (jl < C) {
+          const float xx = (lane < nrows) ? slab[(size_t)lane * a.slab_ld + jl] + u_s[lane] : -CUDART_INF_F;
+          const float mm = warp_max(xx);
+          const float ss = warp_sum(ex2((xx - mm) * kLog2e));
+          if (lane == 0) a.part[(size_t)b * a.ldp + jl] = make_float2(mm, ss);
         }
       } else {
         for (int j = tid; j < C; j += kThreads) {
           float m = -CUDART_INF_F;
           for (int r = 0; r < nrows; ++r) m = fmaxf(m, zbase[(size_t)r * zs + j] + u_s[r]);
           float s = 0.f;
-          for (int r = 0; r < nrows; ++r) s += exp2f((zbase[(size_t)r * zs + j] + u_s[r] - m) * kLog2e);
-          st_relaxed(&a.part[(size_t)b * a.ldp + j], pack2(m, __uint_as_float(__float_as_uint(s) | tagbit)));
+          for (int r = 0; r < nrows; ++r) s += ex2((zbase[(size_t)r * zs + j] + u_s[r] - m) * kLog2e);
+          a.part[(size_t)b * a.ldp + j] = make_float2(m, s);
         }
       }
     }
-    // ---- combine the partials of my column range -> v_j, published with the iteration number --------
-    const unsigned epoch = (unsigned)(it + 1);
+    publish_flag(&a.pflag[b], epoch);
+    SINK_TRACE(2);
+    // ---- combine the partials of my column range -> v_j ------------------------------------------------
+    wait_flags(a.pflag, Ga, epoch, a.err);
     for (int jc = c_begin; jc < c_end; jc += 16) {
       const int jj = tid & 15, gs = tid >> 4, j = jc + jj;
       float m = -CUDART_INF_F, s = 0.f;
       if (j < c_end) {
-        for (int g = gs; g < Ga; g += 32) {
-          u64 w = poll(&a.part[(size_t)g * a.ldp + j], a.err,
-                       [&](u64 x) { return (((unsigned)(x >> 32)) & 0x80000000u) == tagbit; });
-          float pm = __uint_as_float((unsigned)w), ps = __uint_as_float(((unsigned)(w >> 32)) & 0x7fffffffu);
-          lse_merge(m, s, pm, ps);
-        }
+        float2 w[8];                                   // grid <= 256 -> at most 8 producers per (column, slot)
+        const int cnt = (Ga - gs + 31) >> 5;
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (k < cnt) w[k] = __ldcg(&a.part[(size_t)(gs + 32 * k) * a.ldp + j]);
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+          if (k < cnt) lse_merge(m, s, w[k].x, w[k].y);
       }
       red_m[gs][jj] = m; red_s[gs][jj] = s;
       __syncthreads();
+      SINK_TRACE(3);
       const int jw = jc + warp;                      // warp w finishes column jc + w
       if (jw < c_end) {
         float mm = red_m[lane][warp], ss = red_s[lane][warp];
         float M = warp_max(mm);
-        ss = (ss > 0.f) ? ss * exp2f((mm - M) * kLog2e) : 0.f;
+        ss = (ss > 0.f) ? ss * ex2((mm - M) * kLog2e) : 0.f;
         ss = warp_sum(ss);
         if (lane == 0) {
           float lnu = (jw == n1) ? log_nu_last : norm;
           float vj = lnu - (M + logf(ss));
-          st_relaxed(&a.vx[jw], pack2(vj, __uint_as_float(epoch)));
+          a.vg[jw] = vj;
           if (it == a.iters - 1) a.v[jw] = vj;
         }
       }
       __syncthreads();
     }
-    // ---- gather the new v (poll the tagged words) -----------------------------------------------------
+    publish_flag(&a.vflag[b], epoch);
+    SINK_TRACE(4);
+    // ---- gather the new v ----------------------------------------------------------------------------------
+    wait_flags(a.vflag, G, epoch, a.err);
+    // scaled-kernel path: w_j = exp(v_j - vref) with vref = last iteration's v_0 — any reference inside the
+    // (bounded) range of v works, and this one is known before the gather, so no reduction / extra barrier is needed
+    const float vref_next = vmax_next;
     for (int j = tid; j < C; j += kThreads) {
-      u64 w = poll(&a.vx[j], a.err, [&](u64 x) { return (unsigned)(x >> 32) == epoch; });
-      v_s[j] = __uint_as_float((unsigned)w);
+      const float vj = __ldcg(&a.vg[j]);
+      v_s[j] = vj;
+      if (fast) w_s[j] = ex2((vj - vref_next) * kLog2e);
     }
+    vmax = vref_next;
     __syncthreads();
+    vmax_next = v_s[0];
+    SINK_TRACE(5);
   }
 
   // ---- final pass: Z = ((Z0 + u) + v) - norm, row / column max + first argmax -------------------
+  if (fast) { zbase = a.Z + (size_t)r_begin * a.ld; }            // the slab holds exp(z - rowmax): re-read Z0 (L2)
+  const int zsf = fast ? a.ld : zs;
   for (int r = warp; r < nrows; r += kWarps) {
     int gr = r_begin + r;
     float ur = (a.iters > 0) ? u_s[r] : 0.f;
     if (lane == 0) a.u[gr] = ur;
     if (gr >= n0) continue;
-    const float* z = zbase + (size_t)r * zs;
+    const float* z = zbase + (size_t)r * zsf;
     float best = -CUDART_INF_F;
     int bj = 0x7fffffff;
 #pragma unroll 4
@@ -266,22 +492,28 @@ __global__ void __launch_bounds__(kThreads, 1) k_sinkhorn(SinkArgs a) {
       float vj = v_s[j];
       for (int r = 0; r < live; ++r) {
         float ur = (a.iters > 0) ? u_s[r] : 0.f;
-        float t = ((zbase[(size_t)r * zs + j] + ur) + vj) - norm;
+        float t = ((zbase[(size_t)r * zsf + j] + ur) + vj) - norm;
         if (t > best) { best = t; bi = r_begin + r; }
       }
-      st_relaxed(&a.cpart[(size_t)b * a.ldp + j], pack2(best, __int_as_float(bi + 1)));   // row+1 != 0: "written"
+      a.part[(size_t)b * a.ldp + j] = make_float2(best, __int_as_float(bi));
     }
   }
+  publish_flag(&a.pflag[b], (unsigned)(a.iters + 1));
+  wait_flags(a.pflag, Ga, (unsigned)(a.iters + 1), a.err);
   for (int jc = c_begin; jc < c_end; jc += 16) {
     const int jj = tid & 15, gs = tid >> 4, j = jc + jj;
     float best = -CUDART_INF_F;
     int bi = 0x7fffffff;
     if (j < c_end && j < n1) {
-      for (int g = gs; g < Ga; g += 32) {
-        u64 w = poll(&a.cpart[(size_t)g * a.ldp + j], a.err, [&](u64 x) { return (unsigned)(x >> 32) != 0u; });
-        float pv = __uint_as_float((unsigned)w);
-        int pi = (int)(unsigned)(w >> 32) - 1;
-        if (pv > best || (pv == best && pi < bi)) { best = pv; bi = pi; }
+      const int cnt = (Ga - gs + 31) >> 5;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        if (k < cnt) {
+          const float2 w = __ldcg(&a.part[(size_t)(gs + 32 * k) * a.ldp + j]);
+          const float pv = w.x;
+          const int pi = __float_as_int(w.y);
+          if (pv > best || (pv == best && pi < bi)) { best = pv; bi = pi; }
+        }
       }
     }
     red_m[gs][jj] = best; red_s[gs][jj] = __int_as_float(bi);
@@ -334,10 +566,12 @@ __global__ void k_match_finalize(int n0_max, int n1_max, const int* __restrict__
 struct SinkWs {
   // zeroed before every launch (tags)
   unsigned* err;
-  u64* vx;
-  u64* part;
-  u64* cpart;
+  unsigned* pflag;
+  unsigned* vflag;
+  u64* mm;
   size_t zero_bytes;
+  float2* part;
+  float* vg;
   float* max0;
   float* max1;
 };
@@ -346,10 +580,12 @@ size_t carve(SinkWs& w, void* base, size_t cap, int n0_max, int n1_max, int grid
   Arena a(base, cap);
   size_t ldp = (size_t)n1_max + 1;
   w.err = a.take<unsigned>(64);
-  w.vx = a.take<u64>(ldp);
-  w.part = a.take<u64>((size_t)grid * ldp);
-  w.cpart = a.take<u64>((size_t)grid * ldp);
+  w.pflag = a.take<unsigned>(kMaxGrid);
+  w.vflag = a.take<unsigned>(kMaxGrid);
+  w.mm = a.take<u64>(2 * (size_t)kMaxGrid);
   w.zero_bytes = align_up(a.off, 256);
+  w.part = a.take<float2>((size_t)grid * ldp);
+  w.vg = a.take<float>(ldp + 4);
   w.max0 = a.take<float>(n0_max + 1);
   w.max1 = a.take<float>(n1_max + 1);
   return align_up(a.off, 256);
@@ -360,6 +596,11 @@ size_t carve(SinkWs& w, void* base, size_t cap, int n0_max, int n1_max, int grid
 }  // namespace gims
 
 using namespace gims;
+
+extern "C" int gims_debug_sinkhorn_trace(long long* dev_buf) {
+  GIMS_CUDA_OK(cudaMemcpyToSymbol(g_sink_trace, &dev_buf, sizeof(dev_buf)));
+  return GIMS_OK;
+}
 
 extern "C" size_t gims_sinkhorn_workspace_bytes(int n0_max, int n1_max) {
   SinkWs w;
@@ -383,7 +624,7 @@ extern "C" int gims_sinkhorn_match(const float* couplings, int n0_max, int n1_ma
   int R = n0_max + 1, C = n1_max + 1;
   int rpc = (R + G - 1) / G;
   int slab_ld = (C + 3) & ~3;
-  size_t fixed = (size_t)(((C + 3) & ~3) + ((rpc + 3) & ~3)) * sizeof(float);
+  size_t fixed = (size_t)(2 * ((C + 3) & ~3) + 4 * ((rpc + 3) & ~3)) * sizeof(float);   // v, w | u, ut, rmax, e
   size_t slab_bytes = (size_t)rpc * slab_ld * sizeof(float);
   size_t budget = (size_t)smem_optin - 5120;     // static smem (red_m / red_s) + margin
   SinkArgs a;
@@ -393,13 +634,13 @@ extern "C" int gims_sinkhorn_match(const float* couplings, int n0_max, int n1_ma
   size_t dyn = fixed + (a.slab_rows ? slab_bytes : 0);
   if (dyn > budget) { set_error("gims_sinkhorn_match: n1_max=%d needs %zu B of shared memory", n1_max, dyn); return GIMS_ERR_ARG; }
   a.Z = couplings; a.ld = C; a.n0_max = n0_max; a.n1_max = n1_max; a.n_dev = n_dev; a.iters = iters;
-  a.u = u; a.v = v; a.part = w.part; a.vx = w.vx; a.cpart = w.cpart; a.ldp = C; a.err = w.err;
+  a.u = u; a.v = v; a.part = w.part; a.vg = w.vg; a.pflag = w.pflag; a.vflag = w.vflag; a.mm = w.mm; a.ldp = C; a.err = w.err;
   a.idx0 = indices0; a.idx1 = indices1; a.max0 = w.max0; a.max1 = w.max1;
   GIMS_CUDA_OK(cudaFuncSetAttribute(k_sinkhorn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
   int per_sm = 0;
   GIMS_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sinkhorn, kThreads, dyn));
   if (per_sm < 1) { set_error("gims_sinkhorn_match: kernel does not fit an SM (dyn smem %zu)", dyn); return GIMS_ERR_ARG; }
-  GIMS_CUDA_OK(cudaMemsetAsync(w.err, 0, w.zero_bytes, st));    // clears every tag (err, vx, part, cpart are contiguous)
+  GIMS_CUDA_OK(cudaMemsetAsync(w.err, 0, w.zero_bytes, st));    // clears err and every flag / tag word (contiguous)
   void* params[] = {&a};
   GIMS_TRY(coop_chain_wait(st));
   {

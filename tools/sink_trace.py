@@ -1,0 +1,32 @@
+"""Timeline of CTA 0 of k_sinkhorn (gims_debug_sinkhorn_trace) on a 2048x2048 problem."""
+import ctypes as C
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from gims_b200 import _lib
+L = _lib.lib()
+dev = torch.device('cuda')
+n0 = n1 = 2048
+coup = torch.randn(n0 + 1, n1 + 1, device=dev)
+nd = torch.tensor([n0, n1], dtype=torch.int32, device=dev)
+ws = torch.empty(L.gims_sinkhorn_workspace_bytes(n0, n1), dtype=torch.uint8, device=dev)
+uo, vo = torch.zeros(n0 + 1, device=dev), torch.zeros(n1 + 1, device=dev)
+i0, i1 = torch.zeros(n0, dtype=torch.int32, device=dev), torch.zeros(n1, dtype=torch.int32, device=dev)
+m0, m1 = torch.zeros(n0, dtype=torch.int64, device=dev), torch.zeros(n1, dtype=torch.int64, device=dev)
+s0, s1 = torch.zeros(n0, device=dev), torch.zeros(n1, device=dev)
+trace = torch.zeros(16 * 8, dtype=torch.int64, device=dev)
+st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+def run():
+    _lib.check(L.gims_sinkhorn_match(_lib.ptr(coup), n0, n1, _lib.ptr(nd), 100, 0.2, _lib.ptr(ws), ws.numel(), _lib.ptr(uo), _lib.ptr(vo),
+                                     _lib.ptr(i0), _lib.ptr(i1), _lib.ptr(m0), _lib.ptr(m1), _lib.ptr(s0), _lib.ptr(s1), st), 'sinkhorn')
+run(); run(); torch.cuda.synchronize()
+L.gims_debug_sinkhorn_trace(C.c_void_p(trace.data_ptr()))
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record(); run(); e1.record(); torch.cuda.synchronize()
+L.gims_debug_sinkhorn_trace(None)
+print('kernel+finalize time %.1f us' % (1000 * e0.elapsed_time(e1)))
+t = trace.cpu().view(16, 8)
+print('iter   row_pass  col_pass  wait_partials  combine+publish  gather_v   total   (cycles)')
+for it in range(1, 12):
+    r = [int(x) for x in t[it]]
+    print('%3d   %8d %8d %12d %14d %10d %8d' % (it, r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], r[5] - r[4], r[5] - r[0]))
