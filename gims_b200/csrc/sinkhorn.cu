@@ -43,6 +43,8 @@ struct SinkArgs {
   float* vg;                       // [ldp + 4]    v_j exchange buffer
   unsigned* pflag;                 // [grid]       iteration number of the partials CTA g has published
   unsigned* vflag;                 // [grid]       iteration number of the v_j CTA g has published
+  float* colsum;                   // [3][ldp]     scaled-kernel path: column sums accumulated with red.add, 3 rotating buffers
+  unsigned* counter;               // grid-wide arrival counter of the scaled-kernel path
   u64* mm;                         // [2*grid]     (zmin | 1<<32), (zmax | 1<<32) of every CTA's slab
   int ldp;
   unsigned* err;                   // set if a poll timed out (never expected; the results are then poisoned)
@@ -116,6 +118,25 @@ __device__ __forceinline__ void wait_flags(const unsigned* flags, int n, unsigne
   __syncthreads();
 }
 
+// Grid-wide arrive + wait on one monotonically increasing counter (every CTA is co-resident: cooperative launch).
+// Measured on B200 (tools/micro/hop_latency.cu): 2.5 k cycles per hop, about half of a per-CTA flag scheme.
+__device__ __forceinline__ void grid_hop(unsigned* counter, unsigned target, unsigned* err) {
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    atomicAdd(counter, 1u);
+    long long t0 = clock64();
+    unsigned spins = 0;
+    while (ld_acquire_u32(counter) < target) {
+      if ((++spins & 255u) == 0) {
+        if (*(volatile unsigned*)err) break;
+        if (clock64() - t0 > 400000000LL) { atomicExch(err, 1u); break; }
+      }
+    }
+  }
+  __syncthreads();
+}
+
 // Up to N tagged words: issue every load first (one L2 round trip for all of them), then poll only the stragglers.
 template <int N, typename Addr, typename Pred>
 __device__ __forceinline__ void poll_batch(u64 (&w)[N], int count, Addr addr, unsigned* err, Pred ready) {
@@ -155,6 +176,11 @@ __device__ long long* g_sink_trace = nullptr;
 #define SINK_TRACE(slot)                                                        \
   do {                                                                          \
     if (trace && it < 16) trace[it * 8 + (slot)] = clock64();                   \
+    if (g_sink_trace && it == 5 && threadIdx.x == 0) {                          \
+      unsigned long long gt_;                                                   \
+      asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                   \
+      g_sink_trace[128 + blockIdx.x * 8 + (slot)] = (long long)gt_;             \
+    }                                                                           \
   } while (0)
 
 __global__ void __launch_bounds__(kThreads, 1) k_sinkhorn(SinkArgs a) {
@@ -259,6 +285,96 @@ __global__ void __launch_bounds__(kThreads, 1) k_sinkhorn(SinkArgs a) {
   long long* trace = (b == 0 && tid == 0) ? g_sink_trace : nullptr;
   const bool reg_rows = resident && (C4 >> 2) <= kRowChunks * 32;   // a row's (z + v) fits the lanes' registers
   const bool reg_cols = resident && nrows <= kRMax;
+  if (fast) {
+    // ===== scaled-kernel iteration: ONE grid-wide exchange per iteration =================================================
+    //   row pass   sr_r = sum_j E_rj w_j           -> u_r, and the column weight e_r = exp(ut_r - Rref)
+    //   col pass   s_j  = sum_{my rows} E_rj e_r   -> red.add into colsum[it%3][j]   (all CTAs share the reference Rref,
+    //                                                 so partial sums add up directly; fp32 atomics: order-dependent
+    //                                                 rounding, ~1e-7 relative)
+    //   hop        arrive/wait on the counter
+    //   gather     v_j = log_nu_j - (Rref + log colsum_j) computed by every CTA for every column; w_j = exp(v_j - v_0)
+    const int n4 = C4 >> 2;
+    const int Gf = C >> 2;
+    const size_t cs_ld = ((size_t)a.ldp + 3) & ~(size_t)3;
+    float vref = 0.f;                               // reference the current w_s was scaled with (initially v = 0, w = 1)
+    unsigned target = 0;
+    for (int it = 0; it < a.iters; ++it) {
+      SINK_TRACE(0);
+      float* cs = a.colsum + (size_t)(it % 3) * cs_ld;
+      const float Rref = norm - vref;
+      for (int r = warp; r < nrows; r += kWarps) {
+        const float4* e4 = reinterpret_cast<const float4*>(slab + (size_t)r * a.slab_ld);
+        const float4* w4 = reinterpret_cast<const float4*>(w_s);
+        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+        for (int k = 0; k < kRowChunks; ++k) {
+          const int i = lane + 32 * k;
+          if (i < n4) {
+            const float4 ee = e4[i], ww = w4[i];
+            s0 = fmaf(ee.x, ww.x, s0); s1 = fmaf(ee.y, ww.y, s1); s2 = fmaf(ee.z, ww.z, s2); s3 = fmaf(ee.w, ww.w, s3);
+          }
+        }
+        const float sr = warp_sum((s0 + s1) + (s2 + s3));
+        if (lane == 0) {
+          const float lmu = (r_begin + r == n0) ? log_mu_last : norm;
+          const float lse_rel = vref + logf(sr);               // LSE_j(z + v) - rowmax
+          e_s[r] = ex2(((lmu - lse_rel) - Rref) * kLog2e);      // exp(u_r + rowmax_r - Rref)
+          u_s[r] = lmu - (rmax_s[r] + lse_rel);
+        }
+      }
+      __syncthreads();
+      SINK_TRACE(1);
+      if (b < Ga) {
+        for (int g = tid; g < Gf; g += kThreads) {
+          float4 sm = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int r = 0; r < kRMax; ++r) {
+            if (r < nrows) {
+              const float4 ee = *reinterpret_cast<const float4*>(slab + (size_t)r * a.slab_ld + 4 * g);
+              const float er = e_s[r];
+              sm.x = fmaf(ee.x, er, sm.x); sm.y = fmaf(ee.y, er, sm.y); sm.z = fmaf(ee.z, er, sm.z); sm.w = fmaf(ee.w, er, sm.w);
+            }
+          }
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cs + 4 * g), "f"(sm.x), "f"(sm.y), "f"(sm.z),
+                       "f"(sm.w)
+                       : "memory");
+        }
+        const int jl = 4 * Gf + warp;                 // the (at most 3) left-over columns, among them the dustbin column
+        if (jl < C) {
+          const float xx = (lane < nrows) ? slab[(size_t)lane * a.slab_ld + jl] * e_s[lane] : 0.f;
+          const float ss = warp_sum(xx);
+          if (lane == 0) atomicAdd(cs + jl, ss);
+        }
+      }
+      SINK_TRACE(2);
+      target += (unsigned)G;
+      grid_hop(a.counter, target, a.err);
+      SINK_TRACE(3);
+      {                                               // recycle the buffer that was read one iteration ago
+        float* old = a.colsum + (size_t)((it + 2) % 3) * cs_ld;
+        for (int j = c_begin + tid; j < c_end; j += kThreads) old[j] = 0.f;
+      }
+      const float v0 = norm - (Rref + logf(__ldcg(cs)));        // v of column 0: the next reference (n1 >= 1)
+      for (int g4 = tid; g4 < n4; g4 += kThreads) {               // 128-bit loads: 4x fewer requests on these hot lines
+        const float4 c4 = __ldcg(reinterpret_cast<const float4*>(cs) + g4);
+        const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const int j = 4 * g4 + q;
+          if (j < C) {
+            const float lnu = (j == n1) ? log_nu_last : norm;
+            const float vj = lnu - (Rref + logf(cc[q]));
+            v_s[j] = vj;
+            w_s[j] = ex2((vj - v0) * kLog2e);
+            if (it == a.iters - 1 && j >= c_begin && j < c_end) a.v[j] = vj;
+          }
+        }
+      }
+      vref = v0;
+      __syncthreads();
+      SINK_TRACE(5);
+    }
+  } else
   for (int it = 0; it < a.iters; ++it) {
     SINK_TRACE(0);
     // ---- row pass -------------------------------------------------------------------------
@@ -569,6 +685,7 @@ struct SinkWs {
   unsigned* pflag;
   unsigned* vflag;
   u64* mm;
+  float* colsum;
   size_t zero_bytes;
   float2* part;
   float* vg;
@@ -583,6 +700,7 @@ size_t carve(SinkWs& w, void* base, size_t cap, int n0_max, int n1_max, int grid
   w.pflag = a.take<unsigned>(kMaxGrid);
   w.vflag = a.take<unsigned>(kMaxGrid);
   w.mm = a.take<u64>(2 * (size_t)kMaxGrid);
+  w.colsum = a.take<float>(3 * ((ldp + 3) & ~(size_t)3));
   w.zero_bytes = align_up(a.off, 256);
   w.part = a.take<float2>((size_t)grid * ldp);
   w.vg = a.take<float>(ldp + 4);
@@ -634,7 +752,7 @@ extern "C" int gims_sinkhorn_match(const float* couplings, int n0_max, int n1_ma
   size_t dyn = fixed + (a.slab_rows ? slab_bytes : 0);
   if (dyn > budget) { set_error("gims_sinkhorn_match: n1_max=%d needs %zu B of shared memory", n1_max, dyn); return GIMS_ERR_ARG; }
   a.Z = couplings; a.ld = C; a.n0_max = n0_max; a.n1_max = n1_max; a.n_dev = n_dev; a.iters = iters;
-  a.u = u; a.v = v; a.part = w.part; a.vg = w.vg; a.pflag = w.pflag; a.vflag = w.vflag; a.mm = w.mm; a.ldp = C; a.err = w.err;
+  a.u = u; a.v = v; a.part = w.part; a.vg = w.vg; a.pflag = w.pflag; a.vflag = w.vflag; a.mm = w.mm; a.colsum = w.colsum; a.counter = w.err + 32; a.ldp = C; a.err = w.err;
   a.idx0 = indices0; a.idx1 = indices1; a.max0 = w.max0; a.max1 = w.max1;
   GIMS_CUDA_OK(cudaFuncSetAttribute(k_sinkhorn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
   int per_sm = 0;

@@ -14,7 +14,7 @@ uo, vo = torch.zeros(n0 + 1, device=dev), torch.zeros(n1 + 1, device=dev)
 i0, i1 = torch.zeros(n0, dtype=torch.int32, device=dev), torch.zeros(n1, dtype=torch.int32, device=dev)
 m0, m1 = torch.zeros(n0, dtype=torch.int64, device=dev), torch.zeros(n1, dtype=torch.int64, device=dev)
 s0, s1 = torch.zeros(n0, device=dev), torch.zeros(n1, device=dev)
-trace = torch.zeros(16 * 8, dtype=torch.int64, device=dev)
+trace = torch.zeros(16 * 8 + 256 * 8, dtype=torch.int64, device=dev)
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 def run():
     _lib.check(L.gims_sinkhorn_match(_lib.ptr(coup), n0, n1, _lib.ptr(nd), 100, 0.2, _lib.ptr(ws), ws.numel(), _lib.ptr(uo), _lib.ptr(vo),
@@ -25,8 +25,22 @@ e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=Tr
 e0.record(); run(); e1.record(); torch.cuda.synchronize()
 L.gims_debug_sinkhorn_trace(None)
 print('kernel+finalize time %.1f us' % (1000 * e0.elapsed_time(e1)))
-t = trace.cpu().view(16, 8)
+tall = trace.cpu()
+t = tall[:128].view(16, 8)
+pc = tall[128:128 + 148 * 8].view(148, 8)
 print('iter   row_pass  col_pass  wait_partials  combine+publish  gather_v   total   (cycles)')
 for it in range(1, 12):
     r = [int(x) for x in t[it]]
     print('%3d   %8d %8d %12d %14d %10d %8d' % (it, r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], r[5] - r[4], r[5] - r[0]))
+
+import numpy as np
+pc = pc.numpy().astype(np.int64)
+base = pc[:, 0].min()
+print('per-CTA globaltimer (ns) at iteration 5, relative to the earliest start:')
+print('cta   start  row_done  col_done  hop_done  gather_done')
+order = np.argsort(pc[:, 2])
+for b in list(order[:4]) + list(order[-8:]):
+    r = pc[b] - base
+    print('%3d  %6d %8d %9d %9d %10d' % (b, r[0], r[1], r[2], r[3], r[5]))
+print('col_done spread: min %d max %d median %d' % ((pc[:,2]-base).min(), (pc[:,2]-base).max(), int(np.median(pc[:,2]-base))))
+print('start spread: min %d max %d' % ((pc[:,0]-base).min(), (pc[:,0]-base).max()))
