@@ -598,9 +598,11 @@ __global__ void __launch_bounds__(256) k_comp_nn(const float2* __restrict__ cent
 
 constexpr int kPairChunk = 2048;
 
-// block per component c: closest pair (u in c, v in nn(c)) by (d2, v, u) — C7
+// block per component c: closest pair (u in c, v in nn(c)) by (d2, v, u) — C7.
+// The smaller of the two components is staged in shared memory, the threads scan the larger one.
 __global__ void __launch_bounds__(256) k_comp_pair(const float2* __restrict__ kpts, int n, const int* __restrict__ label,
                                                    const int* __restrict__ new_id, const int* __restrict__ comp_of_root,
+                                                   const int* __restrict__ comp_root, const int* __restrict__ comp_size,
                                                    const int* __restrict__ n_comp, const int* __restrict__ cnn,
                                                    int* __restrict__ eu, int* __restrict__ ev, int* __restrict__ evalid,
                                                    int* __restrict__ extra_cnt) {
@@ -614,6 +616,9 @@ __global__ void __launch_bounds__(256) k_comp_pair(const float2* __restrict__ kp
   for (int c = blockIdx.x; c < nc; c += gridDim.x) {
     int j = cnn[c];
     if (j < c && cnn[j] == c) continue;      // (j,c) was connected when j was visited (agc.py:550-552)
+    const bool c_small = comp_size[comp_root[c]] <= comp_size[comp_root[j]];
+    const int cs = c_small ? c : j;          // staged in shared memory
+    const int cl = c_small ? j : c;          // scanned by the threads
     double best = DBL_MAX;
     int bv = 0x7fffffff, bu = 0x7fffffff;
     for (int s0 = 0; s0 < n; s0 += kPairChunk) {
@@ -621,7 +626,7 @@ __global__ void __launch_bounds__(256) k_comp_pair(const float2* __restrict__ kp
       if (threadIdx.x == 0) mem_cnt = 0;
       __syncthreads();
       for (int i = s0 + threadIdx.x; i < min(n, s0 + kPairChunk); i += blockDim.x) {
-        if (new_id[i] >= 0 && comp_of_root[label[i]] == c) {
+        if (new_id[i] >= 0 && comp_of_root[label[i]] == cs) {
           int k = atomicAdd(&mem_cnt, 1);
           mem_id[k] = i;
           mem_p[k] = kpts[i];
@@ -630,12 +635,13 @@ __global__ void __launch_bounds__(256) k_comp_pair(const float2* __restrict__ kp
       __syncthreads();
       int mc = mem_cnt;
       if (mc == 0) continue;
-      for (int v = threadIdx.x; v < n; v += blockDim.x) {
-        if (new_id[v] < 0 || comp_of_root[label[v]] != j) continue;
-        float2 pv = kpts[v];
+      for (int x = threadIdx.x; x < n; x += blockDim.x) {
+        if (new_id[x] < 0 || comp_of_root[label[x]] != cl) continue;
+        float2 px = kpts[x];
         for (int k = 0; k < mc; ++k) {
-          double d = sqdist64(pv, mem_p[k]);
-          int u = mem_id[k];
+          double d = sqdist64(px, mem_p[k]);
+          int u = c_small ? mem_id[k] : x;   // u in component c, v in component j
+          int v = c_small ? x : mem_id[k];
           if (d < best || (d == best && (v < bv || (v == bv && u < bu)))) { best = d; bv = v; bu = u; }
         }
       }
@@ -833,7 +839,8 @@ extern "C" int gims_agc_build(const float* kpts, const float* desc, int desc_cha
   GIMS_LAUNCH_OK();
   k_comp_nn<<<cdiv(n, 8), 256, 0, st>>>(reinterpret_cast<const float2*>(w.cent), n_comp_dev, w.comp_nn);
   GIMS_LAUNCH_OK();
-  k_comp_pair<<<min(n, 296), 256, 0, st>>>(kp, n, w.parent, w.new_id, w.comp_of_root, n_comp_dev, w.comp_nn, w.comp_eu,
+  k_comp_pair<<<min(n, 296), 256, 0, st>>>(kp, n, w.parent, w.new_id, w.comp_of_root, w.comp_root, w.comp_size, n_comp_dev,
+                                           w.comp_nn, w.comp_eu,
                                            w.comp_ev, w.comp_edge_valid, w.extra_cnt);
   GIMS_LAUNCH_OK();
   // a-6

@@ -122,9 +122,7 @@ struct gims_model {
   const float* sage_b[3];
   Wt wqkv[GIMS_MAX_LAYERS];    // [768][256]  Q|K|V rows, head-major
   const float* bqkv[GIMS_MAX_LAYERS];
-  Wt wmerge[GIMS_MAX_LAYERS];  // [256][256]  input columns head-major
-  const float* bmerge[GIMS_MAX_LAYERS];
-  Wt w1[GIMS_MAX_LAYERS];      // [512][512]  BN folded, input = [x | message]
+  Wt w1[GIMS_MAX_LAYERS];      // [512][512]  BN folded, `merge` composed in: input = [x | attention output]
   const float* b1[GIMS_MAX_LAYERS];
   Wt w2[GIMS_MAX_LAYERS];      // [256][512]
   const float* b2[GIMS_MAX_LAYERS];
@@ -148,7 +146,7 @@ extern "C" int gims_get_gemm_mode(void) { return g_gemm_mode.load(); }
 extern "C" int gims_packed_blob_count(const gims_config* c) {
   if (!c) return -1;
   // every weight matrix contributes 3 blobs (W, W_hi, W_lo), every bias 1
-  return 1 + 4 * c->kenc_num + 4 * 3 + 16 * c->num_layers + 4;
+  return 1 + 4 * c->kenc_num + 4 * 3 + 12 * c->num_layers + 4;
 }
 
 extern "C" int gims_model_create(const gims_config* c, const float* packed, const int64_t* off, int n_off,
@@ -172,7 +170,7 @@ extern "C" int gims_model_create(const gims_config* c, const float* packed, cons
   for (int i = 0; i < c->kenc_num; ++i) { m->kenc_w[i] = next_w(); m->kenc_b[i] = next(); }
   for (int i = 0; i < 3; ++i) { m->sage_w[i] = next_w(); m->sage_b[i] = next(); }
   for (int l = 0; l < c->num_layers; ++l) {
-    m->wqkv[l] = next_w(); m->bqkv[l] = next(); m->wmerge[l] = next_w(); m->bmerge[l] = next();
+    m->wqkv[l] = next_w(); m->bqkv[l] = next();
     m->w1[l] = next_w(); m->b1[l] = next(); m->w2[l] = next_w(); m->b2[l] = next();
   }
   m->wfinal = next_w(); m->bfinal = next();
@@ -272,8 +270,8 @@ extern "C" int gims_attn_layer_forward(const gims_model* m, int layer, float* de
     GIMS_TRY(gemm(desc, kD, kD, nullptr, 0, 0, m->wqkv[layer], m->bqkv[layer], nullptr, 0, qkv, 3 * kD, 3 * kD, 0, s, st));
     GIMS_TRY(launch_attention(qkv, att, n0_max, n1_max, n_dev, m->cfg.layer_is_cross[layer], st));
   }
-  GIMS_TRY(gemm(att, kD, kD, nullptr, 0, 0, m->wmerge[layer], m->bmerge[layer], nullptr, 0, msg, kD, kD, 0, s, st));
-  GIMS_TRY(gemm(desc, kD, kD, msg, kD, kD, m->w1[layer], m->b1[layer], nullptr, 0, hid, 2 * kD, 2 * kD, 1, s, st));
+  (void)msg;   // the merge conv is composed into W1 at pack time
+  GIMS_TRY(gemm(desc, kD, kD, att, kD, kD, m->w1[layer], m->b1[layer], nullptr, 0, hid, 2 * kD, 2 * kD, 1, s, st));
   GIMS_TRY(gemm(hid, 2 * kD, 2 * kD, nullptr, 0, 0, m->w2[layer], m->b2[layer], desc, kD, desc, kD, kD, 0, s, st));
   return GIMS_OK;
 }

@@ -5,7 +5,7 @@ Done once at load time, in float64 then rounded to fp32:
         s = gamma / sqrt(running_var + eps);  W' = s[:,None] * W;  b' = (b - running_mean) * s + beta
   * attention heads de-interleaved: the reference views channels as (dim=64, heads=4), i.e. channel
     c = d*4 + h (gmatcher.py:108-111); packed channel c' = h*64 + d, applied to the output rows of
-    proj[0..2] and to the input columns of `merge`
+    proj[0..2] and to the input columns of `merge` (which is then composed into the first MLP conv)
   * proj[0] | proj[1] | proj[2] stacked into one [768][256] matrix (Q | K | V)
   * SAGEConv layer 0 (in > out: fc_neigh before aggregation) stacked as rows [fc_neigh; fc_self];
     layers 1, 2 stacked along K as [fc_self | fc_neigh] acting on cat[h, mean_neigh(h)]
@@ -16,7 +16,7 @@ Done once at load time, in float64 then rounded to fp32:
 
 Blob order (== offsets passed to gims_model_create); each matrix W stands for three blobs W, W_hi, W_lo:
   bin_score, (kenc W_i, b_i) for every kenc conv, (sage W_l, b_l) l=0..2,
-  per attention layer: Wqkv, bqkv, Wmerge, bmerge, W1, b1, W2, b2; final_proj W, b.
+  per attention layer: Wqkv, bqkv, W1 (merge composed in, BN folded), b1, W2, b2; final_proj W, b.
 """
 import torch
 
@@ -89,9 +89,15 @@ def pack_state_dict(sd, config=None):
         bq = [sd['%s.attn.proj.%d.bias' % (p, j)].double()[perm] for j in range(3)]
         add('l%d.wqkv' % l, torch.cat(wq, 0))
         add('l%d.bqkv' % l, torch.cat(bq, 0))
-        add('l%d.wmerge' % l, sd[p + '.attn.merge.weight'].double().squeeze(-1)[:, perm])
-        add('l%d.bmerge' % l, sd[p + '.attn.merge.bias'].double())
-        w1, b1 = _fold_bn(sd[p + '.mlp.0.weight'].double().squeeze(-1), sd[p + '.mlp.0.bias'].double(), sd, p + '.mlp.1')
+        # `merge` (Conv1d on the attention output, gmatcher.py:114) is linear and feeds only the first MLP conv
+        # (gmatcher.py:125): it is composed into that conv here, in fp64 —
+        #   W1 [x | merge(att)] + b1 = [W1x | W1m Wm] [x | att] + (b1 + W1m bm)
+        wm = sd[p + '.attn.merge.weight'].double().squeeze(-1)[:, perm]
+        bm = sd[p + '.attn.merge.bias'].double()
+        w1_raw, b1_raw = sd[p + '.mlp.0.weight'].double().squeeze(-1), sd[p + '.mlp.0.bias'].double()
+        w1_raw = torch.cat([w1_raw[:, :d], w1_raw[:, d:] @ wm], 1)
+        b1_raw = b1_raw + sd[p + '.mlp.0.weight'].double().squeeze(-1)[:, d:] @ bm
+        w1, b1 = _fold_bn(w1_raw, b1_raw, sd, p + '.mlp.1')
         add('l%d.w1' % l, w1)
         add('l%d.b1' % l, b1)
         add('l%d.w2' % l, sd[p + '.mlp.3.weight'].double().squeeze(-1))

@@ -37,7 +37,7 @@ def test_host_queries(lib):
     from gims_b200 import GMatcher
     m = GMatcher({})
     c = m.c_config()
-    assert lib.gims_packed_blob_count(C.byref(c)) == 1 + 4 * 5 + 4 * 3 + 16 * 18 + 4
+    assert lib.gims_packed_blob_count(C.byref(c)) == 1 + 4 * 5 + 4 * 3 + 12 * 18 + 4
     assert [c.layer_is_cross[i] for i in range(4)] == [0, 1, 0, 1]
     assert [c.kenc_dims[i] for i in range(6)] == [2, 32, 64, 128, 256, 256]
 
@@ -104,8 +104,8 @@ def test_packing_equals_oracle_layer():
         sl = slice(h * 64, (h + 1) * 64)
         p = torch.softmax(q[:, sl] @ k[:, sl].t() / 8.0, dim=-1)
         att[:, sl] = p @ v[:, sl]
-    msg = att @ blob['l3.wmerge'][:65536].view(256, 256).t() + blob['l3.bmerge'][:256]
-    hid = F.relu(torch.cat([x, msg], 1) @ blob['l3.w1'][:512 * 512].view(512, 512).t() + blob['l3.b1'][:512])
+    # the merge conv is composed into w1 at pack time: w1 acts on [x | attention output]
+    hid = F.relu(torch.cat([x, att], 1) @ blob['l3.w1'][:512 * 512].view(512, 512).t() + blob['l3.b1'][:512])
     delta = hid @ blob['l3.w2'][:256 * 512].view(256, 512).t() + blob['l3.b2'][:256]
     want = orc.attn_propagation(sd, l, x.t()[None], src.t()[None])[0].t()
     assert torch.allclose(delta, want, rtol=1e-4, atol=1e-5)
