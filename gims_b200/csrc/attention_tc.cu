@@ -8,10 +8,23 @@
 //   Kp [2][rows][256]   hi / lo planes of k
 //   Vt [2][256][ldv]    hi / lo planes of v, TRANSPOSED (channel-major) so that PV's B operand is K-major
 // One CTA = 128 queries of one head of one image; 192 threads:
-//   warp 0      TMA: Q tile once, then K / Vt tiles of 64 keys through a 2-stage ring
-//   warp 1      one thread issues tcgen05.mma:  S = Q K^T (SS, 3 products),  PV = P V (TS: P read from TMEM)
-//   warps 2..5  softmax: tcgen05.ld S -> online max / exp2 / sum in fp32 -> P split into tf32 hi / lo ->
-//               tcgen05.st into TMEM -> after the PV MMAs: O = O * alpha + PV in registers (fp32, RN)
+//   warps 0..3  one thread per query row: put the Q planes into TMEM once; per 64-key tile tcgen05.ld S ->
+//               online max / ex2 / sum in fp32 -> fold the previous PV tile into register accumulators
+//               (O = O * alpha + PV, fp32 RN) -> P split into tf32 hi / lo -> tcgen05.st into TMEM
+//   warp 4      TMA: K and Vt tiles of 64 keys through two 3-stage rings (K is released right after S = Q K^T)
+//   warp 5      one thread issues the S = Q K^T MMAs, warp 6 one thread the PV = P V MMAs (A operand in TMEM, TS form);
+//               two issuers because every barrier wait / commit of a single issuer drained the tensor pipe
+//               (~1000 of 3500 cycles per tile): now one of them is issuing while the other one synchronises
+//
+// Why Q lives in TMEM: at N = 64 an SS-form MMA already saturates the 128 B/clk shared-memory port with its own
+// operand reads (4 KB of A + 2 KB of B per 48 clk, tools/micro/mma_rate.cu); with the TMA writes of the K/V ring on
+// top, the QK phase ran at 67-85 clk per MMA (profiles/r01_attention_pipeline_trace.txt).  Reading A from TMEM
+// leaves shared memory to the K / Vt tiles alone.
+//
+// TMEM columns: S[2] 64 each | P_hi 64 | P_lo 64 | PV 64 | Q_hi 64 | Q_lo 64.  Each S / PV accumulator receives the
+// 16 small correction products of its tile FIRST and the 8 hi*hi products last: the tensor core rounds the accumulator
+// toward zero at every step, and this order keeps those roundings at the magnitude of the small terms for as long as
+// possible (same error as a separate correction accumulator, without its TMEM columns and the extra add).
 #include <math_constants.h>
 
 #include "common.cuh"
@@ -26,34 +39,21 @@ using namespace tc;
 constexpr int TQ = 128;        // queries per CTA (UMMA M)
 constexpr int TKV = 64;        // keys per tile (UMMA N of S, K of PV)
 constexpr int HD = 64;         // head dim
-constexpr int kStagesKV = 2;   // K and Vt travel through separate 2-stage rings (K is released right after S = QK^T)
-constexpr int kBoxBytesQ = TQ * 32 * 4;       // 16 KB: 128 rows x 32 floats
-constexpr int kBoxBytesKV = TKV * 32 * 4;     // 8 KB: 64 rows x 32 floats
-constexpr int kQBytes = 4 * kBoxBytesQ;       // hi{d0-31,d32-63}, lo{...}
-constexpr int kKStageBytes = 4 * kBoxBytesKV;   // K hi(2) lo(2)   (same size for Vt)
-constexpr int kAttnSmem = kQBytes + 2 * kStagesKV * kKStageBytes + 1024 + 256;
-constexpr int kAttnThreads = 192;
+constexpr int kStagesKV = 3;
+constexpr int kBoxBytesKV = TKV * 32 * 4;       // 8 KB: 64 rows x 32 floats
+constexpr int kKStageBytes = 4 * kBoxBytesKV;   // hi(2 boxes) lo(2 boxes); same size for K and Vt
+constexpr int kAttnSmem = 2 * kStagesKV * kKStageBytes + 1024 + 256;
+constexpr int kAttnThreads = 224;
 
-// TMEM columns (all 512 in use): S[2] 64 each | P[2] = (hi 64 | lo 64) each | PV[2] 64 each.
-// Each S / PV accumulator receives the 16 small correction products of its tile FIRST and the 8 hi*hi products
-// last: the tensor core rounds the accumulator toward zero at every step, and this order keeps those roundings at
-// the magnitude of the small terms for as long as possible (same error as a separate correction accumulator,
-// without its TMEM columns and the extra add).
-__device__ __forceinline__ constexpr int cS(int b) { return b * 64; }
-__device__ __forceinline__ constexpr int cPh(int b) { return 128 + b * 128; }
-__device__ __forceinline__ constexpr int cPl(int b) { return 192 + b * 128; }
-__device__ __forceinline__ constexpr int cO(int b) { return 384 + b * 64; }
+constexpr int cS0 = 0, cPh = 128, cPl = 192, cO = 256, cQh = 320, cQl = 384;
 
 // Optional pipeline trace (bring-up / profiling): CTA (0,0,0) stores clock64() stamps per tile.
 //   [j*8+0] MMA: QK(j+1) issue start   [j*8+1] MMA: PV(j) operands ready   [j*8+2] MMA: PV(j) issued
-//   [j*8+4] softmax warp 2: S(j) observed   [j*8+5] P(j) handed over   [j*8+6] fold of PV(j-1) done
+//   [j*8+3] softmax warp 0: P(j) handed over   [j*8+4] softmax warp 0: S(j) observed
 __device__ long long* g_attn_trace = nullptr;
-#define ATTN_TRACE(slot)                                                                       \
-  do {                                                                                         \
-    if (trace) trace[j * 8 + (slot)] = clock64();                                              \
-  } while (0)
 
 struct AttnTcArgs {
+  const float* qp;            // Q planes (read directly by the softmax warps)
   float* out;                 // [rows][256]
   Segs segs;
   int cross;
@@ -91,12 +91,12 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-// Pipeline (per 64-key tile j):  QK(j+1) is issued before PV(j), so the tensor core computes the next score tile
-// while the softmax warps work on tile j; the softmax warps fold PV(j-1) into their register accumulators after
-// they have handed P(j) to the tensor core.  S, P and PV are all double-buffered in TMEM.
+// Pipeline: iteration jq of the MMA thread issues QK(jq) and then PV(jq-1), so the tensor core computes the next score
+// tile while the softmax warps work on the current one.  S is double-buffered; P and PV are single-buffered — their
+// reuse is ordered by p_full / o_full: the softmax warps fold PV(j-1) out of TMEM (which also proves that P(j-1) has
+// been consumed) before they store P(j).
 __global__ void __launch_bounds__(kAttnThreads, 1)
-k_attention_tc(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__ CUtensorMap mapK,
-               const __grid_constant__ CUtensorMap mapVt, AttnTcArgs a) {
+k_attention_tc(const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapVt, AttnTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
   const int img = blockIdx.z, head = blockIdx.y;
   const int src = a.cross ? 1 - img : img;
@@ -111,37 +111,35 @@ k_attention_tc(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
   const int ntiles = (nk + TKV - 1) / TKV;
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* q_smem = smem;
-  uint8_t* k_smem = smem + kQBytes;
+  uint8_t* k_smem = smem;
   uint8_t* v_smem = k_smem + kStagesKV * kKStageBytes;
   uint64_t* bars = reinterpret_cast<uint64_t*>(v_smem + kStagesKV * kKStageBytes);
-  uint64_t* q_full = bars;                 // 1
-  uint64_t* k_full = bars + 1;             // [2] TMA -> MMA
-  uint64_t* k_empty = bars + 3;            // [2] QK MMAs retired (tcgen05.commit)
-  uint64_t* v_full = bars + 5;             // [2]
-  uint64_t* v_empty = bars + 7;            // [2] PV MMAs retired
-  uint64_t* s_full = bars + 9;             // [2] S buffer written (commit)
-  uint64_t* s_free = bars + 11;            // [2] S buffer read by the softmax warps (4 arrivals)
-  uint64_t* p_full = bars + 13;            // [2] P buffer written by the softmax warps (4 arrivals)
-  uint64_t* o_full = bars + 15;            // [2] PV buffer written (commit); also: P buffer consumed
-  uint64_t* o_free = bars + 17;            // [2] PV buffer folded by the softmax warps (4 arrivals)
+  uint64_t* k_full = bars;                       // [3] TMA -> MMA
+  uint64_t* k_empty = bars + 3;                  // [3] QK MMAs retired (tcgen05.commit)
+  uint64_t* v_full = bars + 6;                   // [3]
+  uint64_t* v_empty = bars + 9;                  // [3] PV MMAs retired
+  uint64_t* s_full = bars + 12;                  // [2] S buffer written (commit)
+  uint64_t* p_full = bars + 14;                  // P written, previous PV folded (4 arrivals)
+  uint64_t* o_full = bars + 15;                  // PV written (commit)
+  uint64_t* q_ready = bars + 16;                 // Q planes stored into TMEM (4 arrivals)
+  uint64_t* s_free = bars + 17;                  // [2] S buffer read by the softmax warps (4 arrivals)
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 19);
 
-  // Warp roles: 0..3 = data warps (TMEM lane quarter = warp), 4 = TMA producer, 5 = MMA issuer.  The issuer gets
-  // the highest warp id on its scheduler: the arbiter favours high warp ids, and a starved issuer starves the tensor pipe.
+  // Warp roles: 0..3 = data warps (TMEM lane quarter = warp), 4 = TMA producer, 5 = QK issuer, 6 = PV issuer.
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int kWarpTma = 4, kWarpMma = 5;
+  constexpr int kWarpTma = 4, kWarpMma = 5, kWarpPv = 6;
   if (warp == kWarpTma && lane == 0) {
-    tma_prefetch_desc(&mapQ);
     tma_prefetch_desc(&mapK);
     tma_prefetch_desc(&mapVt);
-    mbar_init(q_full, 1);
-    for (int s = 0; s < 2; ++s) {
+    for (int s = 0; s < kStagesKV; ++s) {
       mbar_init(&k_full[s], 1); mbar_init(&k_empty[s], 1);
       mbar_init(&v_full[s], 1); mbar_init(&v_empty[s], 1);
-      mbar_init(&s_full[s], 1); mbar_init(&s_free[s], 4);
-      mbar_init(&p_full[s], 4); mbar_init(&o_full[s], 1); mbar_init(&o_free[s], 4);
     }
+    mbar_init(&s_full[0], 1); mbar_init(&s_full[1], 1);
+    mbar_init(&s_free[0], 4); mbar_init(&s_free[1], 4);
+    mbar_init(p_full, 4);
+    mbar_init(o_full, 1);
+    mbar_init(q_ready, 4);
     fence_barrier_init();
   }
   if (warp == kWarpMma) tmem_alloc<512>(tmem_slot);
@@ -151,183 +149,193 @@ k_attention_tc(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
   const uint32_t tmem = __shfl_sync(0xffffffffu, *tmem_slot, 0);      // warp-uniform for the compiler
 
   if (threadIdx.x == kWarpTma * 32) {
-    {
-      // Q planes: rows [qrow0, +128) of plane 0 (hi) and plane 1 (lo, row offset rows_total), channels head*64..+64
-      mbar_arrive_expect_tx(q_full, kQBytes);
+    // ===== TMA producer =====
+    int s = 0; uint32_t ph = 0;
+    for (int j = 0; j < ntiles; ++j) {
+      const int key0 = krow0 + j * TKV;                       // row in the K planes
+      const int vcol0 = (src ? a.vbase1 : 0) + j * TKV;       // key column in the Vt planes (multiple of 64)
+      mbar_wait(&k_empty[s], ph ^ 1);
+      mbar_arrive_expect_tx(&k_full[s], kKStageBytes);
       for (int pl = 0; pl < 2; ++pl)
-        for (int hf = 0; hf < 2; ++hf)
-          tma_load_2d(q_smem + (pl * 2 + hf) * kBoxBytesQ, &mapQ, q_full, head * HD + hf * 32, pl * a.rows_total + qrow0);
-      for (int j = 0; j < ntiles; ++j) {
-        const int s = j & 1;
-        const uint32_t ph = (uint32_t)(j >> 1) & 1u;
-        const int key0 = krow0 + j * TKV;                       // row in the K planes
-        const int vcol0 = (src ? a.vbase1 : 0) + j * TKV;       // key column in the Vt planes (multiple of 64)
-        mbar_wait(&k_empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&k_full[s], kKStageBytes);
-        for (int pl = 0; pl < 2; ++pl)
-          for (int hf = 0; hf < 2; ++hf)      // K box: 64 keys x 32 channels
-            tma_load_2d(k_smem + s * kKStageBytes + (pl * 2 + hf) * kBoxBytesKV, &mapK, &k_full[s], head * HD + hf * 32,
-                        pl * a.rows_total + key0);
-        mbar_wait(&v_empty[s], ph ^ 1);
-        mbar_arrive_expect_tx(&v_full[s], kKStageBytes);
-        for (int pl = 0; pl < 2; ++pl)
-          for (int hf = 0; hf < 2; ++hf)      // Vt box: 64 channels x 32 keys
-            tma_load_2d(v_smem + s * kKStageBytes + (pl * 2 + hf) * kBoxBytesKV, &mapVt, &v_full[s], vcol0 + hf * 32,
-                        pl * kD + head * HD);
-      }
+        for (int hf = 0; hf < 2; ++hf)      // K box: 64 keys x 32 channels
+          tma_load_2d(k_smem + s * kKStageBytes + (pl * 2 + hf) * kBoxBytesKV, &mapK, &k_full[s], head * HD + hf * 32,
+                      pl * a.rows_total + key0);
+      mbar_wait(&v_empty[s], ph ^ 1);
+      mbar_arrive_expect_tx(&v_full[s], kKStageBytes);
+      for (int pl = 0; pl < 2; ++pl)
+        for (int hf = 0; hf < 2; ++hf)      // Vt box: 64 channels x 32 keys
+          tma_load_2d(v_smem + s * kKStageBytes + (pl * 2 + hf) * kBoxBytesKV, &mapVt, &v_full[s], vcol0 + hf * 32,
+                      pl * kD + head * HD);
+      if (++s == kStagesKV) { s = 0; ph ^= 1; }
     }
   } else if (threadIdx.x == kWarpMma * 32) {
-    // ===== MMA issuer: ONE thread, written so that all operand arithmetic stays in the uniform datapath
-    // (descriptor = base + constant; no arrays, no lambdas) — an issuer that needs R2UR moves per operand
-    // cannot keep the tensor pipe fed.
-    constexpr uint32_t idesc = umma_idesc_tf32(TQ, TKV);      // M=128, N=64 for both S and PV
-    const uint64_t dq_hi = umma_desc_sw128(smem_u32(q_smem)), dq_lo = dq_hi + ((2 * kBoxBytesQ) >> 4);
-    const uint64_t dk0 = umma_desc_sw128(smem_u32(k_smem)), dv0 = umma_desc_sw128(smem_u32(v_smem));
+    // ===== QK issuer: ONE thread, all operand arithmetic in the uniform datapath (descriptor = base + constant) =====
+    constexpr uint32_t idesc = umma_idesc_tf32(TQ, TKV);      // M=128, N=64
+    const uint64_t dk0 = umma_desc_sw128(smem_u32(k_smem));
+    const uint32_t q_hi = tmem + cQh, q_lo = tmem + cQl;
     long long* trace = (blockIdx.x | blockIdx.y | blockIdx.z) == 0 ? g_attn_trace : nullptr;
-    mbar_wait(q_full, 0);
-    // software pipeline: iteration jq issues QK(jq) and then PV(jq-1)
-    for (int jq = 0; jq <= ntiles; ++jq) {
-      const int j = jq - 1;                                    // tile whose PV is issued in this iteration
-      if (trace && j >= 0) trace[j * 8 + 0] = clock64();
-      if (jq < ntiles) {
-        const int s = jq & 1;
-        const uint32_t ph = (uint32_t)(jq >> 1) & 1u;
-        mbar_wait(&k_full[s], ph);
-        if (jq >= 2) mbar_wait(&s_free[s], ph ^ 1);            // softmax warps have read S(jq-2) out of this buffer
-        tcgen05_fence_after();
-        const uint64_t kh = dk0 + (uint64_t)(s * (kKStageBytes >> 4)), kl = kh + ((2 * kBoxBytesKV) >> 4);
-        const uint32_t sacc = tmem + s * 64;
-        // K-dim = 64 channels = 2 boxes x 4 k-steps; corrections first, hi*hi last
+    mbar_wait(q_ready, 0);
+    int sk = 0; uint32_t phk = 0;
+    for (int jq = 0; jq < ntiles; ++jq) {
+      if (trace) trace[jq * 8 + 0] = clock64();
+      mbar_wait(&k_full[sk], phk);
+      if (jq >= 2) mbar_wait(&s_free[jq & 1], (uint32_t)((jq >> 1) - 1) & 1u);   // S(jq-2) has been read out of this buffer
+      tcgen05_fence_after();
+      if (trace) trace[jq * 8 + 7] = clock64();
+      const uint64_t kh = dk0 + (uint64_t)(sk * (kKStageBytes >> 4)), kl = kh + ((2 * kBoxBytesKV) >> 4);
+      const uint32_t sacc = tmem + cS0 + (jq & 1) * 64;
+      // K-dim = 64 channels = 2 boxes x 4 k-steps (8 TMEM columns of Q each); corrections first, hi*hi last
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t qoff = ((ks >> 2) * kBoxBytesQ + (ks & 3) * 32) >> 4, koff = ((ks >> 2) * kBoxBytesKV + (ks & 3) * 32) >> 4;
-          umma_tf32_ss(sacc, dq_lo + qoff, kh + koff, idesc, ks ? 1u : 0u);
-          umma_tf32_ss(sacc, dq_hi + qoff, kl + koff, idesc, 1u);
-        }
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t qoff = ((ks >> 2) * kBoxBytesQ + (ks & 3) * 32) >> 4, koff = ((ks >> 2) * kBoxBytesKV + (ks & 3) * 32) >> 4;
-          umma_tf32_ss(sacc, dq_hi + qoff, kh + koff, idesc, 1u);
-        }
-        umma_commit(&k_empty[s]);
-        umma_commit(&s_full[s]);
+      for (int ks = 0; ks < 8; ++ks) {
+        const uint64_t koff = ((ks >> 2) * kBoxBytesKV + (ks & 3) * 32) >> 4;
+        umma_tf32_ts(sacc, q_lo + ks * 8, kh + koff, idesc, ks ? 1u : 0u);
+        umma_tf32_ts(sacc, q_hi + ks * 8, kl + koff, idesc, 1u);
       }
-      if (j >= 0) {
-        const int s = j & 1;
-        const uint32_t ph = (uint32_t)(j >> 1) & 1u;
-        mbar_wait(&v_full[s], ph);
-        mbar_wait(&p_full[s], ph);                             // P(j) is in TMEM
-        if (j >= 2) mbar_wait(&o_free[s], ph ^ 1);             // PV(j-2) has been folded out of this buffer
-        tcgen05_fence_after();
-        if (trace) trace[j * 8 + 1] = clock64();
-        const uint64_t vh = dv0 + (uint64_t)(s * (kKStageBytes >> 4)), vl = vh + ((2 * kBoxBytesKV) >> 4);
-        const uint32_t oacc = tmem + 384 + s * 64, p_hi = tmem + 128 + s * 128, p_lo = p_hi + 64;
-        // K-dim = 64 keys = 2 Vt boxes x 4 k-steps; A (P planes) from TMEM, 8 columns per k-step
 #pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t voff = ((ks >> 2) * kBoxBytesKV + (ks & 3) * 32) >> 4;
-          umma_tf32_ts(oacc, p_lo + ks * 8, vh + voff, idesc, ks ? 1u : 0u);
-          umma_tf32_ts(oacc, p_hi + ks * 8, vl + voff, idesc, 1u);
-        }
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) {
-          const uint64_t voff = ((ks >> 2) * kBoxBytesKV + (ks & 3) * 32) >> 4;
-          umma_tf32_ts(oacc, p_hi + ks * 8, vh + voff, idesc, 1u);
-        }
-        umma_commit(&v_empty[s]);
-        umma_commit(&o_full[s]);
-        if (trace) trace[j * 8 + 2] = clock64();
+      for (int ks = 0; ks < 8; ++ks) {
+        const uint64_t koff = ((ks >> 2) * kBoxBytesKV + (ks & 3) * 32) >> 4;
+        umma_tf32_ts(sacc, q_hi + ks * 8, kh + koff, idesc, 1u);
       }
+      if (trace) trace[jq * 8 + 6] = clock64();
+      umma_commit(&k_empty[sk]);
+      umma_commit(&s_full[jq & 1]);
+      if (++sk == kStagesKV) { sk = 0; phk ^= 1; }
+    }
+  } else if (threadIdx.x == kWarpPv * 32) {
+    // ===== PV issuer =====
+    constexpr uint32_t idesc = umma_idesc_tf32(TQ, TKV);      // M=128, N=64
+    const uint64_t dv0 = umma_desc_sw128(smem_u32(v_smem));
+    const uint32_t p_hi = tmem + cPh, p_lo = tmem + cPl, oacc = tmem + cO;
+    long long* trace = (blockIdx.x | blockIdx.y | blockIdx.z) == 0 ? g_attn_trace : nullptr;
+    int sv = 0; uint32_t phv = 0;
+    for (int j = 0; j < ntiles; ++j) {
+      mbar_wait(&v_full[sv], phv);
+      mbar_wait(p_full, j & 1);                                // P(j) is in TMEM, PV(j-1) has been folded away
+      tcgen05_fence_after();
+      if (trace) trace[j * 8 + 1] = clock64();
+      const uint64_t vh = dv0 + (uint64_t)(sv * (kKStageBytes >> 4)), vl = vh + ((2 * kBoxBytesKV) >> 4);
+      // K-dim = 64 keys = 2 Vt boxes x 4 k-steps; A (P planes) from TMEM, 8 columns per k-step
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const uint64_t voff = ((ks >> 2) * kBoxBytesKV + (ks & 3) * 32) >> 4;
+        umma_tf32_ts(oacc, p_lo + ks * 8, vh + voff, idesc, ks ? 1u : 0u);
+        umma_tf32_ts(oacc, p_hi + ks * 8, vl + voff, idesc, 1u);
+      }
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const uint64_t voff = ((ks >> 2) * kBoxBytesKV + (ks & 3) * 32) >> 4;
+        umma_tf32_ts(oacc, p_hi + ks * 8, vh + voff, idesc, 1u);
+      }
+      umma_commit(&v_empty[sv]);
+      umma_commit(o_full);
+      if (trace) trace[j * 8 + 2] = clock64();
+      if (++sv == kStagesKV) { sv = 0; phv ^= 1; }
     }
   } else if (warp < 4) {
     // ===== softmax / accumulate warps: thread <-> query row =====
-    const int q = warp & 3;
-    const uint32_t lane_base = tmem + ((uint32_t)(32 * q) << 16);
-    const int row = q0 + 32 * q + lane;
-    float o[HD];
+    const uint32_t lane_base = tmem + ((uint32_t)(32 * warp) << 16);
+    const int row = q0 + 32 * warp + lane;
+    {   // Q planes of my row -> TMEM (zeros for rows past the live count: nothing of them is ever stored)
+      const float* qsrc = a.qp + (size_t)(qrow0 + 32 * warp + lane) * kD + head * HD;
 #pragma unroll
-    for (int d = 0; d < HD; ++d) o[d] = 0.f;
-    float m_run = -CUDART_INF_F, l_run = 0.f, alpha_prev = 0.f;
-    auto fold_pv = [&](int jj, float alpha) {                  // O = O * alpha + PV(jj)
-      const int b = jj & 1;
-      mbar_wait(&o_full[b], (uint32_t)(jj >> 1) & 1u);
-      tcgen05_fence_after();
+      for (int pl = 0; pl < 2; ++pl) {
+        const float4* p4 = reinterpret_cast<const float4*>(qsrc + (size_t)pl * a.rows_total * kD);
 #pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t v[32];
-        tmem_ld_32x32(lane_base + cO(b) + h * 32, v);
-        tmem_ld_wait();
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[32];
 #pragma unroll
-        for (int i = 0; i < 32; ++i) o[h * 32 + i] = fmaf(o[h * 32 + i], alpha, __uint_as_float(v[i]));
-      }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&o_free[b]);
-    };
-    long long* trace = ((blockIdx.x | blockIdx.y | blockIdx.z) == 0 && lane == 0) ? g_attn_trace : nullptr;
-    const int tw = warp;   // trace: slots 4 (S seen, warp 0), 3/5/6/7 (P handed over by warps 0..3)
-    for (int j = 0; j < ntiles; ++j) {
-      const int sb = j & 1;
-      const uint32_t ph = (uint32_t)(j >> 1) & 1u;
-      mbar_wait(&s_full[sb], ph);
-      tcgen05_fence_after();
-      if (tw == 0) ATTN_TRACE(4);
-      float s[TKV];                                      // scores in the log2 domain (Q was scaled by log2(e)/8)
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t v[32];
-        tmem_ld_32x32(lane_base + cS(sb) + h * 32, v);
-        tmem_ld_wait();
-#pragma unroll
-        for (int i = 0; i < 32; ++i) s[h * 32 + i] = __uint_as_float(v[i]);
-      }
-      tcgen05_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(&s_free[sb]);           // the tensor core may overwrite this S buffer (tile j+2)
-      const int valid = nk - j * TKV;                    // keys of this tile that exist
-      if (valid < TKV) {
-#pragma unroll
-        for (int i = 0; i < TKV; ++i)
-          if (i >= valid) s[i] = -CUDART_INF_F;
-      }
-      float mx = s[0];
-#pragma unroll
-      for (int i = 1; i < TKV; ++i) mx = fmaxf(mx, s[i]);
-      const float m_new = fmaxf(m_run, mx);
-      const float alpha = ex2_approx(m_run - m_new);
-      float rs0 = 0.f, rs1 = 0.f;
-#pragma unroll
-      for (int i = 0; i < TKV; i += 2) {
-        s[i] = ex2_approx(s[i] - m_new);
-        s[i + 1] = ex2_approx(s[i + 1] - m_new);
-        rs0 += s[i];
-        rs1 += s[i + 1];
-      }
-      l_run = l_run * alpha + (rs0 + rs1);
-      m_run = m_new;
-      // P(j) -> TMEM buffer sb; that buffer was last read by PV(j-2), whose completion we observed when folding it
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        uint32_t ph_[32], pl_[32];
-#pragma unroll
-        for (int i = 0; i < 32; ++i) {
-          float hi, lo;
-          split_tf32(s[h * 32 + i], hi, lo);
-          ph_[i] = __float_as_uint(hi);
-          pl_[i] = __float_as_uint(lo);
+          for (int i = 0; i < 8; ++i) {
+            float4 x = (row < nq) ? p4[h * 8 + i] : make_float4(0.f, 0.f, 0.f, 0.f);
+            v[4 * i] = __float_as_uint(x.x); v[4 * i + 1] = __float_as_uint(x.y);
+            v[4 * i + 2] = __float_as_uint(x.z); v[4 * i + 3] = __float_as_uint(x.w);
+          }
+          tmem_st_32x32(lane_base + (pl ? cQl : cQh) + h * 32, v);
         }
-        tmem_st_32x32(lane_base + cPh(sb) + h * 32, ph_);
-        tmem_st_32x32(lane_base + cPl(sb) + h * 32, pl_);
       }
       tmem_st_wait();
       tcgen05_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&p_full[sb]);
-      if (tw == 0) ATTN_TRACE(3);
-      if (j > 0) fold_pv(j - 1, alpha_prev);             // overlaps PV(j) / QK(j+1) on the tensor core
-      alpha_prev = alpha;
+      if (lane == 0) mbar_arrive(q_ready);
     }
-    fold_pv(ntiles - 1, alpha_prev);
+    float o[HD];
+#pragma unroll
+    for (int d = 0; d < HD; ++d) o[d] = 0.f;
+    float m_run = -CUDART_INF_F, l_run = 0.f, alpha_prev = 0.f;
+    long long* trace = ((blockIdx.x | blockIdx.y | blockIdx.z) == 0 && threadIdx.x == 0) ? g_attn_trace : nullptr;
+    for (int j = 0; j <= ntiles; ++j) {
+      float s[TKV];                                      // scores in the log2 domain (Q was scaled by log2(e)/8)
+      float alpha = 0.f;
+      if (j < ntiles) {
+        mbar_wait(&s_full[j & 1], (uint32_t)(j >> 1) & 1u);
+        tcgen05_fence_after();
+        if (trace) trace[j * 8 + 4] = clock64();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[32];
+          tmem_ld_32x32(lane_base + cS0 + (j & 1) * 64 + h * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) s[h * 32 + i] = __uint_as_float(v[i]);
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&s_free[j & 1]);      // the tensor core may overwrite this S buffer (tile j+2)
+        const int valid = nk - j * TKV;                  // keys of this tile that exist
+        if (valid < TKV) {
+#pragma unroll
+          for (int i = 0; i < TKV; ++i)
+            if (i >= valid) s[i] = -CUDART_INF_F;
+        }
+        float mx = s[0];
+#pragma unroll
+        for (int i = 1; i < TKV; ++i) mx = fmaxf(mx, s[i]);
+        const float m_new = fmaxf(m_run, mx);
+        alpha = ex2_approx(m_run - m_new);
+        float rs0 = 0.f, rs1 = 0.f;
+#pragma unroll
+        for (int i = 0; i < TKV; i += 2) {
+          s[i] = ex2_approx(s[i] - m_new);
+          s[i + 1] = ex2_approx(s[i + 1] - m_new);
+          rs0 += s[i];
+          rs1 += s[i + 1];
+        }
+        l_run = l_run * alpha + (rs0 + rs1);
+        m_run = m_new;
+      }
+      if (j > 0) {                                       // fold PV(j-1): O = O * alpha(j-1) + PV; frees P and PV
+        mbar_wait(o_full, (uint32_t)(j - 1) & 1u);
+        tcgen05_fence_after();
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[32];
+          tmem_ld_32x32(lane_base + cO + h * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[h * 32 + i] = fmaf(o[h * 32 + i], alpha_prev, __uint_as_float(v[i]));
+        }
+      }
+      alpha_prev = alpha;
+      if (j < ntiles) {
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t ph_[32], pl_[32];
+#pragma unroll
+          for (int i = 0; i < 32; ++i) {
+            float hi, lo;
+            split_tf32(s[h * 32 + i], hi, lo);
+            ph_[i] = __float_as_uint(hi);
+            pl_[i] = __float_as_uint(lo);
+          }
+          tmem_st_32x32(lane_base + cPh + h * 32, ph_);
+          tmem_st_32x32(lane_base + cPl + h * 32, pl_);
+        }
+        tmem_st_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(p_full);
+        if (trace) trace[j * 8 + 3] = clock64();
+      }
+    }
     if (row < nq) {
       const float inv = 1.f / l_run;
       float4* dst = reinterpret_cast<float4*>(a.out + (size_t)(a.segs.base[img] + row) * kD + head * HD);
@@ -345,20 +353,20 @@ k_attention_tc(const __grid_constant__ CUtensorMap mapQ, const __grid_constant__
 
 }  // namespace
 
-// planes as written by the qkv-mode GEMM epilogue (QkvPlanes, common.cuh)
 int set_attention_trace(long long* dev_buf) {
   GIMS_CUDA_OK(cudaMemcpyToSymbol(g_attn_trace, &dev_buf, sizeof(dev_buf)));
   return GIMS_OK;
 }
 
+// planes as written by the qkv-mode GEMM epilogue (QkvPlanes, common.cuh)
 int launch_attention_tc(const QkvPlanes& pl, float* out, int n0_max, int n1_max, const int* n_dev, int cross,
                         cudaStream_t st) {
   int rows = n0_max + n1_max;
-  CUtensorMap mQ, mK, mV;
-  GIMS_TRY(tc::make_tmap_f32_k32(&mQ, pl.qp, 2 * (uint64_t)rows, kD, kD, TQ));
+  CUtensorMap mK, mV;
   GIMS_TRY(tc::make_tmap_f32_k32(&mK, pl.kp, 2 * (uint64_t)rows, kD, kD, TKV));
   GIMS_TRY(tc::make_tmap_f32_k32(&mV, pl.vt, 2 * (uint64_t)kD, pl.ldv, pl.ldv, HD));
   AttnTcArgs a;
+  a.qp = pl.qp;
   a.out = out;
   a.segs.base[0] = 0; a.segs.base[1] = n0_max; a.segs.nmax[0] = n0_max; a.segs.nmax[1] = n1_max; a.segs.n_dev = n_dev;
   a.segs.nseg = 2;
@@ -368,7 +376,7 @@ int launch_attention_tc(const QkvPlanes& pl, float* out, int n0_max, int n1_max,
   GIMS_CUDA_OK(cudaFuncSetAttribute(k_attention_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
   int nmax = n0_max > n1_max ? n0_max : n1_max;
   ProfScope prof(GIMS_PROF_ATTENTION, st);
-  k_attention_tc<<<dim3(cdiv(nmax, TQ), kHeads, 2), kAttnThreads, kAttnSmem, st>>>(mQ, mK, mV, a);
+  k_attention_tc<<<dim3(cdiv(nmax, TQ), kHeads, 2), kAttnThreads, kAttnSmem, st>>>(mK, mV, a);
   GIMS_LAUNCH_OK();
   return GIMS_OK;
 }

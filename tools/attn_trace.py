@@ -29,5 +29,5 @@ print('tile  qk_issue  pv_ready  pv_issued | s_seen(w0)  p_given by warp 0,1,2,3
 prev = None
 for j in range(32):
     r = [int(x) - t0 if int(x) else -1 for x in t[j]]
-    print('%3d  top %8d  qk_first_mma %8d  pv_ready %8d  pv_issued %8d | s_seen %8d p_given %8d' % (j, r[0], r[6], r[1], r[2], r[4], r[3]))
+    print('%3d  top %7d  k_ready %7d  qk_issued %7d  pv_ready %7d  pv_issued %7d | s_seen %7d p_given %7d' % (j, r[0], r[7], r[6], r[1], r[2], r[4], r[3]))
     prev = r
