@@ -57,7 +57,7 @@ namespace {
 using namespace tc;
 
 constexpr int BM = 128, BK = 32;
-constexpr int kThreadsTc = 192;
+constexpr int kThreadsTc = 224;   // 4 data warps + TMA warp + two MMA issuer warps
 
 template <int BN>
 struct TcCfg {
@@ -68,8 +68,12 @@ struct TcCfg {
   // The tensor core rounds the fp32 accumulator toward zero on every accumulation, so the error of one long
   // accumulation chain grows linearly.  The two small correction products go to their own accumulator, and the
   // hi*hi product alternates over kMainAcc accumulators by k-block; the epilogue adds them in fp32 (RN).
+  // Two issuer threads (even / odd k-blocks) wherever TMEM has room for a correction accumulator each: a single
+  // issuer spends a third of its time in barrier waits / commits, during which the tensor pipe drains.
   static constexpr int kMainAcc = (BN <= 64) ? 4 : (BN <= 128 ? 2 : 1);
-  static constexpr int kAccCols = (kMainAcc + 1) * BN;
+  static constexpr int kIssuers = (BN <= 128) ? 2 : 1;
+  static constexpr int kCorrAcc = kIssuers;
+  static constexpr int kAccCols = (kMainAcc + kCorrAcc) * BN;
   static constexpr int kTmemCols = (kAccCols <= 128) ? 128 : (kAccCols <= 256 ? 256 : 512);
   static_assert(kAccCols <= 512, "accumulators exceed TMEM");
   static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
@@ -123,7 +127,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
   // Warp roles: 0..3 = data warps (TMEM lane quarter = warp), 4 = TMA producer, 5 = MMA issuer.  The issuer gets
   // the highest warp id on its scheduler: the arbiter favours high warp ids, and a starved issuer starves the tensor pipe.
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  constexpr int kWarpTma = 4, kWarpMma = 5;
+  constexpr int kWarpTma = 4, kWarpMma = 5;          // issuer t (0 or 1) is lane 0 of warp kWarpMma + t
   const int nkb = (g.K0 + g.K1) / BK;
 
   if (warp == kWarpTma && lane == 0) {
@@ -136,7 +140,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
       mbar_init(&conv[s], 4);        // one arrival per converter warp
       mbar_init(&empty[s], 1);
     }
-    mbar_init(accum_full, 1);
+    mbar_init(accum_full, (Cfg::kIssuers == 2 && nkb >= 2) ? 2 : 1);   // one commit per issuer that has k-blocks
     fence_barrier_init();
   }
   if (warp == kWarpMma) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
@@ -163,38 +167,40 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
         if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
       }
     }
-  } else if (warp == kWarpMma) {
-    // ===== MMA issuer =====
-    if (lane == 0) {
+  } else if (warp >= kWarpMma) {
+    // ===== MMA issuers: lane 0 of warp kWarpMma + t handles the k-blocks kb = t, t + kIssuers, ... =====
+    const int t = warp - kWarpMma;
+    if (lane == 0 && t < Cfg::kIssuers) {
       constexpr uint32_t idesc = umma_idesc_tf32(BM, BN);
       // one descriptor per stage, built once: inside the loop an operand advance is a single 64-bit add
       const uint64_t d_stage0 = umma_desc_sw128(smem_u32(stage_ptr(0)));
-      int s = 0; uint32_t ph = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(&full[s], ph);
-        mbar_wait(&conv[s], ph);
+      const uint32_t corr = tmem_base + (Cfg::kMainAcc + t) * BN;
+      int last = -1;
+      for (int kb = t; kb < nkb; kb += Cfg::kIssuers) last = kb;
+      for (int kb = t; kb < nkb; kb += Cfg::kIssuers) {
+        const int s = kb % Cfg::kStages;
+        const uint32_t ph = (uint32_t)(kb / Cfg::kStages) & 1u;
+        mbar_wait(&conv[s], ph);                       // the splitters arrive only after they saw full[s] complete
         tcgen05_fence_after();
         const uint64_t a_hi = d_stage0 + (uint64_t)((s * Cfg::kStageBytes) >> 4);
         const uint64_t a_lo = a_hi + (Cfg::kABytes >> 4);
         const uint64_t w_hi = a_hi + ((2 * Cfg::kABytes) >> 4);
         const uint64_t w_lo = w_hi + (Cfg::kWBytes >> 4);
+        const uint32_t main_acc = tmem_base + (kb % Cfg::kMainAcc) * BN;
 #pragma unroll
         for (int ks = 0; ks < BK / 8; ++ks) {
           const uint64_t koff = (ks * 32) >> 4;       // 8 tf32 = 32 bytes inside the 128-B swizzle row
           const uint64_t dah = a_hi + koff, dal = a_lo + koff, dwh = w_hi + koff, dwl = w_lo + koff;
-          const uint32_t corr = tmem_base + Cfg::kMainAcc * BN;
-          const uint32_t main_acc = tmem_base + (kb % Cfg::kMainAcc) * BN;
-          umma_tf32_ss(corr, dal, dwh, idesc, (kb | ks) ? 1u : 0u);
+          umma_tf32_ss(corr, dal, dwh, idesc, (kb >= Cfg::kIssuers || ks) ? 1u : 0u);
           umma_tf32_ss(corr, dah, dwl, idesc, 1u);
           umma_tf32_ss(main_acc, dah, dwh, idesc, (kb >= Cfg::kMainAcc || ks) ? 1u : 0u);
         }
         umma_commit(&empty[s]);                        // smem slot reusable once these MMAs retire
-        if (kb == nkb - 1) umma_commit(accum_full);    // accumulator complete
-        if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
+        if (kb == last) umma_commit(accum_full);       // this issuer's accumulators are complete
       }
     }
-  } else {
-    // ===== A splitters (warps 2..5), then epilogue =====
+  } else if (warp < 4) {
+    // ===== A splitters (warps 0..3), then epilogue =====
     const int t = threadIdx.x;                         // 0..127
     {
       int s = 0; uint32_t ph = 0;
@@ -222,16 +228,17 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
     const int r = r0 + 32 * q + lane;
     const bool row_ok = r < rows;
     const int n_main = nkb < Cfg::kMainAcc ? nkb : Cfg::kMainAcc;
+    const int n_corr = nkb < Cfg::kCorrAcc ? nkb : Cfg::kCorrAcc;
 #pragma unroll 1
     for (int cc = 0; cc < BN / 32; ++cc) {
       uint32_t v[32];
       const uint32_t lane_col = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(cc * 32);
       tmem_ld_32x32(lane_col, v);
       tmem_ld_wait();
-      for (int a = 1; a <= Cfg::kMainAcc; ++a) {
-        if (a < Cfg::kMainAcc && a >= n_main) continue;        // accumulator never written (short K)
+      for (int a = 1; a < Cfg::kMainAcc + Cfg::kCorrAcc; ++a) {
+        if (a < Cfg::kMainAcc ? a >= n_main : a - Cfg::kMainAcc >= n_corr) continue;   // never written (short K)
         uint32_t w[32];
-        tmem_ld_32x32(lane_col + (uint32_t)(a * BN), w);       // a == kMainAcc: the correction accumulator
+        tmem_ld_32x32(lane_col + (uint32_t)(a * BN), w);       // a >= kMainAcc: the correction accumulators
         tmem_ld_wait();
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
