@@ -103,6 +103,7 @@ SIGNATURES = {
                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
                               C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
     'gims_debug_attention_trace': (C.c_int, [C.c_void_p]),
+    'gims_debug_gemm_trace': (C.c_int, [C.c_void_p]),
     'gims_debug_sinkhorn_trace': (C.c_int, [C.c_void_p]),
     'gims_split_tf32': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     'gims_sinkhorn_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int]),

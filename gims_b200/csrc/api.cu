@@ -308,6 +308,7 @@ extern "C" int gims_linear(const float* A0, int lda0, int K0, const float* A1, i
 }
 
 extern "C" int gims_debug_attention_trace(long long* dev_buf) { return set_attention_trace(dev_buf); }
+extern "C" int gims_debug_gemm_trace(long long* dev_buf) { return set_gemm_trace(dev_buf); }
 
 extern "C" int gims_split_tf32(const float* x, float* hi, float* lo, size_t n, void* stream) {
   if (n % 4) { set_error("gims_split_tf32: n must be a multiple of 4"); return GIMS_ERR_ARG; }

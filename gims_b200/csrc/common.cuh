@@ -116,6 +116,7 @@ int launch_gemm_tc(const GemmArgs& a, const float* w_hi, const float* w_lo, cuda
 int launch_attention_tc(const QkvPlanes& pl, float* out, int n0_max, int n1_max, const int* n_dev, int cross,
                         cudaStream_t st);
 int set_attention_trace(long long* dev_buf);
+int set_gemm_trace(long long* dev_buf);
 static inline int attn_vbase1(int n0_max) { return (n0_max + 63) & ~63; }
 static inline int attn_ldv(int n0_max, int n1_max) { return attn_vbase1(n0_max) + ((n1_max + 63) & ~63); }
 int launch_score_gemm_tc(const float* mdesc, int n0_max, int n1_max, const int* n_dev, float* planes, float* couplings,

@@ -61,22 +61,29 @@ constexpr int kThreadsTc = 224;   // 4 data warps + TMA warp + two MMA issuer wa
 
 template <int BN>
 struct TcCfg {
-  static constexpr int kStages = (BN <= 64) ? 4 : (BN <= 128 ? 3 : 2);
-  static constexpr int kABytes = BM * BK * 4;            // 16 KB
+  static constexpr int kABytes = BM * BK * 4;            // 16 KB raw fp32 A tile
   static constexpr int kWBytes = BN * BK * 4;
-  static constexpr int kStageBytes = 2 * kABytes + 2 * kWBytes;
-  // The tensor core rounds the fp32 accumulator toward zero on every accumulation, so the error of one long
-  // accumulation chain grows linearly.  The two small correction products go to their own accumulator, and the
-  // hi*hi product alternates over kMainAcc accumulators by k-block; the epilogue adds them in fp32 (RN).
-  // Two issuer threads (even / odd k-blocks) wherever TMEM has room for a correction accumulator each: a single
-  // issuer spends a third of its time in barrier waits / commits, during which the tensor pipe drains.
-  static constexpr int kMainAcc = (BN <= 64) ? 4 : (BN <= 128 ? 2 : 1);
-  static constexpr int kIssuers = (BN <= 128) ? 2 : 1;
-  static constexpr int kCorrAcc = kIssuers;
+  static constexpr int kStageBytes = kABytes + 2 * kWBytes;
+  static constexpr int kStages = (BN <= 64) ? 6 : (BN <= 128 ? 4 : 3);      // 192 KB of shared memory either way
+  // Two issuer threads (even / odd k-blocks), each with its own accumulators: a single issuer leaves the tensor pipe
+  // idle for ~40 % of the time around its commits (profiles/r01_gemm_pipeline_trace.txt).
+  static constexpr int kIssuers = 2;
+  // The tensor core rounds the fp32 accumulator toward zero on every accumulation, so the error of one accumulation
+  // chain grows linearly with its length.  Splitting the k-blocks over two accumulators halves the chains; at
+  // BN = 64 TMEM also has room for separate accumulators for the two small correction products (kFold = false),
+  // which takes their 2/3 of the roundings off the main chains.  The epilogue adds the accumulators in fp32 (RN).
+  static constexpr bool kFold = BN > 64;
+  static constexpr int kMainAcc = 2;
+  static constexpr int kCorrAcc = kFold ? 0 : kIssuers;
   static constexpr int kAccCols = (kMainAcc + kCorrAcc) * BN;
-  static constexpr int kTmemCols = (kAccCols <= 128) ? 128 : (kAccCols <= 256 ? 256 : 512);
-  static_assert(kAccCols <= 512, "accumulators exceed TMEM");
-  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  // The A operand lives in TMEM: a ring of k-block slots, 32 columns A_hi + 32 columns A_lo each.
+  static constexpr int kRing = (512 - kAccCols) / 64 >= 4 ? 4 : 2;
+  static constexpr int kRingCol = kAccCols;
+  static constexpr int kTmemCols = 512;
+  static_assert(kAccCols + kRing * 64 <= kTmemCols, "accumulators + A ring exceed TMEM");
+  static constexpr int kBarriers = 2 * kStages + 2 * kRing + 1;
+  static constexpr int kBiasOff = (kBarriers * 8 + 16 + 15) & ~15;       // after the barriers and the TMEM address slot
+  static constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + kBiasOff + BN * 4;
 };
 
 struct TcArgs {
@@ -98,19 +105,28 @@ struct TcArgs {
   float* qp; float* kp; float* vt; int ldv; int rows_total; int vbase1;
 };
 
+// Optional pipeline trace (bring-up / profiling): CTA (0,0) stores clock64() stamps, see tools/gemm_trace.py.
+__device__ long long* g_gemm_trace = nullptr;
+
 template <int BN>
 __global__ void __launch_bounds__(kThreadsTc, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
           const __grid_constant__ CUtensorMap mapWhi, const __grid_constant__ CUtensorMap mapWlo, TcArgs g) {
   using Cfg = TcCfg<BN>;
   extern __shared__ uint8_t smem_raw[];
+  long long* trace = (blockIdx.x | blockIdx.y) == 0 && (threadIdx.x & 31) == 0 ? g_gemm_trace : nullptr;
+  if (trace && threadIdx.x == 0) {
+    trace[0] = clock64();
+    unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    trace[6] = (long long)gt;
+  }
   // ---- tile coordinates (uniform per CTA) -------------------------------------------------------
   int seg, tile;
   if (g.score) { seg = 0; tile = blockIdx.y; }
   else if ((int)blockIdx.y < g.tiles0) { seg = 0; tile = blockIdx.y; }
   else { seg = 1; tile = blockIdx.y - g.tiles0; }
-  const int rows = seg_count(g.segs, seg);
-  const int ncols = g.score ? seg_count(g.segs, 1) : g.N;
+  const int rows = __shfl_sync(0xffffffffu, seg_count(g.segs, seg), 0);
+  const int ncols = g.score ? __shfl_sync(0xffffffffu, seg_count(g.segs, 1), 0) : g.N;
   const int r0 = tile * BM, c0 = blockIdx.x * BN;
   if (r0 >= rows || c0 >= ncols) return;
   const int rbase = g.segs.base[seg];
@@ -118,14 +134,16 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
-  uint64_t* full = bars;                          // [kStages]
-  uint64_t* conv = bars + Cfg::kStages;           // [kStages]
-  uint64_t* empty = bars + 2 * Cfg::kStages;      // [kStages]
-  uint64_t* accum_full = bars + 3 * Cfg::kStages; // [1]
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 3 * Cfg::kStages + 1);
+  uint64_t* full = bars;                                // [kStages] TMA bytes landed (A raw, W_hi, W_lo)
+  uint64_t* empty = bars + Cfg::kStages;                // [kStages] the MMAs that read the W tiles have retired
+  uint64_t* conv = bars + 2 * Cfg::kStages;             // [kRing]   A_hi / A_lo of a k-block are in TMEM
+  uint64_t* tfree = conv + Cfg::kRing;                  // [kRing]   the MMAs that read that TMEM slot have retired
+  uint64_t* accum_full = tfree + Cfg::kRing;            // [1]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_full + 1);
+  float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + Cfg::kBiasOff);   // [BN], 16-byte aligned
 
-  // Warp roles: 0..3 = data warps (TMEM lane quarter = warp), 4 = TMA producer, 5 = MMA issuer.  The issuer gets
-  // the highest warp id on its scheduler: the arbiter favours high warp ids, and a starved issuer starves the tensor pipe.
+  // Warp roles: 0..3 = data warps (TMEM lane quarter = warp), 4 = TMA producer, 5/6 = MMA issuers.  The issuers get
+  // the highest warp ids: the arbiter favours high warp ids, and a starved issuer starves the tensor pipe.
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kWarpTma = 4, kWarpMma = 5;          // issuer t (0 or 1) is lane 0 of warp kWarpMma + t
   const int nkb = (g.K0 + g.K1) / BK;
@@ -137,17 +155,22 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
     tma_prefetch_desc(&mapWlo);
     for (int s = 0; s < Cfg::kStages; ++s) {
       mbar_init(&full[s], 1);
-      mbar_init(&conv[s], 4);        // one arrival per converter warp
       mbar_init(&empty[s], 1);
+    }
+    for (int s = 0; s < Cfg::kRing; ++s) {
+      mbar_init(&conv[s], 4);        // one arrival per splitter warp
+      mbar_init(&tfree[s], 1);
     }
     mbar_init(accum_full, (Cfg::kIssuers == 2 && nkb >= 2) ? 2 : 1);   // one commit per issuer that has k-blocks
     fence_barrier_init();
   }
   if (warp == kWarpMma) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
+  if (threadIdx.x < BN) bias_s[threadIdx.x] = (g.bias && c0 + (int)threadIdx.x < g.N) ? g.bias[c0 + threadIdx.x] : 0.f;
   tcgen05_fence_before();
   __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform for the compiler
+  if (trace && threadIdx.x == 0) trace[1] = clock64();
 
   auto stage_ptr = [&](int s) { return smem + (size_t)s * Cfg::kStageBytes; };
 
@@ -162,77 +185,116 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
         int k = kb * BK;
         if (k < g.K0) tma_load_2d(st, &mapA0, &full[s], k, rbase + r0);
         else          tma_load_2d(st, &mapA1, &full[s], k - g.K0, rbase + r0);
-        tma_load_2d(st + 2 * Cfg::kABytes, &mapWhi, &full[s], k, wbase + c0);
-        tma_load_2d(st + 2 * Cfg::kABytes + Cfg::kWBytes, &mapWlo, &full[s], k, wbase + c0);
+        tma_load_2d(st + Cfg::kABytes, &mapWhi, &full[s], k, wbase + c0);
+        tma_load_2d(st + Cfg::kABytes + Cfg::kWBytes, &mapWlo, &full[s], k, wbase + c0);
         if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
       }
     }
   } else if (warp >= kWarpMma) {
     // ===== MMA issuers: lane 0 of warp kWarpMma + t handles the k-blocks kb = t, t + kIssuers, ... =====
-    const int t = warp - kWarpMma;
-    if (lane == 0 && t < Cfg::kIssuers) {
+    // A comes from TMEM (written by the splitters), W from shared memory: with A in shared memory as well the
+    // operand reads of three MMAs per k-step saturated the shared-memory port (profiles/r01_gemm_pipeline_trace.txt).
+    const int t = __shfl_sync(0xffffffffu, warp - kWarpMma, 0);   // provably warp-uniform: the MMA operands stay in
+    if (lane == 0 && t < Cfg::kIssuers) {                        // uniform registers (no ELECT / R2UR.BROADCAST per MMA)
       constexpr uint32_t idesc = umma_idesc_tf32(BM, BN);
       // one descriptor per stage, built once: inside the loop an operand advance is a single 64-bit add
-      const uint64_t d_stage0 = umma_desc_sw128(smem_u32(stage_ptr(0)));
-      const uint32_t corr = tmem_base + (Cfg::kMainAcc + t) * BN;
+      const uint64_t d_stage0 = umma_desc_sw128(smem_u32(stage_ptr(0) + Cfg::kABytes));
       int last = -1;
       for (int kb = t; kb < nkb; kb += Cfg::kIssuers) last = kb;
       for (int kb = t; kb < nkb; kb += Cfg::kIssuers) {
         const int s = kb % Cfg::kStages;
-        const uint32_t ph = (uint32_t)(kb / Cfg::kStages) & 1u;
-        mbar_wait(&conv[s], ph);                       // the splitters arrive only after they saw full[s] complete
+        const int slot = kb % Cfg::kRing;
+        mbar_wait(&conv[slot], (uint32_t)(kb / Cfg::kRing) & 1u);   // the splitters arrive after they saw full[s]
         tcgen05_fence_after();
-        const uint64_t a_hi = d_stage0 + (uint64_t)((s * Cfg::kStageBytes) >> 4);
-        const uint64_t a_lo = a_hi + (Cfg::kABytes >> 4);
-        const uint64_t w_hi = a_hi + ((2 * Cfg::kABytes) >> 4);
+        if (trace && kb < 8) trace[24 + kb] = clock64();
+        const uint64_t w_hi = d_stage0 + (uint64_t)((s * Cfg::kStageBytes) >> 4);
         const uint64_t w_lo = w_hi + (Cfg::kWBytes >> 4);
-        const uint32_t main_acc = tmem_base + (kb % Cfg::kMainAcc) * BN;
+        const uint32_t a_hi = tmem_base + Cfg::kRingCol + slot * 64;
+        const uint32_t a_lo = a_hi + 32;
+        // issuer t owns main accumulator t (kb % 2 == t) and, unless folded into it, correction accumulator t
+        const uint32_t main_acc = tmem_base + t * BN;
+        const uint32_t corr = Cfg::kFold ? main_acc : tmem_base + (Cfg::kMainAcc + t) * BN;
+        const uint32_t fresh = kb >= Cfg::kIssuers ? 1u : 0u;      // 0: first k-block of this issuer
 #pragma unroll
         for (int ks = 0; ks < BK / 8; ++ks) {
           const uint64_t koff = (ks * 32) >> 4;       // 8 tf32 = 32 bytes inside the 128-B swizzle row
-          const uint64_t dah = a_hi + koff, dal = a_lo + koff, dwh = w_hi + koff, dwl = w_lo + koff;
-          umma_tf32_ss(corr, dal, dwh, idesc, (kb >= Cfg::kIssuers || ks) ? 1u : 0u);
-          umma_tf32_ss(corr, dah, dwl, idesc, 1u);
-          umma_tf32_ss(main_acc, dah, dwh, idesc, (kb >= Cfg::kMainAcc || ks) ? 1u : 0u);
+          umma_tf32_ts(corr, a_lo + ks * 8, w_hi + koff, idesc, ks ? 1u : fresh);
+          umma_tf32_ts(corr, a_hi + ks * 8, w_lo + koff, idesc, 1u);
+          umma_tf32_ts(main_acc, a_hi + ks * 8, w_hi + koff, idesc, (Cfg::kFold || ks) ? 1u : fresh);
         }
-        umma_commit(&empty[s]);                        // smem slot reusable once these MMAs retire
+        if (trace && kb < 8) trace[32 + kb] = clock64();
+        umma_commit(&empty[s]);                        // W slot reusable once these MMAs retire
+        umma_commit(&tfree[slot]);                     // and so is the A slot in TMEM
         if (kb == last) umma_commit(accum_full);       // this issuer's accumulators are complete
+        if (trace && kb < 8) trace[40 + kb] = clock64();
       }
     }
   } else if (warp < 4) {
-    // ===== A splitters (warps 0..3), then epilogue =====
+    // ===== A splitters (warps 0..3; thread = tile row = TMEM lane), then epilogue =====
     const int t = threadIdx.x;                         // 0..127
+    const int q = warp;                                // TMEM lane quarter this warp may access
+    const uint32_t lane_base = tmem_base + ((uint32_t)(32 * q) << 16);
     {
       int s = 0; uint32_t ph = 0;
       for (int kb = 0; kb < nkb; ++kb) {
+        const int slot = kb % Cfg::kRing;
         mbar_wait(&full[s], ph);
-        float4* raw = reinterpret_cast<float4*>(stage_ptr(s));
-        float4* lo = reinterpret_cast<float4*>(stage_ptr(s) + Cfg::kABytes);
+        if (trace && t == 0 && kb < 8) trace[8 + kb] = clock64();
+        // row t of the 128-byte-swizzled tile: 16-byte chunk j sits at position j ^ (t & 7)
+        const uint4* rowp = reinterpret_cast<const uint4*>(stage_ptr(s) + t * 128);
+        uint32_t x[32], hi[32];
 #pragma unroll
-        for (int i = 0; i < Cfg::kABytes / 16 / 128; ++i) {
-          int c = t + 128 * i;
-          float4 x = raw[c], h, l;
-          split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y); split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
-          raw[c] = h;
-          lo[c] = l;
+        for (int j = 0; j < 8; ++j) {
+          uint4 v = rowp[j ^ (t & 7)];
+          x[4 * j] = v.x; x[4 * j + 1] = v.y; x[4 * j + 2] = v.z; x[4 * j + 3] = v.w;
         }
-        fence_proxy_async_smem();                      // generic-proxy writes -> visible to the tensor core (async proxy)
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          float h, l;
+          split_tf32(__uint_as_float(x[j]), h, l);
+          hi[j] = __float_as_uint(h); x[j] = __float_as_uint(l);
+        }
+        mbar_wait(&tfree[slot], ((uint32_t)(kb / Cfg::kRing) & 1u) ^ 1u);   // MMAs of k-block kb - kRing are done
+        tcgen05_fence_after();
+        if (trace && t == 0 && kb < 8) trace[48 + kb] = clock64();
+        tmem_st_32x32(lane_base + Cfg::kRingCol + slot * 64, hi);
+        tmem_st_32x32(lane_base + Cfg::kRingCol + slot * 64 + 32, x);
+        tmem_st_wait();
+        tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&conv[s]);
+        if (lane == 0) mbar_arrive(&conv[slot]);
+        if (trace && t == 0 && kb < 8) trace[16 + kb] = clock64();
         if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
       }
     }
-    mbar_wait(accum_full, 0);
-    tcgen05_fence_after();
-    const int q = warp & 3;                            // TMEM lane quarter this warp may access
-    const int r = r0 + 32 * q + lane;
-    const bool row_ok = r < rows;
+    // ---- epilogue ----
     const int n_main = nkb < Cfg::kMainAcc ? nkb : Cfg::kMainAcc;
     const int n_corr = nkb < Cfg::kCorrAcc ? nkb : Cfg::kCorrAcc;
+    // Each warp transposes its 32x32 chunks through a private staging tile in the (now idle) pipeline stages, so that
+    // one store instruction covers four complete 128-byte lines of Y and the residual is read the same way.
+    constexpr int kStgLd = 36;                         // floats; 16-byte aligned rows, conflict-free both ways
+    float* stg = reinterpret_cast<float*>(smem) + q * (32 * kStgLd);
+    const int rl0 = lane >> 3, cj = (lane & 7) * 4;    // read-back: row i*4 + rl0 of the chunk, columns cj..cj+3
+    const bool use_r = g.R != nullptr && !g.qkv && !g.score;
+    float4 rres[8];                                    // residual of the current chunk, fetched one chunk ahead
+    auto fetch_residual = [&](int cc) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = r0 + 32 * q + i * 4 + rl0;
+        const int c = c0 + cc * 32 + cj;
+        rres[i] = (use_r && r < rows && c < ncols)
+                      ? *reinterpret_cast<const float4*>(g.R + (size_t)(rbase + r) * g.ldr + c)
+                      : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    };
+    fetch_residual(0);                                 // its latency hides behind the tail of the k-loop
+    mbar_wait(accum_full, 0);
+    tcgen05_fence_after();
+    if (trace && t == 0) trace[3] = clock64();
 #pragma unroll 1
     for (int cc = 0; cc < BN / 32; ++cc) {
       uint32_t v[32];
-      const uint32_t lane_col = tmem_base + ((uint32_t)(32 * q) << 16) + (uint32_t)(cc * 32);
+      const uint32_t lane_col = lane_base + (uint32_t)(cc * 32);
       tmem_ld_32x32(lane_col, v);
       tmem_ld_wait();
       for (int a = 1; a < Cfg::kMainAcc + Cfg::kCorrAcc; ++a) {
@@ -243,77 +305,84 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
       }
-      int c = c0 + cc * 32;
-      if (g.qkv) {
-        if (c >= ncols) continue;
-        const size_t grow = (size_t)(rbase + r);
-        const bool in_buf = r < g.segs.nmax[seg];              // never touch the other image's rows
-        float x[32];
-#pragma unroll
-        for (int j = 0; j < 32; ++j) x[j] = __uint_as_float(v[j]) + g.bias[c + j];
-        const int part = c >> 8, cc256 = c & 255;
-        if (part < 2) {
-          if (!row_ok) continue;
-          float* hi = (part == 0 ? g.qp : g.kp) + grow * kD + cc256;
-          float* lo = hi + (size_t)g.rows_total * kD;
-          const float sc = part == 0 ? 0.18033688011112042f : 1.f;   // log2(e)/sqrt(64): scores in the log2 domain
-#pragma unroll
-          for (int j = 0; j < 32; j += 4) {
-            float4 h, l;
-            split_tf32(x[j] * sc, h.x, l.x); split_tf32(x[j + 1] * sc, h.y, l.y);
-            split_tf32(x[j + 2] * sc, h.z, l.z); split_tf32(x[j + 3] * sc, h.w, l.w);
-            *reinterpret_cast<float4*>(hi + j) = h;
-            *reinterpret_cast<float4*>(lo + j) = l;
-          }
-        } else if (in_buf) {
-          // key column of this row in Vt: image 1 starts at a 64-aligned column (TMA box starts must be
-          // 16-byte aligned in global memory, so the inner coordinate has to be a multiple of 4 floats)
+      const int c = c0 + cc * 32;
+      if (c >= ncols) continue;                                // warp-uniform
+      if (g.qkv && c >= 2 * kD) {
+        // V: key column of this row in Vt; image 1 starts at a 64-aligned column (TMA box starts must be 16-byte
+        // aligned in global memory).  Lanes = consecutive rows = consecutive addresses: coalesced as it is.
+        const int r = r0 + 32 * q + lane;
+        if (r < g.segs.nmax[seg]) {                            // never touch the other image's rows
+          const bool row_ok = r < rows;
+          const int cc256 = c & 255;
           const size_t kcol = (size_t)(seg ? g.vbase1 : 0) + r;
-          float* hi = g.vt + (size_t)cc256 * g.ldv + kcol;       // lanes = consecutive rows: coalesced
+          float* hi = g.vt + (size_t)cc256 * g.ldv + kcol;
           float* lo = hi + (size_t)kD * g.ldv;
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             float h, l;
-            split_tf32(row_ok ? x[j] : 0.f, h, l);
+            split_tf32(row_ok ? __uint_as_float(v[j]) + bias_s[cc * 32 + j] : 0.f, h, l);
             hi[(size_t)j * g.ldv] = h;
             lo[(size_t)j * g.ldv] = l;
           }
         }
         continue;
       }
-      if (!row_ok || c >= ncols) continue;
+      __syncwarp();                                            // the previous chunk has been read back
+#pragma unroll
+      for (int j = 0; j < 32; j += 4)
+        *reinterpret_cast<uint4*>(stg + lane * kStgLd + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+      __syncwarp();
       if (g.score) {
-        float* y = g.Y + (size_t)r * g.ldy + c;
-#pragma unroll
-        for (int j = 0; j < 32; ++j)
-          if (c + j < ncols) y[j] = __uint_as_float(v[j]) * g.scale;
-      } else {
-        size_t row = (size_t)(rbase + r);
-        float* y = g.Y + row * g.ldy + c;
-        const float* rr = g.R ? g.R + row * g.ldr + c : nullptr;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-          float4 o = make_float4(__uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
-                                 __uint_as_float(v[j + 3]));
-          if (g.bias) {
-            float4 b = *reinterpret_cast<const float4*>(g.bias + c + j);
-            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
+        // couplings rows are n1_max + 1 floats long (not 16-byte aligned) and end raggedly: scalar, one row per store
+        if (c + lane < ncols) {
+#pragma unroll 4
+          for (int i = 0; i < 32; ++i) {
+            const int r = r0 + 32 * q + i;
+            if (r < rows) g.Y[(size_t)r * g.ldy + c + lane] = stg[i * kStgLd + lane] * g.scale;
           }
-          if (rr) {
-            float4 b = *reinterpret_cast<const float4*>(rr + j);
-            o.x += b.x; o.y += b.y; o.z += b.z; o.w += b.w;
-          }
-          if (g.relu) { o.x = fmaxf(o.x, 0.f); o.y = fmaxf(o.y, 0.f); o.z = fmaxf(o.z, 0.f); o.w = fmaxf(o.w, 0.f); }
-          *reinterpret_cast<float4*>(y + j) = o;
+        }
+        continue;
+      }
+      const float4 bias4 = *reinterpret_cast<const float4*>(bias_s + cc * 32 + cj);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int r = r0 + 32 * q + i * 4 + rl0;
+        float4 oi = *reinterpret_cast<const float4*>(stg + (i * 4 + rl0) * kStgLd + cj);
+        oi.x += bias4.x + rres[i].x; oi.y += bias4.y + rres[i].y;
+        oi.z += bias4.z + rres[i].z; oi.w += bias4.w + rres[i].w;
+        if (use_r && cc + 1 < BN / 32 && r < rows)             // the next chunk's residual, one chunk ahead
+          rres[i] = *reinterpret_cast<const float4*>(g.R + (size_t)(rbase + r) * g.ldr + c + 32 + cj);
+        if (r >= rows) continue;
+        const size_t grow = (size_t)(rbase + r);
+        if (g.qkv) {
+          const int part = c >> 8, cc256 = c & 255;            // 0: Q, 1: K
+          float* hi = (part == 0 ? g.qp : g.kp) + grow * kD + cc256 + cj;
+          float* lo = hi + (size_t)g.rows_total * kD;
+          const float sc = part == 0 ? 0.18033688011112042f : 1.f;   // log2(e)/sqrt(64): scores in the log2 domain
+          float4 h, l;
+          split_tf32(oi.x * sc, h.x, l.x); split_tf32(oi.y * sc, h.y, l.y);
+          split_tf32(oi.z * sc, h.z, l.z); split_tf32(oi.w * sc, h.w, l.w);
+          *reinterpret_cast<float4*>(hi) = h;
+          *reinterpret_cast<float4*>(lo) = l;
+        } else {
+          float4 y = oi;
+          if (g.relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+          *reinterpret_cast<float4*>(g.Y + grow * g.ldy + c + cj) = y;
         }
       }
     }
     tcgen05_fence_before();
+    if (trace && t == 0) trace[4] = clock64();
   }
   __syncthreads();
   if (warp == kWarpMma) {
     tcgen05_fence_after();
     tmem_dealloc<Cfg::kTmemCols>(tmem_base);
+  }
+  if (trace && threadIdx.x == 0) {
+    trace[5] = clock64();
+    unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    trace[7] = (long long)gt;
   }
 }
 
@@ -332,13 +401,22 @@ int launch_tc(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w
               const TcArgs& g, int col_tiles, int row_tiles, int prof_class, cudaStream_t st) {
   using Cfg = TcCfg<BN>;
   GIMS_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(col_tiles, row_tiles);
+  cfg.blockDim = dim3(kThreadsTc);
+  cfg.dynamicSmemBytes = Cfg::kSmemBytes;
+  cfg.stream = st;
+  cfg.attrs = nullptr;
+  cfg.numAttrs = 0;
   ProfScope prof(prof_class, st);
-  k_gemm_tc<BN><<<dim3(col_tiles, row_tiles), kThreadsTc, Cfg::kSmemBytes, st>>>(a0, a1, whi, wlo, g);
-  GIMS_LAUNCH_OK();
+  GIMS_CUDA_OK(cudaLaunchKernelEx(&cfg, k_gemm_tc<BN>, a0, a1, whi, wlo, g));
+  count_launch();
   return GIMS_OK;
 }
 
 int pick_bn(int n) {
+  static const int forced = [] { const char* e = getenv("GIMS_GEMM_BN"); return e ? atoi(e) : 0; }();   // tuning knob
+  if (forced == 64 || forced == 128 || forced == 192) return forced;
   if (n >= 768) return 192;
   if (n >= 512) return 128;
   return 64;
@@ -378,6 +456,11 @@ int launch_gemm_tc(const GemmArgs& a, const float* w_hi, const float* w_lo, cuda
     case 128: return launch_tc<128>(mA0, mA1, mWh, mWl, g, ct, tiles, GIMS_PROF_GEMM, st);
     default:  return launch_tc<64>(mA0, mA1, mWh, mWl, g, ct, tiles, GIMS_PROF_GEMM, st);
   }
+}
+
+int set_gemm_trace(long long* dev_buf) {
+  GIMS_CUDA_OK(cudaMemcpyToSymbol(g_gemm_trace, &dev_buf, sizeof(dev_buf)));
+  return GIMS_OK;
 }
 
 int launch_split_planes(const float* x, float* hi, float* lo, size_t n, cudaStream_t st) {

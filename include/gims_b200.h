@@ -87,6 +87,8 @@ GIMS_API int gims_split_tf32(const float* x, float* hi, float* lo, size_t n, voi
 /* Profiling aid: CTA (0,0,0) of every following attention launch stores clock64() stamps of its pipeline
  * (8 int64 per 64-key tile, see attention_tc.cu) into dev_buf; pass NULL to switch the trace off. */
 GIMS_API int gims_debug_attention_trace(long long* dev_buf);
+/* Same for the tensor-core GEMM: CTA (0,0) of every following launch stores 64 int64 stamps (tools/gemm_trace.py). */
+GIMS_API int gims_debug_gemm_trace(long long* dev_buf);
 /* Same for k_sinkhorn: CTA 0 stores 6 stamps (8 int64 slots) for each of its first 16 iterations. */
 GIMS_API int gims_debug_sinkhorn_trace(long long* dev_buf);
 
