@@ -52,6 +52,10 @@ static std::mutex g_coop_mu;
 static cudaEvent_t g_coop_ev[64];
 static bool g_coop_has[64];
 
+static std::mutex g_coop_launch_mu;
+void coop_chain_lock() { g_coop_launch_mu.lock(); }
+void coop_chain_unlock() { g_coop_launch_mu.unlock(); }
+
 int coop_chain_wait(cudaStream_t st) {
   int dev = 0;
   GIMS_CUDA_OK(cudaGetDevice(&dev));

@@ -47,9 +47,18 @@ struct ProfScope {
 };
 
 // Cooperative (grid-synchronising) kernels of different streams must never be partially co-resident:
-// they are chained through one per-process event.  Call before / after such a launch.
+// they are chained through one per-device event.  The scope holds a process-wide lock from the wait to the
+// record, so concurrent host threads (one stream each) cannot both chain onto the same predecessor.
 int coop_chain_wait(cudaStream_t st);
 int coop_chain_record(cudaStream_t st);
+void coop_chain_lock();
+void coop_chain_unlock();
+struct CoopChainScope {
+  cudaStream_t st;
+  int rc;
+  explicit CoopChainScope(cudaStream_t s) : st(s) { coop_chain_lock(); rc = coop_chain_wait(st); }
+  ~CoopChainScope() { if (rc == 0) coop_chain_record(st); coop_chain_unlock(); }
+};
 
 constexpr int kD = GIMS_DESC_DIM;     // 256
 constexpr int kHeads = GIMS_NUM_HEADS;

@@ -305,6 +305,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
       }
+      if (trace && t == 0 && cc < 2) trace[56 + 3 * cc] = clock64();
       const int c = c0 + cc * 32;
       if (c >= ncols) continue;                                // warp-uniform
       if (g.qkv && c >= 2 * kD) {
@@ -332,6 +333,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
       for (int j = 0; j < 32; j += 4)
         *reinterpret_cast<uint4*>(stg + lane * kStgLd + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
       __syncwarp();
+      if (trace && t == 0 && cc < 2) trace[57 + 3 * cc] = clock64();
       if (g.score) {
         // couplings rows are n1_max + 1 floats long (not 16-byte aligned) and end raggedly: scalar, one row per store
         if (c + lane < ncols) {
@@ -370,6 +372,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
           *reinterpret_cast<float4*>(g.Y + grow * g.ldy + c + cj) = y;
         }
       }
+      if (trace && t == 0 && cc < 2) trace[58 + 3 * cc] = clock64();
     }
     tcgen05_fence_before();
     if (trace && t == 0) trace[4] = clock64();

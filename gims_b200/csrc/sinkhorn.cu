@@ -760,12 +760,12 @@ extern "C" int gims_sinkhorn_match(const float* couplings, int n0_max, int n1_ma
   if (per_sm < 1) { set_error("gims_sinkhorn_match: kernel does not fit an SM (dyn smem %zu)", dyn); return GIMS_ERR_ARG; }
   GIMS_CUDA_OK(cudaMemsetAsync(w.err, 0, w.zero_bytes, st));    // clears err and every flag / tag word (contiguous)
   void* params[] = {&a};
-  GIMS_TRY(coop_chain_wait(st));
   {
+    CoopChainScope chain(st);
+    GIMS_TRY(chain.rc);
     ProfScope prof(GIMS_PROF_SINKHORN, st);
     GIMS_CUDA_OK(cudaLaunchCooperativeKernel((const void*)k_sinkhorn, dim3(G), dim3(kThreads), params, dyn, st));
   }
-  GIMS_TRY(coop_chain_record(st));
   count_launch();
   int m = n0_max > n1_max ? n0_max : n1_max;
   k_match_finalize<<<cdiv(m, 256), 256, 0, st>>>(n0_max, n1_max, n_dev, indices0, indices1, w.max0, match_threshold,

@@ -202,7 +202,7 @@ class GMatcher(nn.Module):
         key = (n0, n1, edge_cap, str(dev), slot)
         ws = self._ws.get(key)
         if ws is None:
-            if len(self._ws) > 16:
+            if len(self._ws) > 64:
                 self._ws.clear()
             nbytes = _lib.lib().gims_pair_workspace_bytes(self._model, n0, n1, edge_cap)
             ws = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
@@ -285,8 +285,10 @@ class GMatcher(nn.Module):
         po.couplings = out['couplings'].data_ptr() if debug else None
         po.desc_gnn = out['desc_gnn'].data_ptr() if debug else None
         po.desc_in = out['desc_in'].data_ptr() if debug else None
-        ws = self._workspace(n0, n1, edge_cap, dev, slot)
         st = stream if stream is not None else torch.cuda.current_stream(dev)
+        # one workspace per stream: calls on one stream are ordered, calls on different streams (several pairs in
+        # flight, or several host threads calling forward() concurrently) must not share scratch memory
+        ws = self._workspace(n0, n1, edge_cap, dev, (slot, st.cuda_stream))
         with torch.cuda.device(dev):
             _lib.check(L.gims_forward_pair(model, C.byref(pin), C.byref(po), _lib.ptr(ws), ws.numel(),
                                            C.c_void_p(st.cuda_stream)), 'gims_forward_pair')

@@ -8,7 +8,7 @@ from gims_b200 import _lib
 L = _lib.lib()
 dev = torch.device('cuda')
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
-rows = 4096
+rows = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 
 
 def run(K0, K1, N, reps=50, dump=True):
@@ -48,6 +48,7 @@ def run(K0, K1, N, reps=50, dump=True):
     nkb = (K0 + K1) // 32
     print('  entry 0 | prologue done %d | accum_full seen %d | epilogue done %d | exit %d | globaltimer span %d ns' %
           (t[1] - z, t[3] - z, t[4] - z, t[5] - z, t[7] - t[6]))
+    print('  epilogue chunk 0: acc loaded %d, staged %d, stored %d | chunk 1: %d %d %d' % tuple(x - z for x in t[56:62]))
     print('  kb: full_seen  tmem_slot_free  split_done | mma_start  mma_issued  committed   (first 8 k-blocks)')
     for kb in range(min(nkb, 8)):
         print('  %2d %8d %8d %8d | %8d %8d %8d' % (kb, t[8 + kb] - z, t[48 + kb] - z, t[16 + kb] - z, t[24 + kb] - z,
