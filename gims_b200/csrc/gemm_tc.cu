@@ -108,7 +108,8 @@ struct TcArgs {
 // Optional pipeline trace (bring-up / profiling): CTA (0,0) stores clock64() stamps, see tools/gemm_trace.py.
 __device__ long long* g_gemm_trace = nullptr;
 
-template <int BN>
+// MODE 0: Y = act(acc + bias + R);  1: couplings (score GEMM);  2: Q / K / Vt tf32 planes (QKV projection)
+template <int BN, int MODE>
 __global__ void __launch_bounds__(kThreadsTc, 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
           const __grid_constant__ CUtensorMap mapWhi, const __grid_constant__ CUtensorMap mapWlo, TcArgs g) {
@@ -122,15 +123,15 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
   }
   // ---- tile coordinates (uniform per CTA) -------------------------------------------------------
   int seg, tile;
-  if (g.score) { seg = 0; tile = blockIdx.y; }
+  if (MODE == 1) { seg = 0; tile = blockIdx.y; }
   else if ((int)blockIdx.y < g.tiles0) { seg = 0; tile = blockIdx.y; }
   else { seg = 1; tile = blockIdx.y - g.tiles0; }
   const int rows = __shfl_sync(0xffffffffu, seg_count(g.segs, seg), 0);
-  const int ncols = g.score ? __shfl_sync(0xffffffffu, seg_count(g.segs, 1), 0) : g.N;
+  const int ncols = MODE == 1 ? __shfl_sync(0xffffffffu, seg_count(g.segs, 1), 0) : g.N;
   const int r0 = tile * BM, c0 = blockIdx.x * BN;
   if (r0 >= rows || c0 >= ncols) return;
   const int rbase = g.segs.base[seg];
-  const int wbase = g.score ? g.segs.base[1] : 0;
+  const int wbase = MODE == 1 ? g.segs.base[1] : 0;
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + Cfg::kStages * Cfg::kStageBytes);
@@ -271,24 +272,23 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
     const int n_main = nkb < Cfg::kMainAcc ? nkb : Cfg::kMainAcc;
     const int n_corr = nkb < Cfg::kCorrAcc ? nkb : Cfg::kCorrAcc;
     // Each warp transposes its 32x32 chunks through a private staging tile in the (now idle) pipeline stages, so that
-    // one store instruction covers four complete 128-byte lines of Y and the residual is read the same way.
+    // one store instruction covers four complete 128-byte lines of Y and the residual is read the same way.  An SM
+    // takes ~30 bytes of stores per clock (tools/micro/store_rate.cu), which is what this loop should be bound by:
+    // all shared-memory reads of a chunk are issued before the first store, and MODE is a template parameter, so
+    // there is no branch or address arithmetic between the stores.
     constexpr int kStgLd = 36;                         // floats; 16-byte aligned rows, conflict-free both ways
-    float* stg = reinterpret_cast<float*>(smem) + q * (32 * kStgLd);
+    const uint32_t stg = smem_u32(smem) + (uint32_t)(q * 32 * kStgLd * 4);
     const int rl0 = lane >> 3, cj = (lane & 7) * 4;    // read-back: row i*4 + rl0 of the chunk, columns cj..cj+3
-    const bool use_r = g.R != nullptr && !g.qkv && !g.score;
+    const int rfirst = r0 + 32 * q + rl0;              // tile row of read-back slot i = 0; slot i is 4*i further
+    const int nvalid = rows - rfirst;                  // slot i is a live row iff 4*i < nvalid
+    const bool use_r = MODE == 0 && g.R != nullptr;
+    const float* rrow = use_r ? g.R + (size_t)(rbase + rfirst) * g.ldr + c0 + cj : nullptr;
     float4 rres[8];                                    // residual of the current chunk, fetched one chunk ahead
-    auto fetch_residual = [&](int cc) {
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int r = r0 + 32 * q + i * 4 + rl0;
-        const int c = c0 + cc * 32 + cj;
-        rres[i] = (use_r && r < rows && c < ncols)
-                      ? *reinterpret_cast<const float4*>(g.R + (size_t)(rbase + r) * g.ldr + c)
-                      : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    };
-    fetch_residual(0);                                 // its latency hides behind the tail of the k-loop
-    mbar_wait(accum_full, 0);
+    for (int i = 0; i < 8; ++i)
+      rres[i] = (use_r && 4 * i < nvalid && c0 + cj < ncols) ? *reinterpret_cast<const float4*>(rrow + (size_t)(4 * i) * g.ldr)
+                                                             : make_float4(0.f, 0.f, 0.f, 0.f);
+    mbar_wait(accum_full, 0);                          // the residual's latency hides behind the tail of the k-loop
     tcgen05_fence_after();
     if (trace && t == 0) trace[3] = clock64();
 #pragma unroll 1
@@ -308,7 +308,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
       if (trace && t == 0 && cc < 2) trace[56 + 3 * cc] = clock64();
       const int c = c0 + cc * 32;
       if (c >= ncols) continue;                                // warp-uniform
-      if (g.qkv && c >= 2 * kD) {
+      if (MODE == 2 && c >= 2 * kD) {
         // V: key column of this row in Vt; image 1 starts at a 64-aligned column (TMA box starts must be 16-byte
         // aligned in global memory).  Lanes = consecutive rows = consecutive addresses: coalesced as it is.
         const int r = r0 + 32 * q + lane;
@@ -331,45 +331,67 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
       __syncwarp();                                            // the previous chunk has been read back
 #pragma unroll
       for (int j = 0; j < 32; j += 4)
-        *reinterpret_cast<uint4*>(stg + lane * kStgLd + j) = make_uint4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (uint32_t)((lane * kStgLd + j) * 4)), "r"(v[j]),
+                     "r"(v[j + 1]), "r"(v[j + 2]), "r"(v[j + 3])
+                     : "memory");
       __syncwarp();
       if (trace && t == 0 && cc < 2) trace[57 + 3 * cc] = clock64();
-      if (g.score) {
+      if (MODE == 1) {
         // couplings rows are n1_max + 1 floats long (not 16-byte aligned) and end raggedly: scalar, one row per store
         if (c + lane < ncols) {
-#pragma unroll 4
+          float* yp = g.Y + (size_t)(r0 + 32 * q) * g.ldy + c + lane;
+          const int nrow = min(32, rows - (r0 + 32 * q));
+#pragma unroll 8
           for (int i = 0; i < 32; ++i) {
-            const int r = r0 + 32 * q + i;
-            if (r < rows) g.Y[(size_t)r * g.ldy + c + lane] = stg[i * kStgLd + lane] * g.scale;
+            float x;
+            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(stg + (uint32_t)((i * kStgLd + lane) * 4)) : "memory");
+            if (i < nrow) yp[(size_t)i * g.ldy] = x * g.scale;
           }
         }
         continue;
       }
       const float4 bias4 = *reinterpret_cast<const float4*>(bias_s + cc * 32 + cj);
+      float4 o[8];
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
-        const int r = r0 + 32 * q + i * 4 + rl0;
-        float4 oi = *reinterpret_cast<const float4*>(stg + (i * 4 + rl0) * kStgLd + cj);
-        oi.x += bias4.x + rres[i].x; oi.y += bias4.y + rres[i].y;
-        oi.z += bias4.z + rres[i].z; oi.w += bias4.w + rres[i].w;
-        if (use_r && cc + 1 < BN / 32 && r < rows)             // the next chunk's residual, one chunk ahead
-          rres[i] = *reinterpret_cast<const float4*>(g.R + (size_t)(rbase + r) * g.ldr + c + 32 + cj);
-        if (r >= rows) continue;
-        const size_t grow = (size_t)(rbase + r);
-        if (g.qkv) {
-          const int part = c >> 8, cc256 = c & 255;            // 0: Q, 1: K
-          float* hi = (part == 0 ? g.qp : g.kp) + grow * kD + cc256 + cj;
-          float* lo = hi + (size_t)g.rows_total * kD;
-          const float sc = part == 0 ? 0.18033688011112042f : 1.f;   // log2(e)/sqrt(64): scores in the log2 domain
+        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                     : "=f"(o[i].x), "=f"(o[i].y), "=f"(o[i].z), "=f"(o[i].w)
+                     : "r"(stg + (uint32_t)(((i * 4 + rl0) * kStgLd + cj) * 4))
+                     : "memory");
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        o[i].x += bias4.x + rres[i].x; o[i].y += bias4.y + rres[i].y;
+        o[i].z += bias4.z + rres[i].z; o[i].w += bias4.w + rres[i].w;
+      }
+      if (use_r && cc + 1 < BN / 32 && c + 32 < ncols) {       // the next chunk's residual, one chunk ahead
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (4 * i < nvalid) rres[i] = *reinterpret_cast<const float4*>(rrow + (size_t)(4 * i) * g.ldr + (cc + 1) * 32);
+      }
+      if (MODE == 2) {
+        const int part = c >> 8;                               // 0: Q, 1: K (warp-uniform)
+        float* hi = (part == 0 ? g.qp : g.kp) + (size_t)(rbase + rfirst) * kD + (c & 255) + cj;
+        const size_t plane = (size_t)g.rows_total * kD;
+        const float sc = part == 0 ? 0.18033688011112042f : 1.f;   // log2(e)/sqrt(64): scores in the log2 domain
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
           float4 h, l;
-          split_tf32(oi.x * sc, h.x, l.x); split_tf32(oi.y * sc, h.y, l.y);
-          split_tf32(oi.z * sc, h.z, l.z); split_tf32(oi.w * sc, h.w, l.w);
-          *reinterpret_cast<float4*>(hi) = h;
-          *reinterpret_cast<float4*>(lo) = l;
-        } else {
-          float4 y = oi;
-          if (g.relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
-          *reinterpret_cast<float4*>(g.Y + grow * g.ldy + c + cj) = y;
+          split_tf32(o[i].x * sc, h.x, l.x); split_tf32(o[i].y * sc, h.y, l.y);
+          split_tf32(o[i].z * sc, h.z, l.z); split_tf32(o[i].w * sc, h.w, l.w);
+          if (4 * i < nvalid) {
+            *reinterpret_cast<float4*>(hi + (size_t)(4 * i) * kD) = h;
+            *reinterpret_cast<float4*>(hi + (size_t)(4 * i) * kD + plane) = l;
+          }
+        }
+      } else {
+        float* yp = g.Y + (size_t)(rbase + rfirst) * g.ldy + c + cj;
+        const bool relu = g.relu != 0;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 y = o[i];
+          if (relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+          if (4 * i < nvalid) *reinterpret_cast<float4*>(yp + (size_t)(4 * i) * g.ldy) = y;
         }
       }
       if (trace && t == 0 && cc < 2) trace[58 + 3 * cc] = clock64();
@@ -399,11 +421,11 @@ __global__ void k_split_planes(const float* __restrict__ x, float* __restrict__ 
   reinterpret_cast<float4*>(lo)[i] = l;
 }
 
-template <int BN>
+template <int BN, int MODE>
 int launch_tc(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& whi, const CUtensorMap& wlo,
               const TcArgs& g, int col_tiles, int row_tiles, int prof_class, cudaStream_t st) {
   using Cfg = TcCfg<BN>;
-  GIMS_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+  GIMS_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(col_tiles, row_tiles);
   cfg.blockDim = dim3(kThreadsTc);
@@ -412,7 +434,7 @@ int launch_tc(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w
   cfg.attrs = nullptr;
   cfg.numAttrs = 0;
   ProfScope prof(prof_class, st);
-  GIMS_CUDA_OK(cudaLaunchKernelEx(&cfg, k_gemm_tc<BN>, a0, a1, whi, wlo, g));
+  GIMS_CUDA_OK(cudaLaunchKernelEx(&cfg, k_gemm_tc<BN, MODE>, a0, a1, whi, wlo, g));
   count_launch();
   return GIMS_OK;
 }
@@ -435,7 +457,7 @@ int launch_gemm_tc(const GemmArgs& a, const float* w_hi, const float* w_lo, cuda
     return GIMS_ERR_ARG;
   }
   int total_rows = a.segs.nseg > 1 ? a.segs.base[1] + a.segs.nmax[1] : a.segs.nmax[0];
-  int bn = pick_bn(a.N);
+  int bn = qkv ? 192 : pick_bn(a.N);
   CUtensorMap mA0, mA1, mWh, mWl;
   GIMS_TRY(tc::make_tmap_f32_k32(&mA0, a.A0, total_rows, a.K0, a.lda0, BM));
   if (a.K1) GIMS_TRY(tc::make_tmap_f32_k32(&mA1, a.A1, total_rows, a.K1, a.lda1, BM));
@@ -454,10 +476,11 @@ int launch_gemm_tc(const GemmArgs& a, const float* w_hi, const float* w_lo, cuda
   int tiles = g.tiles0 + (a.segs.nseg > 1 ? cdiv(a.segs.nmax[1], BM) : 0);
   if (tiles == 0) return GIMS_OK;
   int ct = cdiv(a.N, bn);
+  if (qkv) return launch_tc<192, 2>(mA0, mA1, mWh, mWl, g, ct, tiles, GIMS_PROF_GEMM, st);
   switch (bn) {
-    case 192: return launch_tc<192>(mA0, mA1, mWh, mWl, g, ct, tiles, GIMS_PROF_GEMM, st);
-    case 128: return launch_tc<128>(mA0, mA1, mWh, mWl, g, ct, tiles, GIMS_PROF_GEMM, st);
-    default:  return launch_tc<64>(mA0, mA1, mWh, mWl, g, ct, tiles, GIMS_PROF_GEMM, st);
+    case 192: return launch_tc<192, 0>(mA0, mA1, mWh, mWl, g, ct, tiles, GIMS_PROF_GEMM, st);
+    case 128: return launch_tc<128, 0>(mA0, mA1, mWh, mWl, g, ct, tiles, GIMS_PROF_GEMM, st);
+    default:  return launch_tc<64, 0>(mA0, mA1, mWh, mWl, g, ct, tiles, GIMS_PROF_GEMM, st);
   }
 }
 
@@ -492,7 +515,7 @@ int launch_score_gemm_tc(const float* mdesc, int n0_max, int n1_max, const int* 
   g.segs.base[0] = 0; g.segs.base[1] = n0_max; g.segs.nmax[0] = n0_max; g.segs.nmax[1] = n1_max; g.segs.n_dev = n_dev;
   g.segs.nseg = 2;
   g.tiles0 = cdiv(n0_max, BM);
-  return launch_tc<bn>(mA, mA, mWh, mWl, g, cdiv(n1_max, bn), g.tiles0, GIMS_PROF_SCORE, st);
+  return launch_tc<bn, 1>(mA, mA, mWh, mWl, g, cdiv(n1_max, bn), g.tiles0, GIMS_PROF_SCORE, st);
 }
 
 }  // namespace gims
