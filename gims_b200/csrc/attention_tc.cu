@@ -75,6 +75,11 @@ __device__ __forceinline__ float ex2_approx(float x) {
 __global__ void __launch_bounds__(kAttnThreads, 1)
 k_attention_tc(const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapVt, AttnTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
+  if (g_attn_trace && (blockIdx.x | blockIdx.y | blockIdx.z | threadIdx.x) == 0) {
+    unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+    g_attn_trace[40 * 8 + 0] = clock64();
+    g_attn_trace[40 * 8 + 2] = (long long)gt;
+  }
   const int img = blockIdx.z, head = blockIdx.y;
   const int src = a.cross ? 1 - img : img;
   // counts come from device memory; the shuffle makes them provably warp-uniform for the compiler, so that the
@@ -119,6 +124,36 @@ k_attention_tc(const __grid_constant__ CUtensorMap mapK, const __grid_constant__
     mbar_init(q_ready, 4);
     fence_barrier_init();
   }
+  // This thread's Q row is requested before the CTA-wide sync: the global round trip overlaps the TMEM allocation and
+  // the barrier hand-shake instead of following them.  (Not the first TMA stages: the issuing thread would stall on
+  // the tensor-map fetch and hold up the sync.)
+  int tma_j = 0, tma_s = 0; uint32_t tma_ph = 0;
+  auto tma_produce = [&](int j_end) {
+    for (; tma_j < j_end; ++tma_j) {
+      const int key0 = krow0 + tma_j * TKV;                   // row in the K planes
+      const int vcol0 = (src ? a.vbase1 : 0) + tma_j * TKV;   // key column in the Vt planes (multiple of 64)
+      mbar_wait(&k_empty[tma_s], tma_ph ^ 1);
+      mbar_arrive_expect_tx(&k_full[tma_s], kKStageBytes);
+      for (int pl = 0; pl < 2; ++pl)
+        for (int hf = 0; hf < 2; ++hf)      // K box: 64 keys x 32 channels
+          tma_load_2d(k_smem + tma_s * kKStageBytes + (pl * 2 + hf) * kBoxBytesKV, &mapK, &k_full[tma_s],
+                      head * HD + hf * 32, pl * a.rows_total + key0);
+      mbar_wait(&v_empty[tma_s], tma_ph ^ 1);
+      mbar_arrive_expect_tx(&v_full[tma_s], kKStageBytes);
+      for (int pl = 0; pl < 2; ++pl)
+        for (int hf = 0; hf < 2; ++hf)      // Vt box: 64 channels x 32 keys
+          tma_load_2d(v_smem + tma_s * kKStageBytes + (pl * 2 + hf) * kBoxBytesKV, &mapVt, &v_full[tma_s],
+                      vcol0 + hf * 32, pl * kD + head * HD);
+      if (++tma_s == kStagesKV) { tma_s = 0; tma_ph ^= 1; }
+    }
+  };
+  float4 qreg[HD / 4];                                         // warps 0..3: fp32 Q row (scaled by log2(e)/8)
+  if (warp < 4) {
+    const int qr = q0 + 32 * warp + lane;
+    const float4* p4 = reinterpret_cast<const float4*>(a.qp + (size_t)(qrow0 + 32 * warp + lane) * kD + head * HD);
+#pragma unroll
+    for (int i = 0; i < HD / 4; ++i) qreg[i] = (qr < nq) ? p4[i] : make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   if (warp == kWarpMma) tmem_alloc<512>(tmem_slot);
   tcgen05_fence_before();
   __syncthreads();
@@ -127,24 +162,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap mapK, const __grid_constant__
 
   if (threadIdx.x == kWarpTma * 32) {
     // ===== TMA producer =====
-    int s = 0; uint32_t ph = 0;
-    for (int j = 0; j < ntiles; ++j) {
-      const int key0 = krow0 + j * TKV;                       // row in the K planes
-      const int vcol0 = (src ? a.vbase1 : 0) + j * TKV;       // key column in the Vt planes (multiple of 64)
-      mbar_wait(&k_empty[s], ph ^ 1);
-      mbar_arrive_expect_tx(&k_full[s], kKStageBytes);
-      for (int pl = 0; pl < 2; ++pl)
-        for (int hf = 0; hf < 2; ++hf)      // K box: 64 keys x 32 channels
-          tma_load_2d(k_smem + s * kKStageBytes + (pl * 2 + hf) * kBoxBytesKV, &mapK, &k_full[s], head * HD + hf * 32,
-                      pl * a.rows_total + key0);
-      mbar_wait(&v_empty[s], ph ^ 1);
-      mbar_arrive_expect_tx(&v_full[s], kKStageBytes);
-      for (int pl = 0; pl < 2; ++pl)
-        for (int hf = 0; hf < 2; ++hf)      // Vt box: 64 channels x 32 keys
-          tma_load_2d(v_smem + s * kKStageBytes + (pl * 2 + hf) * kBoxBytesKV, &mapVt, &v_full[s], vcol0 + hf * 32,
-                      pl * kD + head * HD);
-      if (++s == kStagesKV) { s = 0; ph ^= 1; }
-    }
+    tma_produce(ntiles);
   } else if (threadIdx.x == kWarpMma * 32) {
     // ===== QK issuer: ONE thread, all operand arithmetic in the uniform datapath (descriptor = base + constant) =====
     constexpr uint32_t idesc = umma_idesc_tf32(TQ, TKV);      // M=128, N=64
@@ -212,22 +230,21 @@ k_attention_tc(const __grid_constant__ CUtensorMap mapK, const __grid_constant__
     // ===== softmax / accumulate warps: thread <-> query row =====
     const uint32_t lane_base = tmem + ((uint32_t)(32 * warp) << 16);
     const int row = q0 + 32 * warp + lane;
-    {   // Q planes of my row -> TMEM (zeros for rows past the live count: nothing of them is ever stored)
-      const float* qsrc = a.qp + (size_t)(qrow0 + 32 * warp + lane) * kD + head * HD;
+    {   // Q row -> tf32 hi / lo planes in TMEM (zeros for rows past the live count: nothing of them is ever stored)
 #pragma unroll
-      for (int pl = 0; pl < 2; ++pl) {
-        const float4* p4 = reinterpret_cast<const float4*>(qsrc + (size_t)pl * a.rows_total * kD);
+      for (int h = 0; h < 2; ++h) {
+        uint32_t vh[32], vl[32];
 #pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t v[32];
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float4 x = (row < nq) ? p4[h * 8 + i] : make_float4(0.f, 0.f, 0.f, 0.f);
-            v[4 * i] = __float_as_uint(x.x); v[4 * i + 1] = __float_as_uint(x.y);
-            v[4 * i + 2] = __float_as_uint(x.z); v[4 * i + 3] = __float_as_uint(x.w);
-          }
-          tmem_st_32x32(lane_base + (pl ? cQl : cQh) + h * 32, v);
+        for (int i = 0; i < 8; ++i) {
+          const float4 x = qreg[h * 8 + i];
+          float hi, lo;
+          split_tf32(x.x, hi, lo); vh[4 * i] = __float_as_uint(hi); vl[4 * i] = __float_as_uint(lo);
+          split_tf32(x.y, hi, lo); vh[4 * i + 1] = __float_as_uint(hi); vl[4 * i + 1] = __float_as_uint(lo);
+          split_tf32(x.z, hi, lo); vh[4 * i + 2] = __float_as_uint(hi); vl[4 * i + 2] = __float_as_uint(lo);
+          split_tf32(x.w, hi, lo); vh[4 * i + 3] = __float_as_uint(hi); vl[4 * i + 3] = __float_as_uint(lo);
         }
+        tmem_st_32x32(lane_base + cQh + h * 32, vh);
+        tmem_st_32x32(lane_base + cQl + h * 32, vl);
       }
       tmem_st_wait();
       tcgen05_fence_before();
@@ -325,6 +342,11 @@ k_attention_tc(const __grid_constant__ CUtensorMap mapK, const __grid_constant__
   if (warp == kWarpMma) {
     tcgen05_fence_after();
     tmem_dealloc<512>(tmem);
+    if (g_attn_trace && (blockIdx.x | blockIdx.y | blockIdx.z) == 0 && lane == 0) {
+      unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+      g_attn_trace[40 * 8 + 1] = clock64();
+      g_attn_trace[40 * 8 + 3] = (long long)gt;
+    }
   }
 }
 

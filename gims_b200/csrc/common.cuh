@@ -114,7 +114,7 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st);
 
 // tensor-core (tcgen05, 3xTF32) variants — gemm_tc.cu
 struct QkvPlanes {            // outputs of the QKV projection in the layout attention_tc.cu consumes
-  float* qp;                  // [2][rows_total][256]
+  float* qp;                  // [rows_total][256] fp32, scaled by log2(e)/8 (room for two planes is reserved)
   float* kp;                  // [2][rows_total][256]
   float* vt;                  // [2][256][ldv]; key columns: image 0 at [0, n0), image 1 at [vbase1, vbase1 + n1)
   int ldv;                    // multiple of 4

@@ -98,7 +98,7 @@ struct TcArgs {
   Segs segs;
   int tiles0;
   // qkv mode (N = 768): instead of Y the epilogue writes the tf32 planes the attention kernel consumes:
-  //   columns [0,256)   -> Qp [2][rows_total][256]  (hi, lo) of (acc + bias) * log2(e)/8
+  //   columns [0,256)   -> Qp [rows_total][256]     fp32 (acc + bias) * log2(e)/8
   //   columns [256,512) -> Kp [2][rows_total][256]
   //   columns [512,768) -> Vt [2][256][ldv]          transposed; rows beyond the live count are zero-filled
   int qkv;
@@ -165,6 +165,23 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
     mbar_init(accum_full, (Cfg::kIssuers == 2 && nkb >= 2) ? 2 : 1);   // one commit per issuer that has k-blocks
     fence_barrier_init();
   }
+  auto stage_ptr = [&](int s) { return smem + (size_t)s * Cfg::kStageBytes; };
+  int tma_kb = 0, tma_s = 0; uint32_t tma_ph = 0;
+  auto tma_produce = [&](int kb_end) {
+    for (; tma_kb < kb_end; ++tma_kb) {
+      mbar_wait(&empty[tma_s], tma_ph ^ 1);
+      uint8_t* st = stage_ptr(tma_s);
+      mbar_arrive_expect_tx(&full[tma_s], Cfg::kABytes + 2 * Cfg::kWBytes);
+      const int k = tma_kb * BK;
+      if (k < g.K0) tma_load_2d(st, &mapA0, &full[tma_s], k, rbase + r0);
+      else          tma_load_2d(st, &mapA1, &full[tma_s], k - g.K0, rbase + r0);
+      tma_load_2d(st + Cfg::kABytes, &mapWhi, &full[tma_s], k, wbase + c0);
+      tma_load_2d(st + Cfg::kABytes + Cfg::kWBytes, &mapWlo, &full[tma_s], k, wbase + c0);
+      if (++tma_s == Cfg::kStages) { tma_s = 0; tma_ph ^= 1; }
+    }
+  };
+  // (Issuing the first stages before the CTA-wide sync was tried: the issuing thread stalls on the tensor-map fetch and
+  // delays the sync for everybody — the prologue went from 1200 to 4100 clk.)
   if (warp == kWarpMma) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
   if (threadIdx.x < BN) bias_s[threadIdx.x] = (g.bias && c0 + (int)threadIdx.x < g.N) ? g.bias[c0 + threadIdx.x] : 0.f;
   tcgen05_fence_before();
@@ -173,24 +190,9 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform for the compiler
   if (trace && threadIdx.x == 0) trace[1] = clock64();
 
-  auto stage_ptr = [&](int s) { return smem + (size_t)s * Cfg::kStageBytes; };
-
   if (warp == kWarpTma) {
     // ===== TMA producer =====
-    if (lane == 0) {
-      int s = 0; uint32_t ph = 0;
-      for (int kb = 0; kb < nkb; ++kb) {
-        mbar_wait(&empty[s], ph ^ 1);
-        uint8_t* st = stage_ptr(s);
-        mbar_arrive_expect_tx(&full[s], Cfg::kABytes + 2 * Cfg::kWBytes);
-        int k = kb * BK;
-        if (k < g.K0) tma_load_2d(st, &mapA0, &full[s], k, rbase + r0);
-        else          tma_load_2d(st, &mapA1, &full[s], k - g.K0, rbase + r0);
-        tma_load_2d(st + Cfg::kABytes, &mapWhi, &full[s], k, wbase + c0);
-        tma_load_2d(st + Cfg::kABytes + Cfg::kWBytes, &mapWlo, &full[s], k, wbase + c0);
-        if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
-      }
-    }
+    if (lane == 0) tma_produce(nkb);
   } else if (warp >= kWarpMma) {
     // ===== MMA issuers: lane 0 of warp kWarpMma + t handles the k-blocks kb = t, t + kIssuers, ... =====
     // A comes from TMEM (written by the splitters), W from shared memory: with A in shared memory as well the
@@ -370,18 +372,28 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
           if (4 * i < nvalid) rres[i] = *reinterpret_cast<const float4*>(rrow + (size_t)(4 * i) * g.ldr + (cc + 1) * 32);
       }
       if (MODE == 2) {
-        const int part = c >> 8;                               // 0: Q, 1: K (warp-uniform)
-        float* hi = (part == 0 ? g.qp : g.kp) + (size_t)(rbase + rfirst) * kD + (c & 255) + cj;
-        const size_t plane = (size_t)g.rows_total * kD;
-        const float sc = part == 0 ? 0.18033688011112042f : 1.f;   // log2(e)/sqrt(64): scores in the log2 domain
+        if (c < kD) {
+          // Q: one fp32 plane, scaled by log2(e)/sqrt(64) (scores in the log2 domain); the attention kernel splits
+          // its own query rows when it loads them into TMEM
+          float* qd = g.qp + (size_t)(rbase + rfirst) * kD + c + cj;
+          const float sc = 0.18033688011112042f;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float4 h, l;
-          split_tf32(o[i].x * sc, h.x, l.x); split_tf32(o[i].y * sc, h.y, l.y);
-          split_tf32(o[i].z * sc, h.z, l.z); split_tf32(o[i].w * sc, h.w, l.w);
-          if (4 * i < nvalid) {
-            *reinterpret_cast<float4*>(hi + (size_t)(4 * i) * kD) = h;
-            *reinterpret_cast<float4*>(hi + (size_t)(4 * i) * kD + plane) = l;
+          for (int i = 0; i < 8; ++i)
+            if (4 * i < nvalid)
+              *reinterpret_cast<float4*>(qd + (size_t)(4 * i) * kD) =
+                  make_float4(o[i].x * sc, o[i].y * sc, o[i].z * sc, o[i].w * sc);
+        } else {
+          float* hi = g.kp + (size_t)(rbase + rfirst) * kD + (c & 255) + cj;
+          const size_t plane = (size_t)g.rows_total * kD;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            float4 h, l;
+            split_tf32(o[i].x, h.x, l.x); split_tf32(o[i].y, h.y, l.y);
+            split_tf32(o[i].z, h.z, l.z); split_tf32(o[i].w, h.w, l.w);
+            if (4 * i < nvalid) {
+              *reinterpret_cast<float4*>(hi + (size_t)(4 * i) * kD) = h;
+              *reinterpret_cast<float4*>(hi + (size_t)(4 * i) * kD + plane) = l;
+            }
           }
         }
       } else {

@@ -25,6 +25,16 @@ torch.cuda.synchronize()
 L.gims_debug_attention_trace(None)
 t = trace.cpu().view(64, 8)
 t0 = int(t[0, 0])
+x = [int(v) for v in t[40]]
+print('kernel entry -> first tile top: %d clk; last stamp -> exit: see below; entry -> exit %d clk = %d ns (globaltimer)' %
+      (t0 - x[0], x[1] - x[0], x[3] - x[2]))
+e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+e0.record()
+for it in range(20):
+    _lib.check(L.gims_attn_layer_forward(model, 0, _lib.ptr(desc), n0, n1, _lib.ptr(nd), _lib.ptr(scratch), st), 'time')
+e1.record()
+torch.cuda.synchronize()
+print('whole layer (QKV GEMM + attention + MLP1 + MLP2), back to back: %.1f us' % (e0.elapsed_time(e1) * 1000 / 20))
 print('tile  qk_issue  pv_ready  pv_issued | s_seen(w0)  p_given by warp 0,1,2,3   (cycles since first stamp)')
 prev = None
 for j in range(32):
