@@ -298,6 +298,108 @@ __global__ void __launch_bounds__(kThreads, 1) k_sinkhorn(SinkArgs a) {
     const size_t cs_ld = ((size_t)a.ldp + 3) & ~(size_t)3;
     float vref = 0.f;                               // reference the current w_s was scaled with (initially v = 0, w = 1)
     unsigned target = 0;
+    if (Gf <= kThreads) {
+      // ----- register-resident variant (C <= 4 * kThreads + 3, i.e. up to 2048 keypoints in image 1): thread t owns the
+      // float4 column group t of every slab row in registers (<= 16 rows x 4 floats) together with the group's weights,
+      // so neither pass reads the slab from shared memory: the row pass is 64 FMAs + a block reduction of <= 16 row
+      // sums, the column pass 64 FMAs whose result is already this CTA's complete partial for those columns.  The
+      // (<= 3) columns past the last full group, among them the dustbin column, still come from the shared-memory slab.
+      const bool own = tid < Gf;
+      float4 ereg[kRMax];
+#pragma unroll
+      for (int r = 0; r < kRMax; ++r)
+        ereg[r] = (own && r < nrows) ? *reinterpret_cast<const float4*>(slab + (size_t)r * a.slab_ld + 4 * tid)
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+      float4 wreg = make_float4(1.f, 1.f, 1.f, 1.f);
+      for (int it = 0; it < a.iters; ++it) {
+        SINK_TRACE(0);
+        float* cs = a.colsum + (size_t)(it % 3) * cs_ld;
+        const float Rref = norm - vref;
+        float part[kRMax];
+#pragma unroll
+        for (int r = 0; r < kRMax; ++r)
+          part[r] = fmaf(ereg[r].x, wreg.x, ereg[r].y * wreg.y) + fmaf(ereg[r].z, wreg.z, ereg[r].w * wreg.w);
+        // 16 sums over 32 lanes with 16 shuffles (a butterfly that halves the number of live values per step) instead
+        // of 16 x 5: shuffles issue at one warp instruction per clock per SM and were the longest part of this pass
+        static_assert(kRMax == 16, "the butterfly below is written for 16 row sums");
+#pragma unroll
+        for (int h = 8, bit = 16; h >= 1; h >>= 1, bit >>= 1) {
+          const bool up = (lane & bit) != 0;
+#pragma unroll
+          for (int i = 0; i < h; ++i) {
+            const float send = up ? part[i] : part[i + h];
+            const float keep = up ? part[i + h] : part[i];
+            part[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+          }
+        }
+        part[0] += __shfl_xor_sync(0xffffffffu, part[0], 1);
+        if ((lane & 1) == 0) red_m[warp][lane >> 1] = part[0];      // lane 2r holds the warp's sum of row r
+        __syncthreads();
+        if (tid < nrows) {                              // thread r finishes row r
+          float sr = 0.f;
+#pragma unroll
+          for (int w = 0; w < kWarps; ++w) sr += red_m[w][tid];
+          for (int j = 4 * Gf; j < C; ++j) sr = fmaf(slab[(size_t)tid * a.slab_ld + j], w_s[j], sr);
+          const float lmu = (r_begin + tid == n0) ? log_mu_last : norm;
+          const float lse_rel = vref + logf(sr);               // LSE_j(z + v) - rowmax
+          e_s[tid] = ex2(((lmu - lse_rel) - Rref) * kLog2e);    // exp(u_r + rowmax_r - Rref)
+          u_s[tid] = lmu - (rmax_s[tid] + lse_rel);
+        }
+        __syncthreads();
+        SINK_TRACE(1);
+        if (b < Ga) {
+          if (own) {
+            float4 sm = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+            for (int r = 0; r < kRMax; ++r) {
+              const float er = (r < nrows) ? e_s[r] : 0.f;
+              sm.x = fmaf(ereg[r].x, er, sm.x); sm.y = fmaf(ereg[r].y, er, sm.y);
+              sm.z = fmaf(ereg[r].z, er, sm.z); sm.w = fmaf(ereg[r].w, er, sm.w);
+            }
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cs + 4 * tid), "f"(sm.x), "f"(sm.y),
+                         "f"(sm.z), "f"(sm.w)
+                         : "memory");
+          }
+          const int jl = 4 * Gf + warp;                 // the (at most 3) left-over columns
+          if (jl < C) {
+            const float xx = (lane < nrows) ? slab[(size_t)lane * a.slab_ld + jl] * e_s[lane] : 0.f;
+            const float ss = warp_sum(xx);
+            if (lane == 0) atomicAdd(cs + jl, ss);
+          }
+        }
+        SINK_TRACE(2);
+        target += (unsigned)G;
+        grid_hop(a.counter, target, a.err);
+        SINK_TRACE(3);
+        {                                               // recycle the buffer that was read one iteration ago
+          float* old = a.colsum + (size_t)((it + 2) % 3) * cs_ld;
+          for (int j = c_begin + tid; j < c_end; j += kThreads) old[j] = 0.f;
+        }
+        const float v0 = norm - (Rref + logf(__ldcg(cs)));      // v of column 0: the next reference (n1 >= 1)
+        for (int g4 = tid; g4 < n4; g4 += kThreads) {
+          const float4 c4 = __ldcg(reinterpret_cast<const float4*>(cs) + g4);
+          const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
+          float wn[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int j = 4 * g4 + q;
+            wn[q] = 0.f;
+            if (j < C) {
+              const float lnu = (j == n1) ? log_nu_last : norm;
+              const float vj = lnu - (Rref + logf(cc[q]));
+              wn[q] = ex2((vj - v0) * kLog2e);
+              v_s[j] = vj;
+              w_s[j] = wn[q];
+              if (it == a.iters - 1 && j >= c_begin && j < c_end) a.v[j] = vj;
+            }
+          }
+          if (g4 == tid) wreg = make_float4(wn[0], wn[1], wn[2], wn[3]);
+        }
+        vref = v0;
+        __syncthreads();
+        SINK_TRACE(5);
+      }
+    } else
     for (int it = 0; it < a.iters; ++it) {
       SINK_TRACE(0);
       float* cs = a.colsum + (size_t)(it % 3) * cs_ld;
