@@ -130,8 +130,8 @@ __global__ void k_normalize_rows(const float* __restrict__ feat, int n, float* _
 // ---------------------------------------------------------------------------------------------
 // a-1  C2: S = fl32(Xhat Xhat^T accumulated in fp64), upper-triangular 64x64 tiles mirrored
 // ---------------------------------------------------------------------------------------------
-constexpr int kCT = 64;   // tile edge
-constexpr int kCK = 16;   // k-slab
+constexpr int kCT = 128;  // tile edge: 8 x 8 fp64 accumulators per thread — 64 DFMA per 16 shared-memory loads, which keeps
+constexpr int kCK = 16;   // the kernel on the fp64 pipe (at 4 x 4 it was bound by shared-memory bandwidth); k-slab of 16
 
 __global__ void __launch_bounds__(256) k_cosine_fp64(const float* __restrict__ xhat, int n, float* __restrict__ S) {
   int bi = blockIdx.y, bj = blockIdx.x;
@@ -140,37 +140,46 @@ __global__ void __launch_bounds__(256) k_cosine_fp64(const float* __restrict__ x
   __shared__ double Bs[kCK][kCT + 2];
   int tid = threadIdx.x;
   int tx = tid & 15, ty = tid >> 4;
-  double acc[4][4];
+  double acc[8][8];
 #pragma unroll
-  for (int a = 0; a < 4; ++a)
+  for (int a = 0; a < 8; ++a)
 #pragma unroll
-    for (int b = 0; b < 4; ++b) acc[a][b] = 0.0;
+    for (int b = 0; b < 8; ++b) acc[a][b] = 0.0;
   int i0 = bi * kCT, j0 = bj * kCT;
-  // loader mapping: 256 threads load 64 rows x 16 k: each thread one float4 (row = tid/4, k4 = tid%4)
+  // loader mapping: 256 threads load 128 rows x 16 k per operand: two float4 each (rows tid/4 and tid/4 + 64, k4 = tid%4)
   int lr = tid >> 2, lk = (tid & 3) * 4;
   for (int k0 = 0; k0 < kD; k0 += kCK) {
-    float4 va = make_float4(0.f, 0.f, 0.f, 0.f), vb = va;
-    if (i0 + lr < n) va = *reinterpret_cast<const float4*>(xhat + (size_t)(i0 + lr) * kD + k0 + lk);
-    if (j0 + lr < n) vb = *reinterpret_cast<const float4*>(xhat + (size_t)(j0 + lr) * kD + k0 + lk);
+    float4 va[2], vb[2];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      va[h] = make_float4(0.f, 0.f, 0.f, 0.f); vb[h] = va[h];
+      int r = lr + 64 * h;
+      if (i0 + r < n) va[h] = *reinterpret_cast<const float4*>(xhat + (size_t)(i0 + r) * kD + k0 + lk);
+      if (j0 + r < n) vb[h] = *reinterpret_cast<const float4*>(xhat + (size_t)(j0 + r) * kD + k0 + lk);
+    }
     __syncthreads();
-    As[lk + 0][lr] = va.x; As[lk + 1][lr] = va.y; As[lk + 2][lr] = va.z; As[lk + 3][lr] = va.w;
-    Bs[lk + 0][lr] = vb.x; Bs[lk + 1][lr] = vb.y; Bs[lk + 2][lr] = vb.z; Bs[lk + 3][lr] = vb.w;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      int r = lr + 64 * h;
+      As[lk + 0][r] = va[h].x; As[lk + 1][r] = va[h].y; As[lk + 2][r] = va[h].z; As[lk + 3][r] = va[h].w;
+      Bs[lk + 0][r] = vb[h].x; Bs[lk + 1][r] = vb[h].y; Bs[lk + 2][r] = vb[h].z; Bs[lk + 3][r] = vb[h].w;
+    }
     __syncthreads();
+#pragma unroll 4
+    for (int k = 0; k < kCK; ++k) {          // k ascending, one fma per k: the accumulation order of contract C2
+      double a[8], b[8];
 #pragma unroll
-    for (int k = 0; k < kCK; ++k) {
-      double a[4], b[4];
+      for (int q = 0; q < 8; ++q) { a[q] = As[k][ty + 16 * q]; b[q] = Bs[k][tx + 16 * q]; }
 #pragma unroll
-      for (int q = 0; q < 4; ++q) { a[q] = As[k][ty + 16 * q]; b[q] = Bs[k][tx + 16 * q]; }
+      for (int q = 0; q < 8; ++q)
 #pragma unroll
-      for (int q = 0; q < 4; ++q)
-#pragma unroll
-        for (int r = 0; r < 4; ++r) acc[q][r] = fma(a[q], b[r], acc[q][r]);
+        for (int r = 0; r < 8; ++r) acc[q][r] = fma(a[q], b[r], acc[q][r]);
     }
   }
 #pragma unroll
-  for (int q = 0; q < 4; ++q)
+  for (int q = 0; q < 8; ++q)
 #pragma unroll
-    for (int r = 0; r < 4; ++r) {
+    for (int r = 0; r < 8; ++r) {
       int i = i0 + ty + 16 * q, j = j0 + tx + 16 * r;
       if (i < n && j < n) {
         float v = (float)acc[q][r];

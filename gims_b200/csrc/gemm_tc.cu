@@ -64,7 +64,7 @@ struct TcCfg {
   static constexpr int kABytes = BM * BK * 4;            // 16 KB raw fp32 A tile
   static constexpr int kWBytes = BN * BK * 4;
   static constexpr int kStageBytes = kABytes + 2 * kWBytes;
-  static constexpr int kStages = (BN <= 64) ? 6 : (BN <= 128 ? 4 : 3);      // 192 KB of shared memory either way
+  static constexpr int kStages = (BN <= 64) ? 3 : (BN <= 128 ? 4 : 3);      // BN = 64: 96 KB, two CTAs per SM
   // Two issuer threads (even / odd k-blocks), each with its own accumulators: a single issuer leaves the tensor pipe
   // idle for ~40 % of the time around its commits (profiles/r01_gemm_pipeline_trace.txt).
   static constexpr int kIssuers = 2;
@@ -72,14 +72,14 @@ struct TcCfg {
   // chain grows linearly with its length.  Splitting the k-blocks over two accumulators halves the chains; at
   // BN = 64 TMEM also has room for separate accumulators for the two small correction products (kFold = false),
   // which takes their 2/3 of the roundings off the main chains.  The epilogue adds the accumulators in fp32 (RN).
-  static constexpr bool kFold = BN > 64;
+  static constexpr bool kFold = true;
   static constexpr int kMainAcc = 2;
   static constexpr int kCorrAcc = kFold ? 0 : kIssuers;
   static constexpr int kAccCols = (kMainAcc + kCorrAcc) * BN;
   // The A operand lives in TMEM: a ring of k-block slots, 32 columns A_hi + 32 columns A_lo each.
-  static constexpr int kRing = (512 - kAccCols) / 64 >= 4 ? 4 : 2;
+  static constexpr int kTmemCols = (BN <= 64) ? 256 : 512;                  // BN = 64: two CTAs per SM
+  static constexpr int kRing = (kTmemCols - kAccCols) / 64 >= 4 ? 4 : 2;
   static constexpr int kRingCol = kAccCols;
-  static constexpr int kTmemCols = 512;
   static_assert(kAccCols + kRing * 64 <= kTmemCols, "accumulators + A ring exceed TMEM");
   static constexpr int kBarriers = 2 * kStages + 2 * kRing + 1;
   static constexpr int kBiasOff = (kBarriers * 8 + 16 + 15) & ~15;       // after the barriers and the TMEM address slot
@@ -110,7 +110,7 @@ __device__ long long* g_gemm_trace = nullptr;
 
 // MODE 0: Y = act(acc + bias + R);  1: couplings (score GEMM);  2: Q / K / Vt tf32 planes (QKV projection)
 template <int BN, int MODE>
-__global__ void __launch_bounds__(kThreadsTc, 1)
+__global__ void __launch_bounds__(kThreadsTc, BN <= 64 ? 2 : 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
           const __grid_constant__ CUtensorMap mapWhi, const __grid_constant__ CUtensorMap mapWlo, TcArgs g) {
   using Cfg = TcCfg<BN>;
@@ -469,7 +469,8 @@ int launch_gemm_tc(const GemmArgs& a, const float* w_hi, const float* w_lo, cuda
     return GIMS_ERR_ARG;
   }
   int total_rows = a.segs.nseg > 1 ? a.segs.base[1] + a.segs.nmax[1] : a.segs.nmax[0];
-  int bn = qkv ? 192 : pick_bn(a.N);
+  int bn = pick_bn(a.N);
+  if (qkv && bn != 64) bn = 192;
   CUtensorMap mA0, mA1, mWh, mWl;
   GIMS_TRY(tc::make_tmap_f32_k32(&mA0, a.A0, total_rows, a.K0, a.lda0, BM));
   if (a.K1) GIMS_TRY(tc::make_tmap_f32_k32(&mA1, a.A1, total_rows, a.K1, a.lda1, BM));
@@ -488,7 +489,10 @@ int launch_gemm_tc(const GemmArgs& a, const float* w_hi, const float* w_lo, cuda
   int tiles = g.tiles0 + (a.segs.nseg > 1 ? cdiv(a.segs.nmax[1], BM) : 0);
   if (tiles == 0) return GIMS_OK;
   int ct = cdiv(a.N, bn);
-  if (qkv) return launch_tc<192, 2>(mA0, mA1, mWh, mWl, g, ct, tiles, GIMS_PROF_GEMM, st);
+  if (qkv) {
+    if (bn == 64) return launch_tc<64, 2>(mA0, mA1, mWh, mWl, g, ct, tiles, GIMS_PROF_GEMM, st);
+    return launch_tc<192, 2>(mA0, mA1, mWh, mWl, g, ct, tiles, GIMS_PROF_GEMM, st);
+  }
   switch (bn) {
     case 192: return launch_tc<192, 0>(mA0, mA1, mWh, mWl, g, ct, tiles, GIMS_PROF_GEMM, st);
     case 128: return launch_tc<128, 0>(mA0, mA1, mWh, mWl, g, ct, tiles, GIMS_PROF_GEMM, st);
