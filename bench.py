@@ -58,20 +58,59 @@ def pair_flops(n0, n1, layers=18, d=256):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md)."""
+    """SM clock and throttle reasons sampled DURING the timed region (B200_PROFILING.md): NVML polled every 2 ms from a
+    host thread; falls back to an `nvidia-smi -lms` child process if NVML is not usable."""
+
+    REASONS = ((0x4, 'sw_power_cap'), (0x8, 'hw_slowdown'), (0x20, 'sw_thermal_slowdown'), (0x40, 'hw_thermal_slowdown'),
+               (0x80, 'hw_power_brake_slowdown'))
 
     def __init__(self, index):
         self.index = index
         self.proc = None
         self.lines = []
+        self.nvml = None
+        self.samples = []
+        self.mask = 0
+        self.stop_flag = False
+
+    def _nvml_handle(self):
+        import pynvml
+        pynvml.nvmlInit()
+        try:
+            uuid = str(torch.cuda.get_device_properties(self.index).uuid)
+            if not uuid.startswith('GPU-'):
+                uuid = 'GPU-' + uuid
+            h = pynvml.nvmlDeviceGetHandleByUUID(uuid.encode() if hasattr(uuid, 'encode') else uuid)
+        except Exception:
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.index)
+        return pynvml, h
+
+    def _poll(self):
+        pynvml, h = self.nvml
+        while not self.stop_flag:
+            try:
+                self.samples.append(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM))
+                self.mask |= int(pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+            except Exception:
+                break
+            time.sleep(0.002)
 
     def start(self):
+        try:
+            self.nvml = self._nvml_handle()
+            pynvml, h = self.nvml
+            self.smax = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            self.t = threading.Thread(target=self._poll, daemon=True)
+            self.t.start()
+            return
+        except Exception:
+            self.nvml = None
         q = ('clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,'
              'clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,'
              'clocks_event_reasons.sw_power_cap')
         try:
             self.proc = subprocess.Popen(['nvidia-smi', '-i', str(self.index), '--query-gpu=' + q,
-                                          '--format=csv,noheader,nounits', '-lms', '100'],
+                                          '--format=csv,noheader,nounits', '-lms', '20'],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.t = threading.Thread(target=self._read, daemon=True)
             self.t.start()
@@ -83,6 +122,13 @@ class ClockSampler:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self.nvml is not None:
+            self.stop_flag = True
+            self.t.join(timeout=1)
+            sm = sorted(self.samples)
+            return {'sm_mhz': float(sm[len(sm) // 2]) if sm else None, 'sm_min_mhz': float(sm[0]) if sm else None,
+                    'sm_max_mhz': float(self.smax), 'reasons': [n for b, n in self.REASONS if self.mask & b],
+                    'samples': len(sm), 'source': 'nvml, 2 ms period'}
         if self.proc is None:
             return {'sm_mhz': None, 'sm_max_mhz': None, 'reasons': ['nvidia-smi unavailable']}
         self.proc.terminate()
@@ -105,7 +151,7 @@ class ClockSampler:
                     reasons.add(name)
         sm.sort()
         med = sm[len(sm) // 2] if sm else None
-        return {'sm_mhz': med, 'sm_max_mhz': smax, 'reasons': sorted(reasons), 'samples': len(sm)}
+        return {'sm_mhz': med, 'sm_max_mhz': smax, 'reasons': sorted(reasons), 'samples': len(sm), 'source': 'nvidia-smi'}
 
 
 def run_reference(args, rank, world):

@@ -148,8 +148,8 @@ __global__ void __launch_bounds__(256) k_cosine_fp64(const float* __restrict__ x
   int i0 = bi * kCT, j0 = bj * kCT;
   // loader mapping: 256 threads load 128 rows x 16 k per operand: two float4 each (rows tid/4 and tid/4 + 64, k4 = tid%4)
   int lr = tid >> 2, lk = (tid & 3) * 4;
-  for (int k0 = 0; k0 < kD; k0 += kCK) {
-    float4 va[2], vb[2];
+  float4 va[2], vb[2];
+  auto fetch = [&](int k0) {
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
       va[h] = make_float4(0.f, 0.f, 0.f, 0.f); vb[h] = va[h];
@@ -157,6 +157,9 @@ __global__ void __launch_bounds__(256) k_cosine_fp64(const float* __restrict__ x
       if (i0 + r < n) va[h] = *reinterpret_cast<const float4*>(xhat + (size_t)(i0 + r) * kD + k0 + lk);
       if (j0 + r < n) vb[h] = *reinterpret_cast<const float4*>(xhat + (size_t)(j0 + r) * kD + k0 + lk);
     }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < kD; k0 += kCK) {
     __syncthreads();
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -165,6 +168,7 @@ __global__ void __launch_bounds__(256) k_cosine_fp64(const float* __restrict__ x
       Bs[lk + 0][r] = vb[h].x; Bs[lk + 1][r] = vb[h].y; Bs[lk + 2][r] = vb[h].z; Bs[lk + 3][r] = vb[h].w;
     }
     __syncthreads();
+    if (k0 + kCK < kD) fetch(k0 + kCK);      // the next slab's global loads fly during this slab's FMAs
 #pragma unroll 4
     for (int k = 0; k < kCK; ++k) {          // k ascending, one fma per k: the accumulation order of contract C2
       double a[8], b[8];
