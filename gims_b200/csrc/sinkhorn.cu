@@ -54,9 +54,6 @@ struct SinkArgs {
   int slab_ld;                     // padded row length of the slab (multiple of 4)
 };
 
-__device__ __forceinline__ u64 pack2(float a, float b) {
-  return (u64)__float_as_uint(a) | ((u64)__float_as_uint(b) << 32);
-}
 __device__ __forceinline__ void st_relaxed(u64* p, u64 v) {
   asm volatile("st.relaxed.gpu.global.b64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
 }
@@ -278,9 +275,6 @@ __global__ void __launch_bounds__(kThreads, 1) k_sinkhorn(SinkArgs a) {
       __syncthreads();
     }
   }
-  float vmax = 0.f;                                 // reference the current w_s was scaled with (scaled-kernel path)
-  float ut_ref = 0.f;                               // reference of the column-pass weights e_s (a recent ut_0)
-  float vmax_next = 0.f;                            // v_0 of the current v: reference for the next gather
 
   long long* trace = (b == 0 && tid == 0) ? g_sink_trace : nullptr;
   const bool reg_rows = resident && (C4 >> 2) <= kRowChunks * 32;   // a row's (z + v) fits the lanes' registers
@@ -480,31 +474,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sinkhorn(SinkArgs a) {
   for (int it = 0; it < a.iters; ++it) {
     SINK_TRACE(0);
     // ---- row pass -------------------------------------------------------------------------
-    if (fast) {
-      const int n4 = C4 >> 2;
-      for (int r = warp; r < nrows; r += kWarps) {
-        const float4* e4 = reinterpret_cast<const float4*>(slab + (size_t)r * a.slab_ld);
-        const float4* w4 = reinterpret_cast<const float4*>(w_s);
-        float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-        for (int k = 0; k < kRowChunks; ++k) {
-          const int i = lane + 32 * k;
-          if (i < n4) {
-            const float4 ee = e4[i], ww = w4[i];
-            s0 = fmaf(ee.x, ww.x, s0); s1 = fmaf(ee.y, ww.y, s1); s2 = fmaf(ee.z, ww.z, s2); s3 = fmaf(ee.w, ww.w, s3);
-          }
-        }
-        const float sr = warp_sum((s0 + s1) + (s2 + s3));
-        if (lane == 0) {
-          const float lmu = (r_begin + r == n0) ? log_mu_last : norm;
-          const float lse_rel = vmax + logf(sr);               // LSE_j(z + v) - rowmax
-          const float ut = lmu - lse_rel;                      // u_r + rowmax_r
-          ut_s[r] = ut;
-          e_s[r] = ex2((ut - ut_ref) * kLog2e);                // column-pass weight, reference = last iteration's ut_0
-          u_s[r] = lmu - (rmax_s[r] + lse_rel);
-        }
-      }
-    } else if (reg_rows) {
+    if (reg_rows) {
       const int n4 = C4 >> 2;
       for (int r = warp; r < nrows; r += kWarps) {
         const float4* z4 = reinterpret_cast<const float4*>(slab + (size_t)r * a.slab_ld);
@@ -552,35 +522,10 @@ __global__ void __launch_bounds__(kThreads, 1) k_sinkhorn(SinkArgs a) {
       }
     }
     __syncthreads();
-    const float ut_ref_used = ut_ref;
-    if (fast && nrows > 0) ut_ref = ut_s[0];         // reference for the next iteration (read after the barrier)
     SINK_TRACE(1);
     // ---- column pass: per-CTA partial LSE, published with the iteration tag in sign(s) --------------
     const unsigned epoch = (unsigned)(it + 1);
-    if (b < Ga && fast) {
-      const float mb = ut_ref_used;                  // e_s[r] = exp(ut_r - mb) was written by the row pass
-      const int Gf = C >> 2;
-      for (int g = tid; g < Gf; g += kThreads) {
-        float4 sm = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int r = 0; r < kRMax; ++r) {
-          if (r < nrows) {
-            const float4 ee = *reinterpret_cast<const float4*>(slab + (size_t)r * a.slab_ld + 4 * g);
-            const float er = e_s[r];
-            sm.x = fmaf(ee.x, er, sm.x); sm.y = fmaf(ee.y, er, sm.y); sm.z = fmaf(ee.z, er, sm.z); sm.w = fmaf(ee.w, er, sm.w);
-          }
-        }
-        float2* dst = &a.part[(size_t)b * a.ldp + 4 * g];
-        dst[0] = make_float2(mb, sm.x); dst[1] = make_float2(mb, sm.y);
-        dst[2] = make_float2(mb, sm.z); dst[3] = make_float2(mb, sm.w);
-      }
-      const int jl = 4 * Gf + warp;
-      if (jl < C) {
-        const float xx = (lane < nrows) ? slab[(size_t)lane * a.slab_ld + jl] * e_s[lane] : 0.f;
-        const float ss = warp_sum(xx);
-        if (lane == 0) a.part[(size_t)b * a.ldp + jl] = make_float2(mb, ss);
-      }
-    } else if (b < Ga) {
+    if (b < Ga) {
       if (reg_cols) {
         const int Gf = C >> 2;                               // groups of 4 columns, one 128-bit LDS per row
         for (int g = tid; g < Gf; g += kThreads) {
@@ -664,17 +609,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_sinkhorn(SinkArgs a) {
     SINK_TRACE(4);
     // ---- gather the new v ----------------------------------------------------------------------------------
     wait_flags(a.vflag, G, epoch, a.err);
-    // scaled-kernel path: w_j = exp(v_j - vref) with vref = last iteration's v_0 — any reference inside the
-    // (bounded) range of v works, and this one is known before the gather, so no reduction / extra barrier is needed
-    const float vref_next = vmax_next;
-    for (int j = tid; j < C; j += kThreads) {
-      const float vj = __ldcg(&a.vg[j]);
-      v_s[j] = vj;
-      if (fast) w_s[j] = ex2((vj - vref_next) * kLog2e);
-    }
-    vmax = vref_next;
+    for (int j = tid; j < C; j += kThreads) v_s[j] = __ldcg(&a.vg[j]);
     __syncthreads();
-    vmax_next = v_s[0];
     SINK_TRACE(5);
   }
 

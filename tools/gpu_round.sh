@@ -1,6 +1,6 @@
 #!/bin/bash
 # One GPU-box visit: parity tests (grouped so a faulting kernel does not poison the rest), smoke, bench, launch list.
-# usage: tools/gpu_round.sh [stage ...]   stages: agc sink fwd smoke bench ncu sanitize
+# usage: tools/gpu_round.sh [stage ...]   stages: tc agc sink fwd all smoke bench ncu ncufull sanitize
 mkdir -p gpurun_out
 STAGES="${@:-agc sink fwd smoke bench ncu}"
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > gpurun_out/gpu.txt 2>&1
@@ -18,6 +18,10 @@ for s in $STAGES; do
     bench) timeout 900 python bench.py --steps 3 --warmup 3 > gpurun_out/bench.log 2>&1; echo "bench rc=$?"; tail -1 gpurun_out/bench.log ;;
     ncu)   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 1200 --csv --log-file gpurun_out/launches.csv \
              python bench.py --steps 1 --warmup 3 --pairs-per-step 1 --streams 1 --pool 2 --no-cpu-baseline --no-e2e > gpurun_out/ncu_bench.log 2>&1; echo "ncu rc=$?" ;;
+    ncufull) B="python bench.py --steps 1 --warmup 3 --pairs-per-step 1 --streams 1 --pool 2 --no-cpu-baseline --no-e2e"
+           timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_attention_tc -s 40 -c 1 -f -o gpurun_out/ncu_attention $B > gpurun_out/ncufull_attn.log 2>&1; echo "ncufull attn rc=$?"
+           timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_gemm_tc -s 150 -c 3 -f -o gpurun_out/ncu_gemm $B > gpurun_out/ncufull_gemm.log 2>&1; echo "ncufull gemm rc=$?"
+           timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_sinkhorn -s 2 -c 1 -f -o gpurun_out/ncu_sinkhorn $B > gpurun_out/ncufull_sink.log 2>&1; echo "ncufull sink rc=$?" ;;
     sanitize) timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python __graft_entry__.py smoke > gpurun_out/sanitize.log 2>&1; echo "sanitize rc=$?" ;;
   esac
 done
