@@ -30,6 +30,8 @@ constexpr int kMaxGrid = 256;
 constexpr int kRMax = 16;            // rows per CTA handled by the unrolled (register) column pass
 constexpr int kRowChunks = 17;       // float4 chunks per lane of the register row pass (rows up to 2176 columns)
 constexpr float kLog2e = 1.4426950408889634f;
+constexpr int kWays = 4;             // copies of the column-sum buffer (CTA b adds into copy b % kWays): the red.adds of
+                                     // 148 CTAs on one 128-byte line serialize in L2, four copies cut that chain by four
 
 typedef unsigned long long u64;
 
@@ -43,7 +45,7 @@ struct SinkArgs {
   float* vg;                       // [ldp + 4]    v_j exchange buffer
   unsigned* pflag;                 // [grid]       iteration number of the partials CTA g has published
   unsigned* vflag;                 // [grid]       iteration number of the v_j CTA g has published
-  float* colsum;                   // [3][ldp]     scaled-kernel path: column sums accumulated with red.add, 3 rotating buffers
+  float* colsum;                   // [3][kWays][ldp] scaled-kernel path: column sums accumulated with red.add, 3 rotating buffers
   unsigned* counter;               // grid-wide arrival counter of the scaled-kernel path
   u64* mm;                         // [2*grid]     (zmin | 1<<32), (zmax | 1<<32) of every CTA's slab
   int ldp;
@@ -291,6 +293,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sinkhorn(SinkArgs a) {
     const int Gf = C >> 2;
     const size_t cs_ld = ((size_t)a.ldp + 3) & ~(size_t)3;
     float vref = 0.f;                               // reference the current w_s was scaled with (initially v = 0, w = 1)
+    float v0_prev = 0.f;                            // v_0 after the previous iteration (initially v = 0)
     unsigned target = 0;
     if (Gf <= kThreads) {
       // ----- register-resident variant (C <= 4 * kThreads + 3, i.e. up to 2048 keypoints in image 1): thread t owns the
@@ -307,7 +310,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_sinkhorn(SinkArgs a) {
       float4 wreg = make_float4(1.f, 1.f, 1.f, 1.f);
       for (int it = 0; it < a.iters; ++it) {
         SINK_TRACE(0);
-        float* cs = a.colsum + (size_t)(it % 3) * cs_ld;
+        float* cs = a.colsum + (size_t)(it % 3) * kWays * cs_ld;   // [kWays][cs_ld]
+        float* my = cs + (size_t)(b % kWays) * cs_ld;
         const float Rref = norm - vref;
         float part[kRMax];
 #pragma unroll
@@ -350,7 +354,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sinkhorn(SinkArgs a) {
               sm.x = fmaf(ereg[r].x, er, sm.x); sm.y = fmaf(ereg[r].y, er, sm.y);
               sm.z = fmaf(ereg[r].z, er, sm.z); sm.w = fmaf(ereg[r].w, er, sm.w);
             }
-            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cs + 4 * tid), "f"(sm.x), "f"(sm.y),
+            asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(my + 4 * tid), "f"(sm.x), "f"(sm.y),
                          "f"(sm.z), "f"(sm.w)
                          : "memory");
           }
@@ -358,7 +362,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sinkhorn(SinkArgs a) {
           if (jl < C) {
             const float xx = (lane < nrows) ? slab[(size_t)lane * a.slab_ld + jl] * e_s[lane] : 0.f;
             const float ss = warp_sum(xx);
-            if (lane == 0) atomicAdd(cs + jl, ss);
+            if (lane == 0) atomicAdd(my + jl, ss);
           }
         }
         SINK_TRACE(2);
@@ -366,12 +370,21 @@ __global__ void __launch_bounds__(kThreads, 1) k_sinkhorn(SinkArgs a) {
         grid_hop(a.counter, target, a.err);
         SINK_TRACE(3);
         {                                               // recycle the buffer that was read one iteration ago
-          float* old = a.colsum + (size_t)((it + 2) % 3) * cs_ld;
-          for (int j = c_begin + tid; j < c_end; j += kThreads) old[j] = 0.f;
+          float* old = a.colsum + (size_t)((it + 2) % 3) * kWays * cs_ld;
+          for (int w = 0; w < kWays; ++w)
+            for (int j = c_begin + tid; j < c_end; j += kThreads) old[(size_t)w * cs_ld + j] = 0.f;
         }
-        const float v0 = norm - (Rref + logf(__ldcg(cs)));      // v of column 0: the next reference (n1 >= 1)
+        // Reference of the new weights: v_0 of the PREVIOUS iteration — every thread already has it, and any reference
+        // inside the (bounded) range of v works.  (Deriving it from this iteration's colsum[0] made every warp of the
+        // grid load the same address right after the hop: 2400 serialized requests on one L2 sector per iteration.)
+        const float v0 = v0_prev;
         for (int g4 = tid; g4 < n4; g4 += kThreads) {
-          const float4 c4 = __ldcg(reinterpret_cast<const float4*>(cs) + g4);
+          float4 c4 = __ldcg(reinterpret_cast<const float4*>(cs) + g4);
+#pragma unroll
+          for (int w = 1; w < kWays; ++w) {
+            const float4 cw = __ldcg(reinterpret_cast<const float4*>(cs + (size_t)w * cs_ld) + g4);
+            c4.x += cw.x; c4.y += cw.y; c4.z += cw.z; c4.w += cw.w;
+          }
           const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
           float wn[4];
 #pragma unroll
@@ -391,12 +404,14 @@ __global__ void __launch_bounds__(kThreads, 1) k_sinkhorn(SinkArgs a) {
         }
         vref = v0;
         __syncthreads();
+        v0_prev = v_s[0];
         SINK_TRACE(5);
       }
     } else
     for (int it = 0; it < a.iters; ++it) {
       SINK_TRACE(0);
-      float* cs = a.colsum + (size_t)(it % 3) * cs_ld;
+      float* cs = a.colsum + (size_t)(it % 3) * kWays * cs_ld;   // [kWays][cs_ld]
+        float* my = cs + (size_t)(b % kWays) * cs_ld;
       const float Rref = norm - vref;
       for (int r = warp; r < nrows; r += kWarps) {
         const float4* e4 = reinterpret_cast<const float4*>(slab + (size_t)r * a.slab_ld);
@@ -431,7 +446,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sinkhorn(SinkArgs a) {
               sm.x = fmaf(ee.x, er, sm.x); sm.y = fmaf(ee.y, er, sm.y); sm.z = fmaf(ee.z, er, sm.z); sm.w = fmaf(ee.w, er, sm.w);
             }
           }
-          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cs + 4 * g), "f"(sm.x), "f"(sm.y), "f"(sm.z),
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(my + 4 * g), "f"(sm.x), "f"(sm.y), "f"(sm.z),
                        "f"(sm.w)
                        : "memory");
         }
@@ -439,7 +454,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sinkhorn(SinkArgs a) {
         if (jl < C) {
           const float xx = (lane < nrows) ? slab[(size_t)lane * a.slab_ld + jl] * e_s[lane] : 0.f;
           const float ss = warp_sum(xx);
-          if (lane == 0) atomicAdd(cs + jl, ss);
+          if (lane == 0) atomicAdd(my + jl, ss);
         }
       }
       SINK_TRACE(2);
@@ -447,12 +462,18 @@ __global__ void __launch_bounds__(kThreads, 1) k_sinkhorn(SinkArgs a) {
       grid_hop(a.counter, target, a.err);
       SINK_TRACE(3);
       {                                               // recycle the buffer that was read one iteration ago
-        float* old = a.colsum + (size_t)((it + 2) % 3) * cs_ld;
-        for (int j = c_begin + tid; j < c_end; j += kThreads) old[j] = 0.f;
+        float* old = a.colsum + (size_t)((it + 2) % 3) * kWays * cs_ld;
+        for (int w = 0; w < kWays; ++w)
+            for (int j = c_begin + tid; j < c_end; j += kThreads) old[(size_t)w * cs_ld + j] = 0.f;
       }
-      const float v0 = norm - (Rref + logf(__ldcg(cs)));        // v of column 0: the next reference (n1 >= 1)
+      const float v0 = v0_prev;                                   // last iteration's v_0 (see the register variant)
       for (int g4 = tid; g4 < n4; g4 += kThreads) {               // 128-bit loads: 4x fewer requests on these hot lines
-        const float4 c4 = __ldcg(reinterpret_cast<const float4*>(cs) + g4);
+        float4 c4 = __ldcg(reinterpret_cast<const float4*>(cs) + g4);
+#pragma unroll
+          for (int w = 1; w < kWays; ++w) {
+            const float4 cw = __ldcg(reinterpret_cast<const float4*>(cs + (size_t)w * cs_ld) + g4);
+            c4.x += cw.x; c4.y += cw.y; c4.z += cw.z; c4.w += cw.w;
+          }
         const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
@@ -468,6 +489,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sinkhorn(SinkArgs a) {
       }
       vref = v0;
       __syncthreads();
+      v0_prev = v_s[0];
       SINK_TRACE(5);
     }
   } else
@@ -738,7 +760,7 @@ size_t carve(SinkWs& w, void* base, size_t cap, int n0_max, int n1_max, int grid
   w.pflag = a.take<unsigned>(kMaxGrid);
   w.vflag = a.take<unsigned>(kMaxGrid);
   w.mm = a.take<u64>(2 * (size_t)kMaxGrid);
-  w.colsum = a.take<float>(3 * ((ldp + 3) & ~(size_t)3));
+  w.colsum = a.take<float>(3 * kWays * ((ldp + 3) & ~(size_t)3));
   w.zero_bytes = align_up(a.off, 256);
   w.part = a.take<float2>((size_t)grid * ldp);
   w.vg = a.take<float>(ldp + 4);
