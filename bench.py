@@ -182,7 +182,8 @@ def run_reference(args, rank, world):
         'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
         'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
         'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'GMatcher forward, 1 pair/step, %d kp/image, 100 Sinkhorn it, AGC 25/7/8' % args.kpts,
+        'config': {'workload': 'BASELINE configs[1]: GMatcher forward, %d kp/image, fp32, 100 Sinkhorn it, AGC r/p/m 25/7/8, '
+                               'random-init weights' % args.kpts, 'sample': 'one pair per step (bounded sample of the same workload)',
                    'pairs_per_step': 1},
         'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': 'port',
                          'sample': '%d pairs of the bench workload, oracle/gims_oracle.py, torch %d threads' %
@@ -416,7 +417,8 @@ def main():
                        'pairs_per_step_per_gpu': P, 'streams': args.streams, 'kept_keypoints': counts[:2],
                        'l2': 'input pool of %d distinct pairs (%.0f MB) > L2' % (args.pool, args.pool * in_bytes / 1e6),
                        'parallelism': 'pair-parallel x%d, no collective' % world},
-            'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches), 'roofline': roof,
+            'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches) * world, 'gpu_launches_per_rank': int(launches),
+            'roofline': roof,
             'pair_gflop': pair_flops(counts[0], counts[1]) / 1e9,
             'model_tflops': value / world * pair_flops(counts[0], counts[1]) / 1e12,
         }
