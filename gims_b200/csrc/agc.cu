@@ -281,33 +281,45 @@ __device__ __forceinline__ double sqdist64(float2 a, float2 b) {
   return __dadd_rn(__dmul_rn(dx, dx), __dmul_rn(dy, dy));
 }
 
+// One warp per row i; the keypoints of the candidate columns are staged through shared memory in chunks of 2048 — with
+// kpts[j] read from L2 inside the ballot loop every iteration paid a dependent global round trip (23 us per pass).
+constexpr int kEdgeChunk = 2048;
+
 template <bool FILL>
 __global__ void __launch_bounds__(256) k_base_edges(const float2* __restrict__ kpts, const float* __restrict__ S, int n,
                                                     double r2, const float* __restrict__ thr_p, int* __restrict__ deg,
                                                     const int* __restrict__ indptr, int* __restrict__ idx, int edge_cap,
                                                     unsigned* status) {
-  int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  int lane = threadIdx.x & 31;
-  if (i >= n) return;
-  float thr = *thr_p;
-  float2 pi = kpts[i];
-  const float* srow = S + (size_t)i * n;
+  __shared__ float2 kp_s[kEdgeChunk];
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  const bool live = i < n;
+  const float thr = *thr_p;
+  const float2 pi = live ? kpts[i] : make_float2(0.f, 0.f);
+  const float* srow = S + (size_t)(live ? i : 0) * n;
   int cnt = 0;
-  int base = FILL ? indptr[i] : 0;
-  for (int j0 = 0; j0 < n; j0 += 32) {
-    int j = j0 + lane;
-    bool p = false;
-    if (j < n && j != i) {
-      if (sqdist64(pi, kpts[j]) <= r2) p = srow[j] >= thr;
+  const int base = (FILL && live) ? indptr[i] : 0;
+  for (int c0 = 0; c0 < n; c0 += kEdgeChunk) {
+    const int cn = min(kEdgeChunk, n - c0);
+    __syncthreads();
+    for (int j = threadIdx.x; j < cn; j += blockDim.x) kp_s[j] = kpts[c0 + j];
+    __syncthreads();
+    if (!live) continue;
+    for (int j0 = 0; j0 < cn; j0 += 32) {
+      const int jl = j0 + lane, j = c0 + jl;
+      bool p = false;
+      if (jl < cn && j != i) {
+        if (sqdist64(pi, kp_s[jl]) <= r2) p = srow[j] >= thr;
+      }
+      const unsigned m = __ballot_sync(0xffffffffu, p);
+      if (FILL && p) {
+        const int pos = base + cnt + __popc(m & ((1u << lane) - 1u));
+        if (pos < edge_cap) idx[pos] = j; else atomicOr(status, GIMS_STATUS_EDGE_OVERFLOW);
+      }
+      cnt += __popc(m);
     }
-    unsigned m = __ballot_sync(0xffffffffu, p);
-    if (FILL && p) {
-      int pos = base + cnt + __popc(m & ((1u << lane) - 1u));
-      if (pos < edge_cap) idx[pos] = j; else atomicOr(status, GIMS_STATUS_EDGE_OVERFLOW);
-    }
-    cnt += __popc(m);
   }
-  if (!FILL && lane == 0) deg[i] = cnt;
+  if (!FILL && live && lane == 0) deg[i] = cnt;
 }
 
 // exclusive scan of `in[0..n)` into out[0..n], out[n] = total; n = n_dev ? *n_dev : n_max. One block.
