@@ -349,7 +349,7 @@ def main():
     # --- e2e: the reference-facing call with pinned host tensors ------------------------------------------
     e2e = None
     if not args.no_e2e:
-        n_e2e = max(8, min(P * args.steps, 48))
+        n_e2e = max(8, min(2 * P * args.steps, 128))
         host = []
         for i in range(n_e2e):
             d = pool_host[i % len(pool_host)]

@@ -227,15 +227,18 @@ class GMatcher(nn.Module):
             edge_cap = max(1024, 64 * max(n0, n1))
         f32 = dict(dtype=torch.float32, device=dev)
         i32 = dict(dtype=torch.int32, device=dev)
+        # counts and kept indices share one buffer so that the host needs ONE device->host copy per call
+        meta = torch.zeros(8 + n0 + n1, **i32)
         out = {
-            'n_kept_dev': torch.zeros(8, **i32),          # [0:2] N', [2:4] E, [4:6] #components, [6] status
+            'meta': meta,
+            'n_kept_dev': meta[:8],                       # [0:2] N', [2:4] E, [4:6] #components, [6] status
+            'kept_idx0': meta[8:8 + n0], 'kept_idx1': meta[8 + n0:],
             'thr_dev': torch.zeros(2, **f32),
             'mdesc': torch.empty(n0 + n1, d, **f32),
             'u': torch.empty(n0 + 1, **f32), 'v': torch.empty(n1 + 1, **f32),
         }
         ns = (n0, n1)
         for s in (0, 1):
-            out['kept_idx%d' % s] = torch.empty(ns[s], **i32)
             out['csr_indptr%d' % s] = torch.empty(ns[s] + 1, **i32)
             out['csr_indices%d' % s] = torch.empty(edge_cap, **i32)
             out['kpts%d' % s] = torch.empty(ns[s], 2, **f32)
@@ -315,7 +318,8 @@ class GMatcher(nn.Module):
                                   data['keypoints1'][b], data['descriptors1'][b], data['scores1'][b],
                                   data['image0'].shape, data['image1'].shape, radius, percentile, min_size,
                                   edge_cap=cap)
-                counts = r['n_kept_dev'].cpu()          # the one device->host sync of the call
+                meta = r['meta'].cpu()                  # the one device->host sync of the call: counts + kept indices
+                counts = meta[:8]
                 if int(counts[6]) & _lib.STATUS_EDGE_OVERFLOW:
                     n_max = max(r['kpts0'].shape[0], r['kpts1'].shape[0])
                     if r['edge_cap'] >= n_max * n_max:
@@ -324,7 +328,11 @@ class GMatcher(nn.Module):
                     continue
                 break
             r['counts'] = counts
+            r['meta_host'] = meta
             per_item.append(r)
+        def stack(lst):                         # batch 1 (the usual call): a view instead of a copy kernel
+            return lst[0].unsqueeze(0) if len(lst) == 1 else torch.stack(lst)
+
         res = {s: [] for s in ('k0', 'k1', 'd0', 'd1', 's0', 's1', 'm0', 'm1', 'ms0', 'ms1', 'md0', 'md1')}
         kept0, kept1, g0, g1 = [], [], [], []
         for r in per_item:
@@ -337,16 +345,17 @@ class GMatcher(nn.Module):
             res['m0'].append(r['matches0'][:a]); res['m1'].append(r['matches1'][:c])
             res['ms0'].append(r['mscores0'][:a]); res['ms1'].append(r['mscores1'][:c])
             res['md0'].append(r['mdesc'][:a]); res['md1'].append(r['mdesc'][n0_in:n0_in + c])
-            kept0.append(r['kept_idx0'][:a].tolist()); kept1.append(r['kept_idx1'][:c].tolist())
+            kept0.append(r['meta_host'][8:8 + a].tolist())
+            kept1.append(r['meta_host'][8 + n0_in:8 + n0_in + c].tolist())
             g0.append((r['csr_indptr0'][:a + 1], r['csr_indices0'][:e0]))
             g1.append((r['csr_indptr1'][:c + 1], r['csr_indices1'][:e1]))
         # same side effects on the caller's dict as gmatcher.py:244-252 (graphs are CSR pairs, not DGL)
-        data['keypoints0'] = torch.stack(res['k0'])
-        data['descriptors0'] = torch.stack(res['d0']).permute(0, 2, 1)
-        data['keypoints1'] = torch.stack(res['k1'])
-        data['descriptors1'] = torch.stack(res['d1']).permute(0, 2, 1)
-        data['scores0'] = torch.stack(res['s0'])
-        data['scores1'] = torch.stack(res['s1'])
+        data['keypoints0'] = stack(res['k0'])
+        data['descriptors0'] = stack(res['d0']).permute(0, 2, 1)
+        data['keypoints1'] = stack(res['k1'])
+        data['descriptors1'] = stack(res['d1']).permute(0, 2, 1)
+        data['scores0'] = stack(res['s0'])
+        data['scores1'] = stack(res['s1'])
         data['kept_kpts0_indices'] = kept0
         data['kept_kpts1_indices'] = kept1
         data['graph0'], data['graph1'] = g0, g1
@@ -359,16 +368,16 @@ class GMatcher(nn.Module):
                 'matching_scores0': kpts0.new_zeros(shape0),
                 'matching_scores1': kpts1.new_zeros(shape1),
             }
-        mdesc0, mdesc1 = torch.stack(res['md0']), torch.stack(res['md1'])
+        mdesc0, mdesc1 = stack(res['md0']), stack(res['md1'])
         return {
             'keypoints0': data['keypoints0'],
             'keypoints1': data['keypoints1'],
             'descriptors0': data['descriptors0'],
             'descriptors1': data['descriptors1'],
-            'matches0': torch.stack(res['m0']),
-            'matches1': torch.stack(res['m1']),
-            'matching_scores0': torch.stack(res['ms0']),
-            'matching_scores1': torch.stack(res['ms1']),
+            'matches0': stack(res['m0']),
+            'matches1': stack(res['m1']),
+            'matching_scores0': stack(res['ms0']),
+            'matching_scores1': stack(res['ms1']),
             'mdesc0': mdesc0.squeeze(),
             'mdesc1': mdesc1.squeeze(),
         }
