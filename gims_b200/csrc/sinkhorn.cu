@@ -814,7 +814,9 @@ extern "C" int gims_sinkhorn_match(const float* couplings, int n0_max, int n1_ma
   a.Z = couplings; a.ld = C; a.n0_max = n0_max; a.n1_max = n1_max; a.n_dev = n_dev; a.iters = iters;
   a.u = u; a.v = v; a.part = w.part; a.vg = w.vg; a.pflag = w.pflag; a.vflag = w.vflag; a.mm = w.mm; a.colsum = w.colsum; a.counter = w.err + 32; a.ldp = C; a.err = w.err;
   a.idx0 = indices0; a.idx1 = indices1; a.max0 = w.max0; a.max1 = w.max1;
-  GIMS_CUDA_OK(cudaFuncSetAttribute(k_sinkhorn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)dyn));
+  // the attribute is per function, not per launch: always the full budget, so that concurrent callers with different
+  // problem sizes cannot lower it under one another's launch (found by test_concurrent_callers_match_sequential)
+  GIMS_CUDA_OK(cudaFuncSetAttribute(k_sinkhorn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)budget));
   int per_sm = 0;
   GIMS_CUDA_OK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_sinkhorn, kThreads, dyn));
   if (per_sm < 1) { set_error("gims_sinkhorn_match: kernel does not fit an SM (dyn smem %zu)", dyn); return GIMS_ERR_ARG; }

@@ -304,6 +304,55 @@ def test_drop_in_call_signature():
     assert pred_np['matches0'].shape == (n0,)
 
 
+def test_concurrent_callers_match_sequential():
+    """Several host threads calling Matching(data) at once (one CUDA stream each, host inputs) — how bench.py measures
+    `e2e` — must give what the same calls give one after the other: per-stream workspaces, the locked
+    cooperative-launch chain and the thread-local error state are what this exercises."""
+    import threading
+    from gims_b200 import Matching
+    cfg = {'sinkhorn_iterations': 20, 'match_threshold': 0.005}
+    matching = Matching(cfg)
+    matching.gmodel.load_state_dict(make_state_dict(0, damped=True))
+    matching = matching.eval().to('cuda')
+    items = []
+    for k in range(8):
+        d = make_pair(300 + 37 * k, seed=500 + k)
+        d['device'] = 'cuda'
+        items.append(d)
+
+    def call(d):
+        with torch.no_grad():
+            pred = matching(dict(d))
+        return {k: pred[k][0].cpu() for k in ('matches0', 'matches1', 'matching_scores0', 'keypoints0')}
+
+    sequential = [call(d) for d in items]
+    results = [None] * len(items)
+    errors = []
+
+    def worker(tid):
+        try:
+            with torch.cuda.stream(torch.cuda.Stream()):
+                for rep in range(3):                                  # several calls per thread, interleaved with the others
+                    for k in range(tid, len(items), 4):
+                        results[k] = call(items[k])
+        except Exception as exc:                                      # noqa: BLE001
+            errors.append(exc)
+
+    threads = [threading.Thread(target=worker, args=(t,)) for t in range(4)]
+    for th in threads:
+        th.start()
+    for th in threads:
+        th.join()
+    torch.cuda.synchronize()
+    assert not errors, errors
+    for a, b in zip(sequential, results):
+        assert torch.equal(a['keypoints0'], b['keypoints0'])          # same graphs, same pruning
+        assert (a['matches0'] == b['matches0']).float().mean() >= 0.999
+        assert (a['matches1'] == b['matches1']).float().mean() >= 0.999
+        # fp32 atomics in the Sinkhorn column sums make the last bits order dependent
+        assert torch.allclose(a['matching_scores0'], b['matching_scores0'], rtol=1e-4, atol=1e-6)
+
+
 def test_round_trip_properties_full_size():
     """BASELINE config 2 (2048 kp, 100 Sinkhorn iterations): size-independent properties.
     * marginals: exp(Z) rows/cols sum to the prescribed masses (Sinkhorn fixed point, last update is v)
