@@ -11,6 +11,8 @@ snapshot) raise NotImplementedError.
 import ctypes as C
 from copy import deepcopy
 
+import threading
+
 import torch
 import torch.nn as nn
 
@@ -31,6 +33,9 @@ def _mlp_container(channels):
             layers.append(nn.ReLU())
     return nn.Sequential(*layers)
 
+
+# one lock for the lazily built native state (packed model, per-stream workspaces) of every GMatcher in the process
+_HANDLE_LOCK = threading.RLock()
 
 class _KeypointEncoderParams(nn.Module):
     def __init__(self, feature_dim, layers):
@@ -168,7 +173,11 @@ class GMatcher(nn.Module):
         return tuple((p.data_ptr(), p._version) for p in list(self.parameters()) + list(self.buffers()))
 
     def handle(self):
-        """(Re)pack the weights if needed and return the `gims_model*`."""
+        """(Re)pack the weights if needed and return the `gims_model*`.  Safe to call from several threads."""
+        with _HANDLE_LOCK:
+            return self._handle_locked()
+
+    def _handle_locked(self):
         dev = self.bin_score.device
         if dev.type != 'cuda':
             raise _lib.GimsError('GMatcher must live on a CUDA device (no CPU path): call .to("cuda")')
@@ -200,6 +209,10 @@ class GMatcher(nn.Module):
 
     def _workspace(self, n0, n1, edge_cap, dev, slot=0):
         key = (n0, n1, edge_cap, str(dev), slot)
+        with _HANDLE_LOCK:
+            return self._workspace_locked(key, n0, n1, edge_cap, dev)
+
+    def _workspace_locked(self, key, n0, n1, edge_cap, dev):
         ws = self._ws.get(key)
         if ws is None:
             if len(self._ws) > 64:
