@@ -226,8 +226,8 @@ def main():
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='ours', choices=['ours', 'reference'])
     ap.add_argument('--kpts', type=int, default=2048)
-    ap.add_argument('--pairs-per-step', type=int, default=16)
-    ap.add_argument('--streams', type=int, default=8)
+    ap.add_argument('--pairs-per-step', type=int, default=24)
+    ap.add_argument('--streams', type=int, default=12)
     ap.add_argument('--e2e-threads', type=int, default=8)
     ap.add_argument('--pool', type=int, default=40, help='distinct resident input pairs (> L2 in total)')
     ap.add_argument('--no-cpu-baseline', action='store_true')

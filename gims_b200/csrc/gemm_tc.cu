@@ -454,8 +454,10 @@ int launch_tc(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w
 int pick_bn(int n) {
   static const int forced = [] { const char* e = getenv("GIMS_GEMM_BN"); return e ? atoi(e) : 0; }();   // tuning knob
   if (forced == 64 || forced == 128 || forced == 192) return forced;
+  // Fewer, fatter CTAs: per output column a 128-wide tile costs half the tensor-pipe time of a 64-wide one, and with
+  // several pairs in flight the SMs a launch leaves idle are used by the other streams (N = 256 at BN = 128 is 64 CTAs).
   if (n >= 768) return 192;
-  if (n >= 512) return 128;
+  if (n >= 256) return 128;
   return 64;
 }
 
