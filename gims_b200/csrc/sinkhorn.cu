@@ -30,7 +30,7 @@ constexpr int kMaxGrid = 256;
 constexpr int kRMax = 16;            // rows per CTA handled by the unrolled (register) column pass
 constexpr int kRowChunks = 17;       // float4 chunks per lane of the register row pass (rows up to 2176 columns)
 constexpr float kLog2e = 1.4426950408889634f;
-constexpr int kWays = 4;             // copies of the column-sum buffer (CTA b adds into copy b % kWays): the red.adds of
+constexpr int kWays = 2;             // copies of the column-sum buffer (CTA b adds into copy b % kWays): the red.adds of
                                      // 148 CTAs on one 128-byte line serialize in L2, four copies cut that chain by four
 
 typedef unsigned long long u64;
