@@ -175,10 +175,10 @@ __device__ long long* g_sink_trace = nullptr;
 #define SINK_TRACE(slot)                                                        \
   do {                                                                          \
     if (trace && it < 16) trace[it * 8 + (slot)] = clock64();                   \
-    if (g_sink_trace && it == 5 && threadIdx.x == 0) {                          \
+    if (gtrace && it == 5) {                                                    \
       unsigned long long gt_;                                                   \
       asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt_));                   \
-      g_sink_trace[128 + blockIdx.x * 8 + (slot)] = (long long)gt_;             \
+      gtrace[128 + blockIdx.x * 8 + (slot)] = (long long)gt_;                   \
     }                                                                           \
   } while (0)
 
@@ -278,7 +278,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_sinkhorn(SinkArgs a) {
     }
   }
 
-  long long* trace = (b == 0 && tid == 0) ? g_sink_trace : nullptr;
+  // the trace pointer is read once: a load of the global per stamp would sit on every iteration's critical path
+  long long* const gtrace = (tid == 0) ? g_sink_trace : nullptr;
+  long long* trace = (b == 0) ? gtrace : nullptr;
   const bool reg_rows = resident && (C4 >> 2) <= kRowChunks * 32;   // a row's (z + v) fits the lanes' registers
   const bool reg_cols = resident && nrows <= kRMax;
   if (fast) {
@@ -378,13 +380,19 @@ __global__ void __launch_bounds__(kThreads, 1) k_sinkhorn(SinkArgs a) {
         // inside the (bounded) range of v works.  (Deriving it from this iteration's colsum[0] made every warp of the
         // grid load the same address right after the hop: 2400 serialized requests on one L2 sector per iteration.)
         const float v0 = v0_prev;
-        for (int g4 = tid; g4 < n4; g4 += kThreads) {
+        // n4 <= kThreads + 1 here: a thread has its own group and at most one more (the left-over columns); both loads
+        // are issued before either is used — one L2 round trip, not two, on the thread every other thread waits for
+        const int g4b = tid + kThreads;
+        auto load_cs = [&](int g4) {
           float4 c4 = __ldcg(reinterpret_cast<const float4*>(cs) + g4);
 #pragma unroll
           for (int w = 1; w < kWays; ++w) {
             const float4 cw = __ldcg(reinterpret_cast<const float4*>(cs + (size_t)w * cs_ld) + g4);
             c4.x += cw.x; c4.y += cw.y; c4.z += cw.z; c4.w += cw.w;
           }
+          return c4;
+        };
+        auto finish = [&](int g4, const float4 c4) {
           const float cc[4] = {c4.x, c4.y, c4.z, c4.w};
           float wn[4];
 #pragma unroll
@@ -401,7 +409,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_sinkhorn(SinkArgs a) {
             }
           }
           if (g4 == tid) wreg = make_float4(wn[0], wn[1], wn[2], wn[3]);
-        }
+        };
+        float4 ca = make_float4(1.f, 1.f, 1.f, 1.f), cb = ca;
+        if (tid < n4) ca = load_cs(tid);
+        if (g4b < n4) cb = load_cs(g4b);
+        if (tid < n4) finish(tid, ca);
+        if (g4b < n4) finish(g4b, cb);
+        SINK_TRACE(4);
         vref = v0;
         __syncthreads();
         v0_prev = v_s[0];
