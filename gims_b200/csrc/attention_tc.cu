@@ -3,12 +3,13 @@
 // Replaces `attention` + the einsums of MultiHeadedAttention (models/gmatcher.py:35-39, 108-113) for
 // head_dim 64:  out = softmax(q^T k / 8) v  per head, without materialising the (4, N, M) probabilities.
 //
-// Operands arrive as tf32 planes written by the QKV projection epilogue (gemm_tc.cu, qkv mode):
-//   Qp [2][rows][256]   hi / lo planes of q * log2(e)/8 (scores land in the log2 domain), channels h*64+d
-//   Kp [2][rows][256]   hi / lo planes of k
-//   Vt [2][256][ldv]    hi / lo planes of v, TRANSPOSED (channel-major) so that PV's B operand is K-major
-// One CTA = 128 queries of one head of one image; 192 threads:
-//   warps 0..3  one thread per query row: put the Q planes into TMEM once; per 64-key tile tcgen05.ld S ->
+// Operands are written by the QKV projection epilogue (gemm_tc.cu, MODE 2):
+//   Qp [rows][256]      fp32 q * log2(e)/8 (scores land in the log2 domain), channels h*64+d; split here
+//   Kp [2][rows][256]   tf32 hi / lo planes of k
+//   Vt [2][256][ldv]    tf32 hi / lo planes of v, TRANSPOSED (channel-major) so that PV's B operand is K-major
+// One CTA = 128 queries of one head of one image; 224 threads:
+//   warps 0..3  one thread per query row: load the Q row (requested before the CTA-wide sync), split it and put the
+//               hi / lo planes into TMEM once; per 64-key tile tcgen05.ld S ->
 //               online max / ex2 / sum in fp32 -> fold the previous PV tile into register accumulators
 //               (O = O * alpha + PV, fp32 RN) -> P split into tf32 hi / lo -> tcgen05.st into TMEM
 //   warp 4      TMA: K and Vt tiles of 64 keys through two 3-stage rings (K is released right after S = Q K^T)

@@ -6,13 +6,16 @@
 // is split x = hi + lo with hi = tf32(x); the accumulator receives A_hi*W_hi + A_lo*W_hi + A_hi*W_lo in fp32
 // (TMEM), i.e. ~2^-21 relative accuracy per product instead of TF32's 2^-11.
 //
-// Structure (one CTA = one 128 x BN output tile, 192 threads):
-//   warp 0      TMA producer: raw A tile, W_hi tile, W_lo tile per k-block (32 floats = one 128-B swizzle row)
-//   warp 1      allocates TMEM, then a single thread issues tcgen05.mma (3 per 8-wide k-step) and commits
-//   warps 2..5  split the raw A tile in shared memory into hi (in place) / lo, then run the epilogue:
-//               tcgen05.ld (32 lanes x 32 columns) -> bias / residual / ReLU -> 128-bit global stores
+// Structure (one CTA = one 128 x BN output tile, 224 threads; DESIGN.md section 5 has the measurements behind it):
+//   warp 4      TMA producer: raw fp32 A tile, W_hi tile, W_lo tile per k-block (32 floats = one 128-B swizzle row)
+//   warps 0..3  thread = tile row = TMEM lane: read the row of the raw A tile from shared memory, split it into tf32
+//               hi / lo and tcgen05.st both into a ring of TMEM slots; afterwards the epilogue: tcgen05.ld, sum of the
+//               accumulators, transpose through a staging tile, bias / residual / ReLU (or the Q / K / Vt planes of the
+//               QKV projection, or the scaled couplings), 128-bit stores that cover whole lines
+//   warps 5, 6  one MMA issuer thread each (even / odd k-blocks, own accumulator): three TS-form tcgen05.mma per
+//               8-wide k-step (A from TMEM, W from shared memory), tcgen05.commit to free the W stage and the A slot
 // W_hi / W_lo are split once at weight-pack time; activations are split on the fly, so no tensor in HBM
-// changes layout.  Pipeline: full[s] (TMA bytes) -> conv[s] (A split done) -> MMA -> empty[s] (tcgen05.commit).
+// changes layout.  Pipeline: full[s] (TMA bytes) -> conv[slot] (A in TMEM) -> MMA -> empty[s] / tfree[slot].
 #include "common.cuh"
 #include "tc_common.cuh"
 
