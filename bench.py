@@ -155,6 +155,29 @@ class ClockSampler:
         return {'sm_mhz': med, 'sm_max_mhz': smax, 'reasons': sorted(reasons), 'samples': len(sm), 'source': 'nvidia-smi'}
 
 
+def measure_tf32_peak(dev):
+    """Dense TF32 tensor throughput of this GPU (cuBLAS, 8192^3), measured like MEASURED_PEAKS.json's bf16 number
+    (SURVEY.md 8d asks for it: the file has no TF32 entry).  Used only as a roofline denominator."""
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    try:
+        a = torch.randn(8192, 8192, device=dev)
+        b = torch.randn(8192, 8192, device=dev)
+        for _ in range(3):
+            c = a @ b
+        torch.cuda.synchronize(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(10):
+            c = a @ b
+        e1.record()
+        torch.cuda.synchronize(dev)
+        del c
+        return 10 * 2.0 * 8192 ** 3 / (e0.elapsed_time(e1) / 1e3) / 1e12
+    finally:
+        torch.backends.cuda.matmul.allow_tf32 = prev
+
+
 def run_reference(args, rank, world):
     """--impl reference: the reference algorithm (oracle port, torch-CPU + numpy) on the host cores."""
     if rank != 0:
@@ -322,6 +345,10 @@ def main():
         if cnt.value:
             avg_s = tot.value / cnt.value / 1e3
             if args.prof_kernel == 'attention':
+                try:
+                    tf32_peak = measure_tf32_peak(dev)
+                except Exception:      # noqa: BLE001 - the extra denominator is optional
+                    tf32_peak = None
                 # QK^T + PV over 4 heads x 64: 4*D*nq*nk per image; averaged over self / cross layers
                 flops = 2.0 * 256 * (n0k + n1k) ** 2
                 ach = flops / avg_s / 1e12
@@ -333,6 +360,8 @@ def main():
                         'traffic_source': 'dram__bytes_read+write per launch, profiles/r01_ncu_full_metrics.txt '
                                           '(algorithmic: Q 4.2 MB + K, Vt tf32 planes 16.7 MB)',
                         'ceiling_frac': 1.0 / 6.0, 'frac_of_ceiling': ach / peak * 6.0,
+                        'tf32_dense_tflops_measured': tf32_peak,
+                        'frac_of_measured_tf32_over_3': (ach / (tf32_peak / 3.0)) if tf32_peak else None,
                         'ceiling_note': '3xTF32 error compensation (fp32 parity): 3 MMAs per product at the tf32 rate',
                         'peak_source': peaks['_source'] + ' bf16 sustained', 'launches_timed': cnt.value,
                         'avg_launch_ms': avg_s * 1e3, 'flops_per_launch': flops}
