@@ -22,7 +22,7 @@
 // top, the QK phase ran at 67-85 clk per MMA (profiles/r01_attention_pipeline_trace.txt).  Reading A from TMEM
 // leaves shared memory to the K / Vt tiles alone.
 //
-// TMEM columns: S[2] 64 each | P_hi 64 | P_lo 64 | PV 64 | Q_hi 64 | Q_lo 64.  Each S / PV accumulator receives the
+// TMEM columns: S[2] 64 each | P_hi 64 | P_lo 64 | PV[0] 64 | Q_hi 64 | Q_lo 64 | PV[1] 64 (all 512).  Each S / PV accumulator receives the
 // 16 small correction products of its tile FIRST and the 8 hi*hi products last: the tensor core rounds the accumulator
 // toward zero at every step, and this order keeps those roundings at the magnitude of the small terms for as long as
 // possible (same error as a separate correction accumulator, without its TMEM columns and the extra add).
@@ -40,13 +40,21 @@ using namespace tc;
 constexpr int TQ = 128;        // queries per CTA (UMMA M)
 constexpr int TKV = 64;        // keys per tile (UMMA N of S, K of PV)
 constexpr int HD = 64;         // head dim
-constexpr int kStagesKV = 3;
+constexpr int kStagesKV = 3;                    // Vt ring (64 keys per stage); K ring at KT = 64
 constexpr int kBoxBytesKV = TKV * 32 * 4;       // 8 KB: 64 rows x 32 floats
-constexpr int kKStageBytes = 4 * kBoxBytesKV;   // hi(2 boxes) lo(2 boxes); same size for K and Vt
-constexpr int kAttnSmem = 2 * kStagesKV * kKStageBytes + 1024 + 256;
+constexpr int kKStageBytes = 4 * kBoxBytesKV;   // hi(2 boxes) lo(2 boxes); Vt stage, and K stage at KT = 64
 constexpr int kAttnThreads = 224;
+// KT = keys per S = Q K^T tile (UMMA N).  At 128 the QK product costs 64 clk per MMA for 128 keys instead of 2 x 45 for
+// 2 x 64 (tools/micro/mma_rate.cu), the PV product and the softmax still work on 64-key halves of that tile.  The
+// default is 64 (see launch_attention_tc).
+template <int KT> struct AttnCfg {
+  static constexpr int kKBox = KT * 32 * 4;                 // K box: KT keys x 32 channels
+  static constexpr int kKStage = 4 * kKBox;
+  static constexpr int kStagesK = KT == 64 ? 3 : 2;
+  static constexpr int kSmem = kStagesK * kKStage + kStagesKV * kKStageBytes + 1024 + 256;
+};
 
-constexpr int cS0 = 0, cPh = 128, cPl = 192, cO = 256, cQh = 320, cQl = 384;
+constexpr int cS0 = 0, cPh = 128, cPl = 192, cO0 = 256, cQh = 320, cQl = 384, cO1 = 448;
 
 // Optional pipeline trace (bring-up / profiling): CTA (0,0,0) stores clock64() stamps per tile.
 //   [j*8+0] MMA: QK(j+1) issue start   [j*8+1] MMA: PV(j) operands ready   [j*8+2] MMA: PV(j) issued
@@ -69,10 +77,11 @@ __device__ __forceinline__ float ex2_approx(float x) {
   return y;
 }
 
-// Pipeline: iteration jq of the MMA thread issues QK(jq) and then PV(jq-1), so the tensor core computes the next score
-// tile while the softmax warps work on the current one.  S is double-buffered; P and PV are single-buffered — their
-// reuse is ordered by p_full / o_full: the softmax warps fold PV(j-1) out of TMEM (which also proves that P(j-1) has
-// been consumed) before they store P(j).
+// Pipeline: the QK issuer runs ahead into the free S buffer while the softmax warps work on the current tile and the PV
+// issuer multiplies the previous one.  S and PV are double-buffered, P is single-buffered: the softmax warps store
+// P(j) as soon as o_full says that PV(j-1) has consumed P(j-1), and fold PV(j-1) out of its buffer afterwards, while
+// PV(j) already accumulates into the other one.
+template <int KT>
 __global__ void __launch_bounds__(kAttnThreads, 1)
 k_attention_tc(const __grid_constant__ CUtensorMap mapK, const __grid_constant__ CUtensorMap mapVt, AttnTcArgs a) {
   extern __shared__ uint8_t smem_raw[];
@@ -95,7 +104,8 @@ k_attention_tc(const __grid_constant__ CUtensorMap mapK, const __grid_constant__
 
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* k_smem = smem;
-  uint8_t* v_smem = k_smem + kStagesKV * kKStageBytes;
+  using Cfg = AttnCfg<KT>;
+  uint8_t* v_smem = k_smem + Cfg::kStagesK * Cfg::kKStage;
   uint64_t* bars = reinterpret_cast<uint64_t*>(v_smem + kStagesKV * kKStageBytes);
   uint64_t* k_full = bars;                       // [3] TMA -> MMA
   uint64_t* k_empty = bars + 3;                  // [3] QK MMAs retired (tcgen05.commit)
@@ -128,24 +138,27 @@ k_attention_tc(const __grid_constant__ CUtensorMap mapK, const __grid_constant__
   // This thread's Q row is requested before the CTA-wide sync: the global round trip overlaps the TMEM allocation and
   // the barrier hand-shake instead of following them.  (Not the first TMA stages: the issuing thread would stall on
   // the tensor-map fetch and hold up the sync.)
-  int tma_j = 0, tma_s = 0; uint32_t tma_ph = 0;
-  auto tma_produce = [&](int j_end) {
-    for (; tma_j < j_end; ++tma_j) {
-      const int key0 = krow0 + tma_j * TKV;                   // row in the K planes
-      const int vcol0 = (src ? a.vbase1 : 0) + tma_j * TKV;   // key column in the Vt planes (multiple of 64)
-      mbar_wait(&k_empty[tma_s], tma_ph ^ 1);
-      mbar_arrive_expect_tx(&k_full[tma_s], kKStageBytes);
-      for (int pl = 0; pl < 2; ++pl)
-        for (int hf = 0; hf < 2; ++hf)      // K box: 64 keys x 32 channels
-          tma_load_2d(k_smem + tma_s * kKStageBytes + (pl * 2 + hf) * kBoxBytesKV, &mapK, &k_full[tma_s],
-                      head * HD + hf * 32, pl * a.rows_total + key0);
-      mbar_wait(&v_empty[tma_s], tma_ph ^ 1);
-      mbar_arrive_expect_tx(&v_full[tma_s], kKStageBytes);
+  auto tma_produce = [&]() {
+    int sk = 0, sv = 0; uint32_t phk = 0, phv = 0;
+    for (int j = 0; j < ntiles; ++j) {
+      if (j % (KT / TKV) == 0) {                              // K tile of KT keys
+        const int key0 = krow0 + j * TKV;                     // row in the K planes
+        mbar_wait(&k_empty[sk], phk ^ 1);
+        mbar_arrive_expect_tx(&k_full[sk], Cfg::kKStage);
+        for (int pl = 0; pl < 2; ++pl)
+          for (int hf = 0; hf < 2; ++hf)    // K box: KT keys x 32 channels
+            tma_load_2d(k_smem + sk * Cfg::kKStage + (pl * 2 + hf) * Cfg::kKBox, &mapK, &k_full[sk], head * HD + hf * 32,
+                        pl * a.rows_total + key0);
+        if (++sk == Cfg::kStagesK) { sk = 0; phk ^= 1; }
+      }
+      const int vcol0 = (src ? a.vbase1 : 0) + j * TKV;       // key column in the Vt planes (multiple of 64)
+      mbar_wait(&v_empty[sv], phv ^ 1);
+      mbar_arrive_expect_tx(&v_full[sv], kKStageBytes);
       for (int pl = 0; pl < 2; ++pl)
         for (int hf = 0; hf < 2; ++hf)      // Vt box: 64 channels x 32 keys
-          tma_load_2d(v_smem + tma_s * kKStageBytes + (pl * 2 + hf) * kBoxBytesKV, &mapVt, &v_full[tma_s],
-                      vcol0 + hf * 32, pl * kD + head * HD);
-      if (++tma_s == kStagesKV) { tma_s = 0; tma_ph ^= 1; }
+          tma_load_2d(v_smem + sv * kKStageBytes + (pl * 2 + hf) * kBoxBytesKV, &mapVt, &v_full[sv], vcol0 + hf * 32,
+                      pl * kD + head * HD);
+      if (++sv == kStagesKV) { sv = 0; phv ^= 1; }
     }
   };
   float4 qreg[HD / 4];                                         // warps 0..3: fp32 Q row (scaled by log2(e)/8)
@@ -163,53 +176,61 @@ k_attention_tc(const __grid_constant__ CUtensorMap mapK, const __grid_constant__
 
   if (threadIdx.x == kWarpTma * 32) {
     // ===== TMA producer =====
-    tma_produce(ntiles);
+    tma_produce();
   } else if (threadIdx.x == kWarpMma * 32) {
     // ===== QK issuer: ONE thread, all operand arithmetic in the uniform datapath (descriptor = base + constant) =====
-    constexpr uint32_t idesc = umma_idesc_tf32(TQ, TKV);      // M=128, N=64
+    constexpr uint32_t idesc = umma_idesc_tf32(TQ, KT);       // M=128, N=KT
     const uint64_t dk0 = umma_desc_sw128(smem_u32(k_smem));
     const uint32_t q_hi = tmem + cQh, q_lo = tmem + cQl;
     long long* trace = (blockIdx.x | blockIdx.y | blockIdx.z) == 0 ? g_attn_trace : nullptr;
     mbar_wait(q_ready, 0);
     int sk = 0; uint32_t phk = 0;
-    for (int jq = 0; jq < ntiles; ++jq) {
+    for (int jq = 0; jq < ntiles; jq += KT / TKV) {
       if (trace) trace[jq * 8 + 0] = clock64();
       mbar_wait(&k_full[sk], phk);
-      if (jq >= 2) mbar_wait(&s_free[jq & 1], (uint32_t)((jq >> 1) - 1) & 1u);   // S(jq-2) has been read out of this buffer
+      // the 64-key halves of S this tile overwrites have been read out: S(jq-2) at KT = 64, both halves of the
+      // previous 128-key tile at KT = 128 (half h of every tile lives in columns 64 h and signals s_free[h])
+      if (KT == 64) {
+        if (jq >= 2) mbar_wait(&s_free[jq & 1], (uint32_t)((jq >> 1) - 1) & 1u);
+      } else if (jq >= 2) {
+        mbar_wait(&s_free[0], (uint32_t)((jq >> 1) - 1) & 1u);
+        mbar_wait(&s_free[1], (uint32_t)((jq >> 1) - 1) & 1u);
+      }
       tcgen05_fence_after();
       if (trace) trace[jq * 8 + 7] = clock64();
-      const uint64_t kh = dk0 + (uint64_t)(sk * (kKStageBytes >> 4)), kl = kh + ((2 * kBoxBytesKV) >> 4);
-      const uint32_t sacc = tmem + cS0 + (jq & 1) * 64;
+      const uint64_t kh = dk0 + (uint64_t)(sk * (Cfg::kKStage >> 4)), kl = kh + ((2 * Cfg::kKBox) >> 4);
+      const uint32_t sacc = tmem + cS0 + (KT == 64 ? (jq & 1) * 64 : 0);
       // K-dim = 64 channels = 2 boxes x 4 k-steps (8 TMEM columns of Q each); corrections first, hi*hi last
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks) {
-        const uint64_t koff = ((ks >> 2) * kBoxBytesKV + (ks & 3) * 32) >> 4;
+        const uint64_t koff = ((ks >> 2) * Cfg::kKBox + (ks & 3) * 32) >> 4;
         umma_tf32_ts(sacc, q_lo + ks * 8, kh + koff, idesc, ks ? 1u : 0u);
         umma_tf32_ts(sacc, q_hi + ks * 8, kl + koff, idesc, 1u);
       }
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks) {
-        const uint64_t koff = ((ks >> 2) * kBoxBytesKV + (ks & 3) * 32) >> 4;
+        const uint64_t koff = ((ks >> 2) * Cfg::kKBox + (ks & 3) * 32) >> 4;
         umma_tf32_ts(sacc, q_hi + ks * 8, kh + koff, idesc, 1u);
       }
       if (trace) trace[jq * 8 + 6] = clock64();
       umma_commit(&k_empty[sk]);
-      umma_commit(&s_full[jq & 1]);
-      if (++sk == kStagesKV) { sk = 0; phk ^= 1; }
+      umma_commit(&s_full[KT == 64 ? (jq & 1) : 0]);
+      if (++sk == Cfg::kStagesK) { sk = 0; phk ^= 1; }
     }
   } else if (threadIdx.x == kWarpPv * 32) {
     // ===== PV issuer =====
     constexpr uint32_t idesc = umma_idesc_tf32(TQ, TKV);      // M=128, N=64
     const uint64_t dv0 = umma_desc_sw128(smem_u32(v_smem));
-    const uint32_t p_hi = tmem + cPh, p_lo = tmem + cPl, oacc = tmem + cO;
+    const uint32_t p_hi = tmem + cPh, p_lo = tmem + cPl;
     long long* trace = (blockIdx.x | blockIdx.y | blockIdx.z) == 0 ? g_attn_trace : nullptr;
     int sv = 0; uint32_t phv = 0;
     for (int j = 0; j < ntiles; ++j) {
       mbar_wait(&v_full[sv], phv);
-      mbar_wait(p_full, j & 1);                                // P(j) is in TMEM, PV(j-1) has been folded away
+      mbar_wait(p_full, j & 1);                                // P(j) is in TMEM (and PV(j-2) was folded before that)
       tcgen05_fence_after();
       if (trace) trace[j * 8 + 1] = clock64();
       const uint64_t vh = dv0 + (uint64_t)(sv * (kKStageBytes >> 4)), vl = vh + ((2 * kBoxBytesKV) >> 4);
+      const uint32_t oacc = tmem + ((j & 1) ? cO1 : cO0);      // PV is double-buffered: the fold of PV(j-1) overlaps
       // K-dim = 64 keys = 2 Vt boxes x 4 k-steps; A (P planes) from TMEM, 8 columns per k-step
 #pragma unroll
       for (int ks = 0; ks < 8; ++ks) {
@@ -261,7 +282,9 @@ k_attention_tc(const __grid_constant__ CUtensorMap mapK, const __grid_constant__
       float s[TKV];                                      // scores in the log2 domain (Q was scaled by log2(e)/8)
       float alpha = 0.f;
       if (j < ntiles) {
-        mbar_wait(&s_full[j & 1], (uint32_t)(j >> 1) & 1u);
+        // S(j) sits in columns 64 (j & 1): one of two 64-key buffers (KT = 64) or one half of the 128-key tile of
+        // this key pair (KT = 128, one s_full barrier per pair)
+        if (KT == 64 || (j & 1) == 0) mbar_wait(&s_full[KT == 64 ? (j & 1) : 0], (uint32_t)(j >> 1) & 1u);
         tcgen05_fence_after();
         if (trace) trace[j * 8 + 4] = clock64();
 #pragma unroll
@@ -274,7 +297,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap mapK, const __grid_constant__
         }
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&s_free[j & 1]);      // the tensor core may overwrite this S buffer (tile j+2)
+        if (lane == 0) mbar_arrive(&s_free[j & 1]);      // the tensor core may overwrite these 64 columns of S
         const int valid = nk - j * TKV;                  // keys of this tile that exist
         if (valid < TKV) {
 #pragma unroll
@@ -297,19 +320,13 @@ k_attention_tc(const __grid_constant__ CUtensorMap mapK, const __grid_constant__
         l_run = l_run * alpha + (rs0 + rs1);
         m_run = m_new;
       }
-      if (j > 0) {                                       // fold PV(j-1): O = O * alpha(j-1) + PV; frees P and PV
+      if (j > 0) {                                       // PV(j-1) is complete: P may be overwritten, O[(j-1)&1] is final
         mbar_wait(o_full, (uint32_t)(j - 1) & 1u);
         tcgen05_fence_after();
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          uint32_t v[32];
-          tmem_ld_32x32(lane_base + cO + h * 32, v);
-          tmem_ld_wait();
-#pragma unroll
-          for (int i = 0; i < 32; ++i) o[h * 32 + i] = fmaf(o[h * 32 + i], alpha_prev, __uint_as_float(v[i]));
-        }
       }
-      alpha_prev = alpha;
+      // P(j) goes out BEFORE PV(j-1) is folded: the PV -> P -> PV chain through these warps is what paces the loop
+      // once the tensor pipe has slack, and the fold (two TMEM loads + 64 FMAs) need not be on it — PV is
+      // double-buffered, PV(j) accumulates into the other buffer meanwhile.
       if (j < ntiles) {
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
@@ -330,6 +347,19 @@ k_attention_tc(const __grid_constant__ CUtensorMap mapK, const __grid_constant__
         if (lane == 0) mbar_arrive(p_full);
         if (trace) trace[j * 8 + 3] = clock64();
       }
+      if (j > 0) {                                       // fold PV(j-1): O = O * alpha(j-1) + PV
+        const uint32_t ocol = ((j - 1) & 1) ? cO1 : cO0;
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+          uint32_t v[32];
+          tmem_ld_32x32(lane_base + ocol + h * 32, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int i = 0; i < 32; ++i) o[h * 32 + i] = fmaf(o[h * 32 + i], alpha_prev, __uint_as_float(v[i]));
+        }
+        tcgen05_fence_before();
+      }
+      alpha_prev = alpha;
     }
     if (row < nq) {
       const float inv = 1.f / l_run;
@@ -363,7 +393,10 @@ int launch_attention_tc(const QkvPlanes& pl, float* out, int n0_max, int n1_max,
                         cudaStream_t st) {
   int rows = n0_max + n1_max;
   CUtensorMap mK, mV;
-  GIMS_TRY(tc::make_tmap_f32_k32(&mK, pl.kp, 2 * (uint64_t)rows, kD, kD, TKV));
+  // KT = 128 (GIMS_ATTN_KT=128) is correct but measured slower on B200 (56 vs 51 us per launch): the softmax warps need
+  // ~1700 clk per 64-key tile, which is under the tensor pipe's 2170 clk at KT = 64 but not under its 1850 clk at 128.
+  static const int kt = [] { const char* e = getenv("GIMS_ATTN_KT"); return (e && atoi(e) == 128) ? 128 : 64; }();
+  GIMS_TRY(tc::make_tmap_f32_k32(&mK, pl.kp, 2 * (uint64_t)rows, kD, kD, kt));
   GIMS_TRY(tc::make_tmap_f32_k32(&mV, pl.vt, 2 * (uint64_t)kD, pl.ldv, pl.ldv, HD));
   AttnTcArgs a;
   a.qp = pl.qp;
@@ -373,10 +406,16 @@ int launch_attention_tc(const QkvPlanes& pl, float* out, int n0_max, int n1_max,
   a.cross = cross;
   a.rows_total = rows;
   a.vbase1 = pl.vbase1;
-  GIMS_CUDA_OK(cudaFuncSetAttribute(k_attention_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, kAttnSmem));
   int nmax = n0_max > n1_max ? n0_max : n1_max;
+  dim3 grid(cdiv(nmax, TQ), kHeads, 2);
   ProfScope prof(GIMS_PROF_ATTENTION, st);
-  k_attention_tc<<<dim3(cdiv(nmax, TQ), kHeads, 2), kAttnThreads, kAttnSmem, st>>>(mK, mV, a);
+  if (kt == 64) {
+    GIMS_CUDA_OK(cudaFuncSetAttribute(k_attention_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<64>::kSmem));
+    k_attention_tc<64><<<grid, kAttnThreads, AttnCfg<64>::kSmem, st>>>(mK, mV, a);
+  } else {
+    GIMS_CUDA_OK(cudaFuncSetAttribute(k_attention_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<128>::kSmem));
+    k_attention_tc<128><<<grid, kAttnThreads, AttnCfg<128>::kSmem, st>>>(mK, mV, a);
+  }
   GIMS_LAUNCH_OK();
   return GIMS_OK;
 }
