@@ -183,12 +183,15 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
       if (++tma_s == Cfg::kStages) { tma_s = 0; tma_ph ^= 1; }
     }
   };
-  // (Issuing the first stages before the CTA-wide sync was tried: the issuing thread stalls on the tensor-map fetch and
-  // delays the sync for everybody — the prologue went from 1200 to 4100 clk.)
   if (warp == kWarpMma) tmem_alloc<Cfg::kTmemCols>(tmem_slot);
   if (threadIdx.x < BN) bias_s[threadIdx.x] = (g.bias && c0 + (int)threadIdx.x < g.N) ? g.bias[c0 + threadIdx.x] : 0.f;
   tcgen05_fence_before();
-  __syncthreads();
+  // The TMA warp only ARRIVES at the start-up barrier (it has initialised the mbarriers, and needs neither the TMEM
+  // address nor the bias) and goes straight on to request the first stages; everybody else waits for it and for the
+  // TMEM allocation.  (With a plain __syncthreads the first TMA was issued ~1200 clk into the kernel; issuing it from
+  // inside the sync-ing warp before the barrier delayed the barrier for everybody instead.)
+  if (warp == kWarpTma) asm volatile("bar.arrive 1, %0;" ::"n"(kThreadsTc) : "memory");
+  else                  asm volatile("bar.sync 1, %0;" ::"n"(kThreadsTc) : "memory");
   tcgen05_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform for the compiler
   if (trace && threadIdx.x == 0) trace[1] = clock64();
