@@ -47,6 +47,13 @@ def load_peaks():
     return d
 
 
+def projection_flops(n0, n1, layers=18, d=256):
+    """Algorithmic FLOPs of the per-node linear maps of one pair (q/k/v/merge, MLP, kenc, SAGE, final_proj)."""
+    per_node = layers * (4 * 2 * d * d + 2 * (2 * d) * (2 * d) + 2 * (2 * d) * d) + 2 * 108608 + \
+        2 * (2 * 256 * 128 + 2 * 128 * 128 + 2 * 128 * 256) + 2 * d * d
+    return per_node * (n0 + n1)
+
+
 def pair_flops(n0, n1, layers=18, d=256):
     """Algorithmic FLOPs of one pair, N = surviving keypoints per image."""
     per_node = layers * (4 * 2 * d * d + 2 * (2 * d) * (2 * d) + 2 * (2 * d) * d) + 2 * 108608 + \
@@ -375,6 +382,37 @@ def main():
                         'peak_source': peaks['_source'],
                         'launches_timed': cnt.value, 'avg_launch_ms': avg_s * 1e3, 'bytes_per_launch': byts}
 
+    # --- the other kernel classes, timed the same way (one stream, CUDA events inside the library) -------------
+    other = {}
+    if rank == 0 and roof is not None:
+        npair = min(P, 4)
+        d = 256
+        for cls in ('gemm', 'sinkhorn', 'cosine'):
+            L.gims_profile_begin(_lib.PROF[cls], 4096)
+            torch.cuda.synchronize(dev)
+            PairBatchRunner(gm, n_streams=1).run([pool[i % len(pool)] for i in range(npair)])
+            torch.cuda.synchronize(dev)
+            tot, cnt = C.c_double(0), C.c_int(0)
+            L.gims_profile_end(C.byref(tot), C.byref(cnt))
+            if not cnt.value:
+                continue
+            ent = {'launches_per_pair': cnt.value / npair, 'ms_per_pair': tot.value / npair}
+            if cls == 'gemm':
+                # every per-node linear map of a pair (the reference's count: the merge conv that we fold away included)
+                fl = float(projection_flops(n0k, n1k))
+                ent.update({'bound': 'tensor', 'achieved': fl / (tot.value / npair / 1e3) / 1e12, 'unit': 'TFLOP/s',
+                            'flops_per_pair': fl})
+                ent['frac'] = ent['achieved'] / peaks['bf16_tflops_sustained']
+                ent['frac_of_ceiling'] = ent['frac'] * 6.0
+            elif cls == 'sinkhorn':
+                ent.update({'bound': 'latency (100 grid-wide exchanges through L2)', 'us_per_iteration':
+                            tot.value / cnt.value * 1e3 / 100.0, 'hbm_bytes_per_launch': 4.0 * (n0k + 1) * (n1k + 1)})
+            elif cls == 'cosine':
+                fl = 2.0 * d * (n0k * (n0k + 1) / 2 + n1k * (n1k + 1) / 2)
+                ent.update({'bound': 'fp64 pipe', 'achieved': fl / (tot.value / npair / 1e3) / 1e12, 'unit': 'TFLOP/s (fp64)',
+                            'flops_per_pair': fl})
+            other[cls] = ent
+
     # --- e2e: the reference-facing call with pinned host tensors ------------------------------------------
     e2e = None
     if not args.no_e2e:
@@ -447,7 +485,7 @@ def main():
                        'l2': 'input pool of %d distinct pairs (%.0f MB) > L2' % (args.pool, args.pool * in_bytes / 1e6),
                        'parallelism': 'pair-parallel x%d, no collective' % world},
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches) * world, 'gpu_launches_per_rank': int(launches),
-            'roofline': roof,
+            'roofline': roof, 'roofline_other': other,
             'pair_gflop': pair_flops(counts[0], counts[1]) / 1e9,
             'model_tflops': value / world * pair_flops(counts[0], counts[1]) / 1e12,
         }
