@@ -148,3 +148,38 @@ def test_packing_equals_oracle_sage_kenc():
         if i < 4:
             hcur = F.relu(hcur)
     assert torch.allclose(hcur, want_k, rtol=1e-4, atol=1e-5)
+
+
+def test_weight_change_detection():
+    """The packed model is rebuilt when weights change: in-place edits move the version sum, load_state_dict /
+    .to() drop the cached tensor list (gims_b200/gmatcher.py::_param_version)."""
+    from gims_b200 import GMatcher
+    from gims_b200.synth import make_state_dict
+    gm = GMatcher({})
+    gm.load_state_dict(make_state_dict(3))
+    v0 = gm._param_version()
+    assert gm._param_version() == v0                       # stable without changes
+    with torch.no_grad():
+        gm.final_proj.weight.mul_(2.0)                     # in-place edit
+    v1 = gm._param_version()
+    assert v1 != v0
+    gm.load_state_dict(make_state_dict(4))                 # copies in place and invalidates
+    assert gm.__dict__['_ptensors'] is None
+    v2 = gm._param_version()
+    assert v2 != v1
+    gm = gm.double().float()                               # _apply replaces the tensors: the cached list is dropped
+    assert gm.__dict__['_ptensors'] is None
+    ts = list(gm.parameters()) + list(gm.buffers())
+    assert gm._param_version()[1] == len(ts)
+
+
+def test_bench_flop_model():
+    """bench.py's algorithmic FLOP model (SURVEY.md 8a totals): 256 GFLOP per pair at 2048 surviving keypoints."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location('bench', os.path.join(os.path.dirname(__file__), '..', 'bench.py'))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    total = bench.pair_flops(2048, 2048)
+    assert abs(total / 1e9 - 256.0) < 3.0
+    assert bench.projection_flops(2048, 2048) < total
