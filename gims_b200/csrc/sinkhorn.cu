@@ -335,6 +335,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sinkhorn(SinkArgs a) {
         part[0] += __shfl_xor_sync(0xffffffffu, part[0], 1);
         if ((lane & 1) == 0) red_m[warp][lane >> 1] = part[0];      // lane 2r holds the warp's sum of row r
         __syncthreads();
+        SINK_TRACE(7);
         if (tid < nrows) {                              // thread r finishes row r
           float sr = 0.f;
 #pragma unroll
@@ -356,6 +357,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_sinkhorn(SinkArgs a) {
               sm.x = fmaf(ereg[r].x, er, sm.x); sm.y = fmaf(ereg[r].y, er, sm.y);
               sm.z = fmaf(ereg[r].z, er, sm.z); sm.w = fmaf(ereg[r].w, er, sm.w);
             }
+            // (packed FFMA2 for these passes and a 16-lanes-per-row finish were tried: both slower on B200)
+            SINK_TRACE(6);
             asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(my + 4 * tid), "f"(sm.x), "f"(sm.y),
                          "f"(sm.z), "f"(sm.w)
                          : "memory");

@@ -29,10 +29,11 @@ tall = trace.cpu()
 t = tall[:128].view(16, 8)
 pc = tall[128:128 + 148 * 8].view(148, 8)
 print('scaled-kernel path, CTA 0 (cycles):')
-print('iter   row_pass  col_pass+red.add  grid hop  gather: loads+math  barrier   total')
+print('iter   row: fma+butterfly+sync  finish rows+sync | col: fma   red+leftover | grid hop | gather: loads+math  barrier | total')
 for it in range(1, 12):
     r = [int(x) for x in t[it]]
-    print('%3d   %8d %12d %13d %14d %10d %10d' % (it, r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], r[5] - r[4], r[5] - r[0]))
+    print('%3d   %14d %18d %14d %12d %12d %14d %10d %10d' % (it, r[7] - r[0], r[1] - r[7], r[6] - r[1], r[2] - r[6], r[3] - r[2],
+                                                       r[4] - r[3], r[5] - r[4], r[5] - r[0]))
 
 import numpy as np
 pc = pc.numpy().astype(np.int64)
