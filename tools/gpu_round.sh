@@ -20,7 +20,7 @@ for s in $STAGES; do
              python bench.py --steps 1 --warmup 3 --pairs-per-step 1 --streams 1 --pool 2 --no-cpu-baseline --no-e2e > gpurun_out/ncu_bench.log 2>&1; echo "ncu rc=$?" ;;
     ncufull) B="python bench.py --steps 1 --warmup 3 --pairs-per-step 1 --streams 1 --pool 2 --no-cpu-baseline --no-e2e"
            timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_attention_tc -s 40 -c 1 -f -o gpurun_out/ncu_attention $B > gpurun_out/ncufull_attn.log 2>&1; echo "ncufull attn rc=$?"
-           timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_gemm_tc -s 150 -c 3 -f -o gpurun_out/ncu_gemm $B > gpurun_out/ncufull_gemm.log 2>&1; echo "ncufull gemm rc=$?"
+           timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_gemm_tc -s 158 -c 4 -f -o gpurun_out/ncu_gemm_layer $B > gpurun_out/ncufull_gemm.log 2>&1; echo "ncufull gemm rc=$?"
            timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_sinkhorn -s 2 -c 1 -f -o gpurun_out/ncu_sinkhorn $B > gpurun_out/ncufull_sink.log 2>&1; echo "ncufull sink rc=$?" ;;
     sanitize) timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python __graft_entry__.py smoke > gpurun_out/sanitize.log 2>&1; echo "sanitize rc=$?" ;;
   esac
