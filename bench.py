@@ -3,8 +3,13 @@
 2048 keypoints/image (configs[1]: fp32, 100 Sinkhorn iterations, r/p/m = 25/7/8).
 
   python bench.py --gpus N --steps K --warmup W            our CUDA path
-  python bench.py --impl reference ...                     the reference algorithm on the host CPU cores
-                                                           (oracle port; the reference is Python)
+  python bench.py --impl reference ...                     the reference's own CPU implementation on the host cores:
+                                                           the UNMODIFIED reference modules (baseline/_ref, a git-ignored
+                                                           copy made by __graft_entry__.build(), run under oracle/ref_shims)
+                                                           or, if that copy is absent, the oracle port
+  --kpts N                                                 keypoints per image (BASELINE configs[3] = 4096, configs[4] = 8192)
+  --weights random|damped                                  random-init weights (degenerate scores: mean 0.3, std 0.002) or
+                                                           the non-degenerate "damped" set (scores ~ 90 +- 2.6 like a trained net)
 A step = one batch of `--pairs-per-step` synthetic pairs per GPU through the whole hot path
 (AGC graphs -> SAGE -> kenc -> 18 attention layers -> scores -> Sinkhorn -> matches).
 `value`   : pairs/s, inputs already resident in HBM, pairs issued over several CUDA streams.
@@ -30,9 +35,54 @@ import torch  # noqa: E402
 
 from gims_b200.synth import make_pair, make_state_dict  # noqa: E402
 
-METRIC = 'image_pairs_per_sec_2048kp'
 UNIT = 'pairs/s'
 FALLBACK_PEAKS = {'hbm_gbs': 6650.0, 'bf16_tflops': 1590.0, 'bf16_tflops_sustained': 1400.0}
+
+
+def metric_name(kpts):
+    return 'image_pairs_per_sec_%dkp' % kpts
+
+
+def workload_name(args):
+    cfg = {2048: 'configs[1]', 4096: 'configs[3]', 8192: 'configs[4]'}.get(args.kpts, 'custom size')
+    return ('BASELINE %s: GMatcher forward, %d kp/image, fp32, 100 Sinkhorn it, AGC r/p/m 25/7/8, %s weights'
+            % (cfg, args.kpts, 'random-init' if args.weights == 'random' else 'random-init "damped" (non-degenerate)'))
+
+
+def adjust_sizes(args):
+    """Keep the step (and the per-stream workspaces) bounded at the large configs; both arms call this."""
+    if args.kpts > 2048:
+        scale = (args.kpts // 2048) ** 2
+        args.pairs_per_step = max(4, args.pairs_per_step // scale)
+        args.streams = max(2, min(args.streams, args.pairs_per_step))
+        args.pool = max(8, args.pool // scale)
+
+
+def pair_input_bytes(kpts):
+    return 2 * (kpts * 2 + 256 * kpts + kpts) * 4
+
+
+def base_config(args, world):
+    """The `config` object of the JSON line — identical for `--impl ours` and `--impl reference`."""
+    return {'workload': workload_name(args), 'kpts_per_image': args.kpts, 'weights': args.weights,
+            'sinkhorn_iterations': 100, 'agc_radius_percentile_minsize': [25, 7, 8],
+            'pairs_per_step_per_gpu': args.pairs_per_step, 'streams': args.streams,
+            'l2': 'input pool of %d distinct pairs (%.0f MB) > L2' % (args.pool, args.pool * pair_input_bytes(args.kpts) / 1e6),
+            'parallelism': 'pair-parallel x%d, no collective' % world}
+
+
+def ncu_traffic(kernel):
+    """dram__bytes_read + write per launch of `kernel` from the newest committed `ncu --set full` summary under
+    profiles/ (lines `<kernel> dram_bytes_read=<n> dram_bytes_write=<n>`); None if there is no such capture."""
+    import glob
+    import re
+    for path in sorted(glob.glob(os.path.join(ROOT, 'profiles', 'r*_ncu_full_metrics.txt')), reverse=True):
+        with open(path) as fh:
+            for ln in fh:
+                m = re.match(r'\s*%s\S*\s.*dram_bytes_read=(\d+)\s+dram_bytes_write=(\d+)' % re.escape(kernel), ln)
+                if m:
+                    return int(m.group(1)) + int(m.group(2)), os.path.relpath(path, ROOT)
+    return None, None
 
 
 def load_peaks():
@@ -185,39 +235,66 @@ def measure_tf32_peak(dev):
         torch.backends.cuda.matmul.allow_tf32 = prev
 
 
-def run_reference(args, rank, world):
-    """--impl reference: the reference algorithm (oracle port, torch-CPU + numpy) on the host cores."""
-    if rank != 0:
-        return
-    from oracle import gims_oracle as orc
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    sd = make_state_dict(0)
+def _reference_runner(args):
+    """Callable one(seed) that runs one pair of the bench workload through the reference's CPU implementation, and
+    a description of what it is.  Preferred: the unmodified reference modules copied to baseline/_ref (git-ignored,
+    made by __graft_entry__.build() where /root/reference exists; they travel to the GPU box) imported under
+    oracle/ref_shims.py.  Fallback: the oracle port."""
+    import contextlib
+    import io
+    sd = make_state_dict(0, damped=(args.weights == 'damped'))
     cfg = {'sinkhorn_iterations': 100, 'match_threshold': 0.2}
+    ref_root = os.path.join(ROOT, 'baseline', '_ref')
+    if os.path.isfile(os.path.join(ref_root, 'models', 'gmatcher.py')) and not os.environ.get('GIMS_BENCH_FORCE_PORT'):
+        os.environ['GIMS_REFERENCE_ROOT'] = ref_root
+        from oracle import ref_shims
+        ref_shims.REFERENCE_ROOT = ref_root
+        _, gm = ref_shims.load_reference()
+        model = gm.GMatcher(cfg)
+        model.load_state_dict(sd)
+        model.eval()
+
+        def one(seed):
+            data = make_pair(args.kpts, seed=seed)
+            data.update({'radius': 25, 'percentile': 7, 'min_size': 8, 'device': torch.device('cpu')})
+            with torch.no_grad(), contextlib.redirect_stdout(io.StringIO()):
+                return model(data)
+        return one, 'reference', 'unmodified reference models/{agc,gmatcher}.py (baseline/_ref) under oracle/ref_shims.py'
+    from oracle import gims_oracle as orc
 
     def one(seed):
         data = make_pair(args.kpts, seed=seed)
         data.update({'radius': 25, 'percentile': 7, 'min_size': 8})
         with torch.no_grad():
             return orc.gmatcher_forward(sd, data, cfg)
+    return one, 'port', 'oracle/gims_oracle.py (port of the reference)'
 
-    for w in range(max(1, min(args.warmup, 1))):
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's CPU implementation of the path on the host cores (rank 0 only)."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    one, kind, what = _reference_runner(args)
+    # bounded sample: each step is one pair; cap the run at a few minutes whatever --steps says
+    per_pair_guess = {2048: 1.5, 4096: 8.0, 8192: 45.0}.get(args.kpts, 1.5 * (args.kpts / 2048.0) ** 2.3)
+    steps = max(1, min(args.steps, int(180.0 / per_pair_guess)))
+    for w in range(1 if per_pair_guess < 20 else 0):
         one(1000 + w)
     t0 = time.perf_counter()
-    for s in range(args.steps):
+    for s in range(steps):
         one(2000 + s)
     dt = time.perf_counter() - t0
-    val = args.steps / dt
+    val = steps / dt
     line = {
-        'impl': 'reference', 'metric': METRIC, 'value': val, 'unit': UNIT, 'n_gpus': args.gpus, 'steps': args.steps,
-        'warmup': args.warmup, 'ms_per_step': 1e3 * dt / args.steps, 'higher_is_better': True, 'scaling': 'weak',
-        'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
-        'config': {'workload': 'BASELINE configs[1]: GMatcher forward, %d kp/image, fp32, 100 Sinkhorn it, AGC r/p/m 25/7/8, '
-                               'random-init weights' % args.kpts, 'sample': 'one pair per step (bounded sample of the same workload)',
-                   'pairs_per_step': 1},
-        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-                         'sample': '%d pairs of the bench workload, oracle/gims_oracle.py, torch %d threads' %
-                                   (args.steps, cores)},
+        'impl': 'reference', 'metric': metric_name(args.kpts), 'value': val, 'unit': UNIT, 'n_gpus': args.gpus,
+        'steps': args.steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / steps, 'higher_is_better': True,
+        'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32', 'data': 'synthetic',
+        'config': base_config(args, world),
+        'cpu_baseline': {'value': val, 'unit': UNIT, 'cores': cores, 'kind': kind,
+                         'sample': 'one pair per step, %d steps timed (bounded sample of the same workload), %s, torch %d '
+                                   'threads' % (steps, what, cores)},
         'e2e': {'value': val, 'unit': UNIT, 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
         'gpu_launches': 0,
     }
@@ -225,28 +302,19 @@ def run_reference(args, rank, world):
 
 
 def cpu_baseline(args):
-    from oracle import gims_oracle as orc
+    """Rank 0, N = 1: the CPU arm on a bounded sample (10-60 s) of the same workload, timed beside the GPU number."""
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sd = make_state_dict(0)
-    cfg = {'sinkhorn_iterations': 100, 'match_threshold': 0.2}
-    timings = {}
-
-    def one(seed):
-        data = make_pair(args.kpts, seed=seed)
-        data.update({'radius': 25, 'percentile': 7, 'min_size': 8})
-        with torch.no_grad():
-            orc.gmatcher_forward(sd, data, cfg, timings=timings)
-
-    one(1000)
-    n = 3
+    one, kind, what = _reference_runner(args)
+    n = 3 if args.kpts <= 2048 else 1
+    if args.kpts <= 4096:
+        one(1000)
     t0 = time.perf_counter()
     for s in range(n):
         one(2000 + s)
     dt = time.perf_counter() - t0
-    return {'value': n / dt, 'unit': UNIT, 'cores': cores, 'kind': 'port',
-            'sample': '%d pairs at %d kp (1 warm-up), oracle port of the reference, torch %d threads' % (n, args.kpts, cores),
-            'stage_seconds_last_pair': {k: round(v, 4) for k, v in timings.items()}}
+    return {'value': n / dt, 'unit': UNIT, 'cores': cores, 'kind': kind,
+            'sample': '%d pair(s) at %d kp, %s, torch %d threads' % (n, args.kpts, what, cores)}
 
 
 def main():
@@ -263,7 +331,10 @@ def main():
     ap.add_argument('--no-cpu-baseline', action='store_true')
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--prof-kernel', default='attention')
+    ap.add_argument('--weights', default='random', choices=['random', 'damped'])
     args = ap.parse_args()
+    METRIC = metric_name(args.kpts)
+    adjust_sizes(args)
 
     rank = int(os.environ.get('RANK', 0))
     world = int(os.environ.get('WORLD_SIZE', 1))
@@ -286,7 +357,7 @@ def main():
 
     cfg = {'sinkhorn_iterations': 100, 'match_threshold': 0.2}
     matching = Matching(cfg)
-    matching.gmodel.load_state_dict(make_state_dict(0))
+    matching.gmodel.load_state_dict(make_state_dict(0, damped=(args.weights == 'damped')))
     matching = matching.eval().to(dev)
     gm = matching.gmodel
 
@@ -312,8 +383,10 @@ def main():
         outs = step()
     torch.cuda.synchronize(dev)
     counts = outs[0]['n_kept_dev'].cpu().tolist()
-    if counts[6] != 0:
-        raise RuntimeError('edge capacity overflow in the benchmark workload')
+    if counts[6] & _lib.STATUS_ERROR_MASK:
+        raise RuntimeError('error status %#x in the benchmark workload' % counts[6])
+    sink_path = 'fast (exp-free scaled-kernel iteration)' if counts[6] & _lib.STATUS_SINKHORN_FAST else \
+        'exact (log-sum-exp iteration)'
     if world > 1:
         dist.barrier()
     torch.cuda.synchronize(dev)
@@ -359,13 +432,14 @@ def main():
                 # QK^T + PV over 4 heads x 64: 4*D*nq*nk per image; averaged over self / cross layers
                 flops = 2.0 * 256 * (n0k + n1k) ** 2
                 ach = flops / avg_s / 1e12
+                traffic, traffic_src = ncu_traffic('k_attention_tc') if args.kpts == 2048 else (None, None)
                 peak = peaks['bf16_tflops_sustained']
                 # fp32 parity = 3 tf32 MMAs per product on a pipe whose tf32 rate is half the bf16 rate: an fp32-exact
                 # kernel cannot exceed 1/6 of the bf16 peak; `frac` is against the full bf16 peak as the contract asks
                 roof = {'kernel': 'k_attention_tc', 'bound': 'tensor', 'achieved': ach, 'peak': peak,
-                        'unit': 'TFLOP/s', 'frac': ach / peak, 'traffic': 20988160,
-                        'traffic_source': 'dram__bytes_read+write per launch, profiles/r01_ncu_full_metrics.txt '
-                                          '(algorithmic: Q 4.2 MB + K, Vt tf32 planes 16.7 MB)',
+                        'unit': 'TFLOP/s', 'frac': ach / peak, 'traffic': traffic,
+                        'traffic_source': ('dram__bytes_read+write per launch, %s (algorithmic: Q 4.2 MB + K, Vt tf32 '
+                                           'planes 16.7 MB)' % traffic_src) if traffic else 'no ncu capture at this size',
                         'ceiling_frac': 1.0 / 6.0, 'frac_of_ceiling': ach / peak * 6.0,
                         'tf32_dense_tflops_measured': tf32_peak,
                         'frac_of_measured_tf32_over_3': (ach / (tf32_peak / 3.0)) if tf32_peak else None,
@@ -376,9 +450,10 @@ def main():
                 byts = 4.0 * (n0k + 1) * (n1k + 1)
                 ach = byts / avg_s / 1e9
                 peak = peaks['hbm_gbs']
+                traffic, traffic_src = ncu_traffic('k_sinkhorn') if args.kpts == 2048 else (None, None)
                 roof = {'kernel': 'k_sinkhorn', 'bound': 'hbm', 'achieved': ach, 'peak': peak, 'unit': 'GB/s',
-                        'frac': ach / peak, 'traffic': 16961024,
-                        'traffic_source': 'dram__bytes_read+write per launch, profiles/r01_ncu_full_metrics.txt',
+                        'frac': ach / peak, 'traffic': traffic,
+                        'traffic_source': ('dram__bytes_read+write per launch, %s' % traffic_src) if traffic else None,
                         'peak_source': peaks['_source'],
                         'launches_timed': cnt.value, 'avg_launch_ms': avg_s * 1e3, 'bytes_per_launch': byts}
 
@@ -406,7 +481,8 @@ def main():
                 ent['frac_of_ceiling'] = ent['frac'] * 6.0
             elif cls == 'sinkhorn':
                 ent.update({'bound': 'latency (100 grid-wide exchanges through L2)', 'us_per_iteration':
-                            tot.value / cnt.value * 1e3 / 100.0, 'hbm_bytes_per_launch': 4.0 * (n0k + 1) * (n1k + 1)})
+                            tot.value / cnt.value * 1e3 / 100.0, 'hbm_bytes_per_launch': 4.0 * (n0k + 1) * (n1k + 1),
+                            'path': sink_path})
             elif cls == 'cosine':
                 fl = 2.0 * d * (n0k * (n0k + 1) / 2 + n1k * (n1k + 1) / 2)
                 ent.update({'bound': 'fp64 pipe', 'achieved': fl / (tot.value / npair / 1e3) / 1e12, 'unit': 'TFLOP/s (fp64)',
@@ -479,11 +555,7 @@ def main():
             'metric': METRIC, 'value': value, 'unit': UNIT, 'n_gpus': world, 'steps': args.steps, 'warmup': args.warmup,
             'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic',
-            'config': {'workload': 'BASELINE configs[1]: GMatcher forward, %d kp/image, fp32, 100 Sinkhorn it, AGC r/p/m 25/7/8, '
-                                   'random-init weights' % args.kpts,
-                       'pairs_per_step_per_gpu': P, 'streams': args.streams, 'kept_keypoints': counts[:2],
-                       'l2': 'input pool of %d distinct pairs (%.0f MB) > L2' % (args.pool, args.pool * in_bytes / 1e6),
-                       'parallelism': 'pair-parallel x%d, no collective' % world},
+            'config': base_config(args, world), 'kept_keypoints': counts[:2], 'sinkhorn_path': sink_path,
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches) * world, 'gpu_launches_per_rank': int(launches),
             'roofline': roof, 'roofline_other': other,
             'pair_gflop': pair_flops(counts[0], counts[1]) / 1e9,

@@ -9,8 +9,12 @@ from .build import LIB_PATH
 
 MAX_LAYERS = 64
 MAX_KENC = 8
-MAX_KPTS = 32768
+MAX_KPTS = 16384
 STATUS_EDGE_OVERFLOW = 1
+STATUS_SINKHORN_TIMEOUT = 2
+STATUS_ERROR_MASK = 0xff
+STATUS_SINKHORN_FAST = 0x100
+STATUS_SINKHORN_EXACT = 0x200
 GEMM_SIMT, GEMM_TC = 0, 1
 PROF = {'gemm': 1, 'attention': 2, 'sinkhorn': 3, 'score': 4, 'cosine': 5, 'sage_gather': 6}
 
@@ -109,7 +113,8 @@ SIGNATURES = {
     'gims_sinkhorn_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int]),
     'gims_sinkhorn_match': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_void_p,
                                       C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
-                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    'gims_sinkhorn_max_columns': (C.c_int, []),
     'gims_pair_workspace_bytes': (C.c_size_t, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     'gims_forward_pair': (C.c_int, [C.c_void_p, C.POINTER(PairInputs), C.POINTER(PairOutputs), C.c_void_p,
                                     C.c_size_t, C.c_void_p]),

@@ -39,7 +39,7 @@ def _digest():
     files = _sources() + sorted(glob.glob(os.path.join(CSRC, '*.cuh'))) + \
         [os.path.join(os.path.dirname(HERE), 'include', 'gims_b200.h')]
     for f in files:
-        h.update(f.encode())
+        h.update(os.path.basename(f).encode())        # names and contents only: the digest is checkout-independent
         with open(f, 'rb') as fh:
             h.update(fh.read())
     h.update(' '.join(NVCC_FLAGS).encode())

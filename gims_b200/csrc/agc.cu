@@ -718,7 +718,9 @@ __global__ void __launch_bounds__(256) k_final_fill(int n, const int* __restrict
   int row = indptr[id];
   int b0 = indptr_base[i], nb = indptr_base[i + 1] - b0;
   int total = nb + extra_cnt[i];
-  if (row + total > edge_cap) {
+  // the base CSR itself may have overflowed (entries past edge_cap were never written): never read or write past
+  // either capacity; the status bit makes the host retry with a larger edge_cap
+  if (row + total > edge_cap || b0 + nb > edge_cap) {
     if (lane == 0) atomicOr(status, GIMS_STATUS_EDGE_OVERFLOW);
     return;
   }
@@ -781,6 +783,13 @@ __global__ void __launch_bounds__(256) k_gather_kept(int n, const int* __restric
   }
 }
 
+// Edge-capacity overflow: the CSR is incomplete (rows past the capacity were never written) while indptr / E hold the
+// uncapped totals.  Report an EMPTY graph (N' = 0, E = 0) so that no later kernel — they all size themselves from
+// N' in device memory — walks the unwritten part of `indices`; the status bit tells the host to retry.
+__global__ void k_overflow_guard(const unsigned* __restrict__ status, int* n_kept, int* n_edges, int* n_comp, int* indptr) {
+  if (*status & GIMS_STATUS_EDGE_OVERFLOW) { *n_kept = 0; *n_edges = 0; *n_comp = 0; indptr[0] = 0; }
+}
+
 }  // namespace
 
 }  // namespace gims
@@ -799,7 +808,15 @@ extern "C" int gims_agc_build(const float* kpts, const float* desc, int desc_cha
                               unsigned* status_dev, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   if (n < 2 || n > GIMS_MAX_KPTS) { set_error("gims_agc_build: n=%d outside [2, %d]", n, GIMS_MAX_KPTS); return GIMS_ERR_ARG; }
-  if (edge_cap < 1 || k_rank < 0) { set_error("gims_agc_build: bad edge_cap/k_rank"); return GIMS_ERR_ARG; }
+  if (edge_cap < 1 || k_rank < 0 || k_rank >= (long long)n * (n - 1) / 2) {
+    set_error("gims_agc_build: bad edge_cap %d / k_rank %lld (need 0 <= k_rank < n(n-1)/2)", edge_cap, k_rank);
+    return GIMS_ERR_ARG;
+  }
+  if (!kpts || !desc || !scores || !workspace || !kept_idx || !n_kept_dev || !indptr || !indices || !n_edges_dev ||
+      !kpts_out || !feat_out || !scores_out || !thr_out || !n_comp_dev || !status_dev) {
+    set_error("gims_agc_build: null pointer argument");
+    return GIMS_ERR_ARG;
+  }
   AgcWs w;
   size_t need = carve(w, workspace, workspace_bytes, n, edge_cap);
   if (need > workspace_bytes) { set_error("gims_agc_build: workspace %zu < %zu", workspace_bytes, need); return GIMS_ERR_WORKSPACE; }
@@ -880,6 +897,8 @@ extern "C" int gims_agc_build(const float* kpts, const float* desc, int desc_cha
   // a-7
   k_gather_kept<<<cdiv(n, 8), 256, 0, st>>>(n, kept_idx, n_kept_dev, kp, feat, scores,
                                             reinterpret_cast<float2*>(kpts_out), feat_out, scores_out);
+  GIMS_LAUNCH_OK();
+  k_overflow_guard<<<1, 1, 0, st>>>(status_dev, n_kept_dev, n_edges_dev, n_comp_dev, indptr);
   GIMS_LAUNCH_OK();
   return GIMS_OK;
 }

@@ -358,8 +358,34 @@ extern "C" size_t gims_pair_workspace_bytes(const gims_model* m, int n0, int n1,
 extern "C" int gims_forward_pair(const gims_model* m, const gims_pair_inputs* in, const gims_pair_outputs* o,
                                  void* workspace, size_t workspace_bytes, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (!m || !in || !o) { set_error("gims_forward_pair: null argument"); return GIMS_ERR_ARG; }
+  if (!m || !in || !o || !workspace) { set_error("gims_forward_pair: null argument"); return GIMS_ERR_ARG; }
   int n0 = in->n[0], n1 = in->n[1];
+  // validate everything BEFORE the first launch: a late error would leave half a forward enqueued
+  if (n0 < 2 || n1 < 2 || n0 > GIMS_MAX_KPTS || n1 > GIMS_MAX_KPTS) {
+    set_error("gims_forward_pair: keypoint counts (%d, %d) outside [2, %d]", n0, n1, GIMS_MAX_KPTS);
+    return GIMS_ERR_ARG;
+  }
+  if (n1 > gims_sinkhorn_max_columns()) {
+    set_error("gims_forward_pair: n1=%d exceeds the Sinkhorn kernel's shared-memory limit of %d columns", n1, gims_sinkhorn_max_columns());
+    return GIMS_ERR_ARG;
+  }
+  if (in->edge_cap < 1) { set_error("gims_forward_pair: edge_cap %d", in->edge_cap); return GIMS_ERR_ARG; }
+  if (!o->n_kept_dev || !o->n_edges_dev || !o->n_comp_dev || !o->thr_dev || !o->mdesc || !o->u || !o->v || !o->status_dev) {
+    set_error("gims_forward_pair: null output pointer");
+    return GIMS_ERR_ARG;
+  }
+  for (int s = 0; s < 2; ++s) {
+    if (!in->kpts[s] || !in->desc[s] || !in->scores[s] || !o->kept_idx[s] || !o->csr_indptr[s] || !o->csr_indices[s] ||
+        !o->kpts[s] || !o->feat[s] || !o->scores[s] || !o->matches[s] || !o->mscores[s] || !o->indices[s]) {
+      set_error("gims_forward_pair: null pointer for image %d", s);
+      return GIMS_ERR_ARG;
+    }
+    long long len = (long long)in->n[s] * (in->n[s] - 1) / 2;
+    if (in->k_rank[s] < 0 || in->k_rank[s] >= len) {
+      set_error("gims_forward_pair: k_rank[%d]=%lld outside [0, %lld)", s, in->k_rank[s], len);
+      return GIMS_ERR_ARG;
+    }
+  }
   PairWs w;
   size_t need = carve_pair(w, workspace, workspace_bytes, n0, n1, in->edge_cap);
   if (need > workspace_bytes) { set_error("gims_forward_pair: workspace %zu < %zu", workspace_bytes, need); return GIMS_ERR_WORKSPACE; }
@@ -396,6 +422,6 @@ extern "C" int gims_forward_pair(const gims_model* m, const gims_pair_inputs* in
   GIMS_TRY(gims_final_scores(m, w.desc, n0, n1, o->n_kept_dev, o->mdesc, coup, w.scratch, stream));
   GIMS_TRY(gims_sinkhorn_match(coup, n0, n1, o->n_kept_dev, m->cfg.sinkhorn_iterations, m->cfg.match_threshold, w.sink,
                                w.sink_bytes, o->u, o->v, o->indices[0], o->indices[1], o->matches[0], o->matches[1],
-                               o->mscores[0], o->mscores[1], stream));
+                               o->mscores[0], o->mscores[1], o->status_dev, stream));
   return GIMS_OK;
 }

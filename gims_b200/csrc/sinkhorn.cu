@@ -30,6 +30,9 @@ constexpr int kMaxGrid = 256;
 constexpr int kRMax = 16;            // rows per CTA handled by the unrolled (register) column pass
 constexpr int kRowChunks = 17;       // float4 chunks per lane of the register row pass (rows up to 2176 columns)
 constexpr float kLog2e = 1.4426950408889634f;
+// Bound of every poll in clock64 cycles (~2 s at 1.9 GHz): far beyond any legitimate wait, also under ncu replay, MPS
+// time-slicing or a debugger; on expiry the launch poisons its outputs and raises GIMS_STATUS_SINKHORN_TIMEOUT.
+constexpr long long kPollTimeoutClk = 4000000000LL;
 constexpr int kWays = 2;             // copies of the column-sum buffer (CTA b adds into copy b % kWays): the red.adds of
                                      // 148 CTAs on one 128-byte line serialize in L2, four copies cut that chain by four
 
@@ -77,7 +80,7 @@ __device__ __forceinline__ u64 poll(const u64* p, unsigned* err, Pred ready) {
     if (ready(w)) return w;
     if ((++spins & 1023u) == 0) {
       if (*(volatile unsigned*)err) return w;
-      if (clock64() - t0 > 400000000LL) { atomicExch(err, 1u); return w; }
+      if (clock64() - t0 > kPollTimeoutClk) { atomicExch(err, 1u); return w; }
     }
   }
 }
@@ -109,7 +112,7 @@ __device__ __forceinline__ void wait_flags(const unsigned* flags, int n, unsigne
       if (__all_sync(0xffffffffu, ok)) break;
       if ((++spins & 63u) == 0) {
         bool bail = *(volatile unsigned*)err != 0u;
-        if (clock64() - t0 > 400000000LL) { atomicExch(err, 1u); bail = true; }
+        if (clock64() - t0 > kPollTimeoutClk) { atomicExch(err, 1u); bail = true; }
         if (__any_sync(0xffffffffu, bail)) break;
       }
     }
@@ -129,7 +132,7 @@ __device__ __forceinline__ void grid_hop(unsigned* counter, unsigned target, uns
     while (ld_acquire_u32(counter) < target) {
       if ((++spins & 255u) == 0) {
         if (*(volatile unsigned*)err) break;
-        if (clock64() - t0 > 400000000LL) { atomicExch(err, 1u); break; }
+        if (clock64() - t0 > kPollTimeoutClk) { atomicExch(err, 1u); break; }
       }
     }
   }
@@ -278,6 +281,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sinkhorn(SinkArgs a) {
     }
   }
 
+  if (b == 0 && tid == 0) a.err[1] = fast ? GIMS_STATUS_SINKHORN_FAST : GIMS_STATUS_SINKHORN_EXACT;
   // the trace pointer is read once: a load of the global per stamp would sit on every iteration's critical path
   long long* const gtrace = (tid == 0) ? g_sink_trace : nullptr;
   long long* trace = (b == 0) ? gtrace : nullptr;
@@ -731,10 +735,13 @@ __global__ void __launch_bounds__(kThreads, 1) k_sinkhorn(SinkArgs a) {
 __global__ void k_match_finalize(int n0_max, int n1_max, const int* __restrict__ n_dev, const int* __restrict__ idx0,
                                  const int* __restrict__ idx1, const float* __restrict__ max0, float thr,
                                  int64_t* __restrict__ matches0, int64_t* __restrict__ matches1,
-                                 float* __restrict__ ms0, float* __restrict__ ms1, const unsigned* __restrict__ err) {
+                                 float* __restrict__ ms0, float* __restrict__ ms1, const unsigned* __restrict__ err,
+                                 unsigned* __restrict__ status) {
   int n0 = n_dev ? min(n_dev[0], n0_max) : n0_max;
   int n1 = n_dev ? min(n_dev[1], n1_max) : n1_max;
   int t = blockIdx.x * blockDim.x + threadIdx.x;
+  // err[0]: a poll timed out; err[1]: which iteration the launch ran (GIMS_STATUS_SINKHORN_FAST / _EXACT)
+  if (t == 0 && status) atomicOr(status, (err[0] ? GIMS_STATUS_SINKHORN_TIMEOUT : 0u) | err[1]);
   if (*err) {                                     // a poll timed out inside k_sinkhorn: fail loudly, not silently
     if (t < n0) { ms0[t] = CUDART_NAN_F; matches0[t] = -2; }
     if (t < n1) { ms1[t] = CUDART_NAN_F; matches1[t] = -2; }
@@ -802,11 +809,29 @@ extern "C" size_t gims_sinkhorn_workspace_bytes(int n0_max, int n1_max) {
   return carve(w, nullptr, 0, n0_max, n1_max, kMaxGrid);
 }
 
+// largest n1_max (image-1 keypoints) whose potentials fit the kernel's shared memory, for n0_max <= GIMS_MAX_KPTS
+extern "C" int gims_sinkhorn_max_columns(void) {
+  int dev = 0, sms = 0, smem_optin = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess ||
+      cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev) != cudaSuccess || sms < 1)
+    return 0;
+  int G = sms < kMaxGrid ? sms : kMaxGrid;
+  long long budget = (long long)smem_optin - 5120;
+  long long rlen = ((GIMS_MAX_KPTS + 1 + G - 1) / G + 3) & ~3;
+  long long c = (budget / 4 - 4 * rlen) / 2 - 4;         // 2 * round4(C) + 4 * rlen floats <= budget
+  return (int)(c < 1 ? 0 : c - 1);
+}
+
 extern "C" int gims_sinkhorn_match(const float* couplings, int n0_max, int n1_max, const int* n_dev, int iters,
                                    float match_threshold, void* workspace, size_t workspace_bytes, float* u, float* v,
                                    int* indices0, int* indices1, int64_t* matches0, int64_t* matches1, float* mscores0,
-                                   float* mscores1, void* stream) {
+                                   float* mscores1, unsigned* status_dev, void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!couplings || !workspace || !u || !v || !indices0 || !indices1 || !matches0 || !matches1 || !mscores0 || !mscores1) {
+    set_error("gims_sinkhorn_match: null pointer argument");
+    return GIMS_ERR_ARG;
+  }
   if (n0_max < 1 || n1_max < 1 || iters < 0) { set_error("gims_sinkhorn_match: bad sizes"); return GIMS_ERR_ARG; }
   int dev = 0, sms = 0, smem_optin = 0;
   GIMS_CUDA_OK(cudaGetDevice(&dev));
@@ -848,7 +873,7 @@ extern "C" int gims_sinkhorn_match(const float* couplings, int n0_max, int n1_ma
   count_launch();
   int m = n0_max > n1_max ? n0_max : n1_max;
   k_match_finalize<<<cdiv(m, 256), 256, 0, st>>>(n0_max, n1_max, n_dev, indices0, indices1, w.max0, match_threshold,
-                                                 matches0, matches1, mscores0, mscores1, w.err);
+                                                 matches0, matches1, mscores0, mscores1, w.err, status_dev);
   GIMS_LAUNCH_OK();
   return GIMS_OK;
 }

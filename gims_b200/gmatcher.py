@@ -109,7 +109,10 @@ class GMatcher(nn.Module):
         self._model = None            # C handle
         self._packed = None           # device buffer the handle points into
         self._packed_key = None
-        self._ws = {}                 # (n0, n1, edge_cap, device) -> workspace tensor
+        self._inflight = {}           # handle value -> number of host calls currently inside the library with it
+        self._retired = []            # (handle, packed buffer) replaced by a re-pack, destroyed once idle
+        self._ws = {}                 # (device, stream slot) -> [workspace tensor, n0 cap, n1 cap, edge cap]
+        self.edge_cap_factor = 64     # initial capacity of the CSR edge list = factor * max(n0, n1); grows on overflow
         if cfg['weights_path']:
             weights = torch.load(cfg['weights_path'], map_location='cpu', weights_only=False)
             if ('ema' in weights) and (weights['ema'] is not None):
@@ -138,16 +141,40 @@ class GMatcher(nn.Module):
         return out
 
     def _invalidate(self):
-        if getattr(self, '_model', None) is not None:
-            _lib.lib().gims_model_destroy(self._model)
-        self._model = None
-        self._packed = None
-        self._packed_key = None
-        self.__dict__['_ptensors'] = None
+        """Drop the packed weights (parameters changed / moved).  Another thread may still be inside the library with
+        the current handle, and enqueued kernels may still read the packed buffer: both are only RETIRED here and
+        destroyed by `_reap` once no host call holds the handle (after a device synchronisation)."""
+        with _HANDLE_LOCK:
+            if getattr(self, '_model', None) is not None:
+                self._retired.append((self._model, self._packed))
+            self._model = None
+            self._packed = None
+            self._packed_key = None
+            self.__dict__['_ptensors'] = None
+            self._reap()
+
+    def _reap(self, force=False):
+        keep = []
+        for h, packed in getattr(self, '_retired', []):
+            if not force and self._inflight.get(h.value, 0) > 0:
+                keep.append((h, packed))
+                continue
+            if packed is not None and packed.is_cuda:
+                torch.cuda.synchronize(packed.device)       # kernels that read the old weights have finished
+            _lib.lib().gims_model_destroy(h)
+        self._retired = keep
+
+    def repack(self):
+        """Force a re-pack of the weights on the next call.  Needed only after edits that bypass autograd's version
+        counter (`param.data[...] = ...`, raw pointer writes); in-place ops, `.to()` and `load_state_dict` are
+        detected automatically."""
+        self._invalidate()
 
     def __del__(self):
         try:
-            self._invalidate()
+            with _HANDLE_LOCK:
+                self._invalidate()
+                self._reap(force=True)
         except Exception:
             pass
 
@@ -188,6 +215,23 @@ class GMatcher(nn.Module):
         with _HANDLE_LOCK:
             return self._handle_locked()
 
+    def _acquire(self):
+        """handle() + mark it in use by this host call (see `_invalidate`); pair with `_release`."""
+        with _HANDLE_LOCK:
+            h = self._handle_locked()
+            self._inflight[h.value] = self._inflight.get(h.value, 0) + 1
+            return h
+
+    def _release(self, h):
+        with _HANDLE_LOCK:
+            left = self._inflight.get(h.value, 1) - 1
+            if left:
+                self._inflight[h.value] = left
+            else:
+                self._inflight.pop(h.value, None)
+                if self._retired:
+                    self._reap()
+
     def _handle_locked(self):
         dev = self.bin_score.device
         if dev.type != 'cuda':
@@ -196,6 +240,7 @@ class GMatcher(nn.Module):
         if self._model is not None and key == self._packed_key:
             return self._model
         self._invalidate()
+        key = (self._param_version(), self.config['sinkhorn_iterations'], self.config['match_threshold'])
         flat, offsets, _ = pack_state_dict(self.state_dict(), self.config)
         self._packed = flat.to(dev)
         cfg = self.c_config()
@@ -219,19 +264,24 @@ class GMatcher(nn.Module):
         return k
 
     def _workspace(self, n0, n1, edge_cap, dev, slot=0):
-        key = (n0, n1, edge_cap, str(dev), slot)
+        """One GROW-ONLY workspace per (device, stream slot): sized for the largest (n0, n1, edge_cap) seen so far on
+        that slot (rounded up, so that real data with a different keypoint count per pair does not reallocate on
+        every call).  The library carves it for the actual sizes of each call."""
+        key = (str(dev), slot)
         with _HANDLE_LOCK:
-            return self._workspace_locked(key, n0, n1, edge_cap, dev)
-
-    def _workspace_locked(self, key, n0, n1, edge_cap, dev):
-        ws = self._ws.get(key)
-        if ws is None:
-            if len(self._ws) > 64:
-                self._ws.clear()
-            nbytes = _lib.lib().gims_pair_workspace_bytes(self._model, n0, n1, edge_cap)
+            ent = self._ws.get(key)
+            if ent is not None and ent[1] >= n0 and ent[2] >= n1 and ent[3] >= edge_cap:
+                return ent[0]
+            c0 = max(-(-n0 // 256) * 256, ent[1] if ent else 0)
+            c1 = max(-(-n1 // 256) * 256, ent[2] if ent else 0)
+            ce = max(edge_cap, ent[3] if ent else 0)
+            nbytes = _lib.lib().gims_pair_workspace_bytes(None, c0, c1, ce)
+            if ent is not None:
+                self._ws[key] = None          # release the old block before taking the larger one
+                del ent
             ws = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
-            self._ws[key] = ws
-        return ws
+            self._ws[key] = [ws, c0, c1, ce]
+            return ws
 
     def run_pair(self, kpts0, desc0, scores0, kpts1, desc1, scores1, shape0, shape1, radius=25, percentile=7,
                  min_size=8, edge_cap=None, debug=False, stream=None, slot=0):
@@ -239,8 +289,9 @@ class GMatcher(nn.Module):
         Enqueues everything on `stream` (default: current) and returns a dict of device tensors sized
         for the INPUT counts plus `n_kept_dev`; nothing synchronises.  `forward` slices them."""
         L = _lib.lib()
-        model = self.handle()
         dev = self.bin_score.device          # host inputs are copied here (the H2D of the e2e path)
+        if dev.type != 'cuda':
+            raise _lib.GimsError('GMatcher must live on a CUDA device (no CPU path): call .to("cuda")')
         n0, n1 = int(kpts0.shape[0]), int(kpts1.shape[0])
         if n0 < 2 or n1 < 2:
             raise ValueError('each image needs at least 2 keypoints (the reference fails earlier, agc.py:439)')
@@ -248,7 +299,7 @@ class GMatcher(nn.Module):
             raise ValueError('more than %d keypoints per image' % _lib.MAX_KPTS)
         d = self.config['descriptor_dim']
         if edge_cap is None:
-            edge_cap = max(1024, 64 * max(n0, n1))
+            edge_cap = max(1024, int(self.edge_cap_factor) * max(n0, n1))
         f32 = dict(dtype=torch.float32, device=dev)
         i32 = dict(dtype=torch.int32, device=dev)
         # counts and kept indices share one buffer so that the host needs ONE device->host copy per call
@@ -316,9 +367,13 @@ class GMatcher(nn.Module):
         # one workspace per stream: calls on one stream are ordered, calls on different streams (several pairs in
         # flight, or several host threads calling forward() concurrently) must not share scratch memory
         ws = self._workspace(n0, n1, edge_cap, dev, (slot, st.cuda_stream))
-        with torch.cuda.device(dev):
-            _lib.check(L.gims_forward_pair(model, C.byref(pin), C.byref(po), _lib.ptr(ws), ws.numel(),
-                                           C.c_void_p(st.cuda_stream)), 'gims_forward_pair')
+        model = self._acquire()
+        try:
+            with torch.cuda.device(dev):
+                _lib.check(L.gims_forward_pair(model, C.byref(pin), C.byref(po), _lib.ptr(ws), ws.numel(),
+                                               C.c_void_p(st.cuda_stream)), 'gims_forward_pair')
+        finally:
+            self._release(model)
         out['_inputs'] = keep          # keep the staged inputs alive until the stream has consumed them
         out['edge_cap'] = edge_cap
         return out
@@ -344,12 +399,17 @@ class GMatcher(nn.Module):
                                   edge_cap=cap)
                 meta = r['meta'].cpu()                  # the one device->host sync of the call: counts + kept indices
                 counts = meta[:8]
-                if int(counts[6]) & _lib.STATUS_EDGE_OVERFLOW:
+                status = int(counts[6])
+                if status & _lib.STATUS_EDGE_OVERFLOW:
+                    # the graph of this attempt was reported empty (nothing downstream ran on it): retry with more room
                     n_max = max(r['kpts0'].shape[0], r['kpts1'].shape[0])
                     if r['edge_cap'] >= n_max * n_max:
                         raise _lib.GimsError('edge capacity overflow')
                     cap = min(r['edge_cap'] * 4, n_max * n_max)
                     continue
+                if status & _lib.STATUS_SINKHORN_TIMEOUT:
+                    raise _lib.GimsError('Sinkhorn kernel: a grid-wide wait timed out (GPU shared / preempted?); '
+                                         'the results of this call are invalid')
                 break
             r['counts'] = counts
             r['meta_host'] = meta

@@ -46,10 +46,17 @@ extern "C" {
 #define GIMS_NUM_HEADS       4   /* hard-coded in the reference too (gmatcher.py:131) */
 #define GIMS_MAX_LAYERS     64
 #define GIMS_MAX_KENC        8
-#define GIMS_MAX_KPTS    32768   /* per image */
+#define GIMS_MAX_KPTS    16384   /* per image: the AGC cosine matrix is n^2 fp32 (1 GiB), the Sinkhorn kernel keeps
+                                    2(n+1) floats of potentials in shared memory */
 
-/* status words written by the kernels into `gims_pair_outputs.status_dev` / agc `status_dev` */
-#define GIMS_STATUS_EDGE_OVERFLOW  1u
+/* status word written by the kernels into `gims_pair_outputs.status_dev` / the `status_dev` arguments.
+ * Error bits (the host side raises on them): */
+#define GIMS_STATUS_EDGE_OVERFLOW     1u   /* edge_cap exceeded: the graph is reported EMPTY (N' = 0), retry larger */
+#define GIMS_STATUS_SINKHORN_TIMEOUT  2u   /* a bounded poll inside k_sinkhorn expired: outputs are poisoned (NaN / -2) */
+#define GIMS_STATUS_ERROR_MASK        0xffu
+/* Information bits: which Sinkhorn iteration the launch ran */
+#define GIMS_STATUS_SINKHORN_FAST   0x100u /* exp-free scaled-kernel iteration */
+#define GIMS_STATUS_SINKHORN_EXACT  0x200u /* log-sum-exp iteration (fallback) */
 
 typedef struct gims_model gims_model;
 
@@ -130,7 +137,8 @@ GIMS_API int  gims_packed_blob_count(const gims_config* cfg_host);
  *   kpts_out [n][2], feat_out [n][256], scores_out [n]   = ndata point/feat/score (agc.py:705-707)
  *   thr_out            the cosine threshold (agc.py:439-440)
  *   n_comp_dev         number of components after pruning (the value agc.py:540 prints)
- *   status_dev         GIMS_STATUS_* bits (edge_cap overflow)
+ *   status_dev         GIMS_STATUS_* bits are OR-ed in.  On GIMS_STATUS_EDGE_OVERFLOW the CSR is incomplete and the
+ *                      graph is reported empty (*n_kept_dev = *n_edges_dev = 0), so nothing downstream reads it.
  * edge_cap = capacity of `indices` in ints (directed edges). */
 GIMS_API size_t gims_agc_workspace_bytes(int n, int edge_cap);
 GIMS_API int gims_agc_build(const float* kpts, const float* desc, int desc_channel_major, const float* scores, int n,
@@ -173,12 +181,16 @@ GIMS_API int gims_final_scores(const gims_model* m, const float* desc, int n0_ma
  *   u [n0_max+1], v [n1_max+1]  final potentials (log_sinkhorn_iterations' u, v)
  *   indices0/1 int32  pre-threshold row/column argmax (gmatcher.py:284-285)
  *   matches0/1 int64 (-1 = unmatched), mscores0/1 fp32 (gmatcher.py:286-294)
- * workspace: gims_sinkhorn_workspace_bytes(n0_max, n1_max). */
+ *   status_dev (may be NULL): GIMS_STATUS_SINKHORN_* bits are OR-ed in
+ * workspace: gims_sinkhorn_workspace_bytes(n0_max, n1_max).  n1_max is limited by shared memory
+ * (gims_sinkhorn_max_columns()). */
+GIMS_API int gims_sinkhorn_max_columns(void);
 GIMS_API size_t gims_sinkhorn_workspace_bytes(int n0_max, int n1_max);
 GIMS_API int gims_sinkhorn_match(const float* couplings, int n0_max, int n1_max, const int* n_dev, int iters,
                         float match_threshold, void* workspace, size_t workspace_bytes,
                         float* u, float* v, int* indices0, int* indices1,
-                        int64_t* matches0, int64_t* matches1, float* mscores0, float* mscores1, void* stream);
+                        int64_t* matches0, int64_t* matches1, float* mscores0, float* mscores1,
+                        unsigned* status_dev, void* stream);
 
 /* ---- whole pair: replaces GMatcher.forward (gmatcher.py:219-307), test mode ----------------- */
 typedef struct {

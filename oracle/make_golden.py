@@ -53,6 +53,16 @@ FWD_CASES = {
     'fwd_n2048_damped': dict(n0=2048, n1=2048, seed=25, width=800, height=600, radius=25, percentile=7,
                              min_size=8, wseed=0, peaked=False, damped=True, iters=100, image_style='tensor',
                              match_threshold=0.005),
+    # BASELINE configs[3] / configs[4] sizes (L2-resident and HBM-streaming Sinkhorn regimes), non-degenerate weights
+    'fwd_n4096_damped': dict(n0=4096, n1=4096, seed=27, width=800, height=600, radius=25, percentile=7,
+                             min_size=8, wseed=0, peaked=False, damped=True, iters=100, image_style='tensor',
+                             match_threshold=0.005),
+    'fwd_n4096_ragged_peaked': dict(n0=4096, n1=3500, seed=28, width=800, height=600, radius=15, percentile=2,
+                                    min_size=7, wseed=1, peaked=True, damped=False, iters=20, image_style='eval',
+                                    match_threshold=0.0005),
+    'fwd_n8192_damped': dict(n0=8192, n1=8192, seed=29, width=1600, height=1200, radius=25, percentile=7,
+                             min_size=8, wseed=0, peaked=False, damped=True, iters=100, image_style='tensor',
+                             match_threshold=0.005),
 }
 SUB = 48   # rows/cols kept of dense matrices
 
@@ -151,11 +161,16 @@ def run_fwd(rec):
 def main():
     os.makedirs(GOLDEN_DIR, exist_ok=True)
     torch.manual_seed(0)
+    only = set(sys.argv[1:])          # optional: fixture names to (re)generate; default all
     for name, rec in AGC_CASES.items():
+        if only and name not in only:
+            continue
         out = run_agc(rec)
         np.savez_compressed(os.path.join(GOLDEN_DIR, name + '.npz'), recipe=np.array(repr(rec)), **out)
         print(name, {k: v.shape for k, v in out.items() if k.startswith('kept')})
     for name, rec in FWD_CASES.items():
+        if only and name not in only:
+            continue
         out = run_fwd(rec)
         np.savez_compressed(os.path.join(GOLDEN_DIR, name + '.npz'), recipe=np.array(repr(rec)), **out)
         print(name, 'kept', out['kept0'].shape, out['kept1'].shape,

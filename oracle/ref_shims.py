@@ -1,7 +1,8 @@
 """TEST INFRASTRUCTURE — import shims that let the UNMODIFIED reference run in this container.
 
-Only `oracle/make_golden.py` and `tests/test_oracle_vs_reference.py` use this file, and only where
-`/root/reference` exists (the build container).  It never travels into the product path.
+Only `oracle/make_golden.py`, `tests/test_oracle_vs_reference.py` and the reference arm of `bench.py`
+(`--impl reference`, on the git-ignored copy under baseline/_ref) use this file.  It never travels into the
+product path.
 
 The reference imports three packages that are absent here:
 `matplotlib` (import only), `torch_scatter` (training loss only) and `dgl` — pinned `dgl==1.1.2+cu117`

@@ -225,7 +225,8 @@ def test_forward_stages_vs_oracle():
 
 
 @pytest.mark.parametrize('n0,n1,iters,scale', [(1, 1, 3, 1.0), (5, 9, 100, 1.0), (300, 257, 20, 5.0), (2048, 2048, 100, 1.0),
-                                                (1000, 3100, 10, 30.0), (4500, 4000, 4, 1.0)])
+                                                (1000, 3100, 10, 30.0), (4500, 4000, 4, 1.0), (4500, 4000, 100, 3.0),
+                                                (8200, 8100, 30, 1.0)])
 def test_sinkhorn_vs_oracle(n0, n1, iters, scale):
     """a-14/a-15 alone on random couplings: resident (smem slab) and streamed regimes, ragged, tiny."""
     import ctypes as C
@@ -249,11 +250,16 @@ def test_sinkhorn_vs_oracle(n0, n1, iters, scale):
     i0, i1 = torch.zeros(n0m, dtype=torch.int32, device=dev), torch.zeros(n1m, dtype=torch.int32, device=dev)
     m0, m1 = torch.zeros(n0m, dtype=torch.int64, device=dev), torch.zeros(n1m, dtype=torch.int64, device=dev)
     s0, s1 = torch.zeros(n0m, device=dev), torch.zeros(n1m, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
     _lib.check(L.gims_sinkhorn_match(_lib.ptr(cbuf), n0m, n1m, _lib.ptr(nd), iters, 0.0, _lib.ptr(ws), ws.numel(),
                                      _lib.ptr(uo), _lib.ptr(vo), _lib.ptr(i0), _lib.ptr(i1), _lib.ptr(m0), _lib.ptr(m1),
-                                     _lib.ptr(s0), _lib.ptr(s1), C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+                                     _lib.ptr(s0), _lib.ptr(s1), _lib.ptr(status),
+                                     C.c_void_p(torch.cuda.current_stream().cuda_stream)),
                'gims_sinkhorn_match')
     torch.cuda.synchronize()
+    st_word = int(status.cpu())
+    assert st_word & _lib.STATUS_ERROR_MASK == 0, 'status %#x' % st_word
+    assert st_word & (_lib.STATUS_SINKHORN_FAST | _lib.STATUS_SINKHORN_EXACT)
     eu = _rel(uo[:n0 + 1].cpu().numpy(), u[0].numpy()).max()
     ev = _rel(vo[:n1 + 1].cpu().numpy(), v[0].numpy()).max()
     zi = z[0, :-1, :-1].numpy()
@@ -302,6 +308,77 @@ def test_drop_in_call_signature():
     assert np.allclose(pred['keypoints0'][0].cpu().numpy(), g['keypoints0'])
     pred_np = {k: v[0].cpu().numpy() for k, v in pred.items()}       # what eval_homography.py:181 does
     assert pred_np['matches0'].shape == (n0,)
+
+
+def test_edge_cap_overflow_retry():
+    """gmatcher.py host loop: an edge list that does not fit makes the kernels report an EMPTY graph + the overflow bit
+    (nothing downstream walks the unwritten CSR); forward() retries with 4x the capacity until it fits and then returns
+    the same result as a roomy first attempt."""
+    from gims_b200 import Matching, _lib
+    rec, g = load_golden('fwd_n512_damped')
+    data = inputs_for(rec)
+    data['device'] = 'cuda'
+    matching = Matching({'sinkhorn_iterations': rec['iters'], 'match_threshold': rec['match_threshold']})
+    matching.gmodel.load_state_dict(weights_for(rec))
+    matching = matching.eval().to('cuda')
+    # the raw single attempt with a capacity that cannot hold the graph: status bit set, graph reported empty
+    gm = matching.gmodel
+    dev = torch.device('cuda')
+    r = gm.run_pair(data['keypoints0'][0].to(dev), data['descriptors0'][0].to(dev), data['scores0'][0].to(dev),
+                    data['keypoints1'][0].to(dev), data['descriptors1'][0].to(dev), data['scores1'][0].to(dev),
+                    data['image0'].shape, data['image1'].shape, rec['radius'], rec['percentile'], rec['min_size'],
+                    edge_cap=256)
+    torch.cuda.synchronize()
+    cnt = r['n_kept_dev'].cpu().numpy()
+    assert cnt[6] & _lib.STATUS_EDGE_OVERFLOW
+    assert cnt[0] == 0 or cnt[1] == 0
+    # the reference-facing call recovers by itself
+    gm.edge_cap_factor = 0           # -> initial capacity 1024 directed edges (the graph has several thousand)
+    with torch.no_grad():
+        pred = matching(dict(data))
+    torch.cuda.synchronize()
+    assert pred['keypoints0'].shape[1] == len(g['kept0'])
+    assert (pred['matches0'][0].cpu().numpy() == g['matches0']).mean() >= 0.999
+    assert (pred['matches1'][0].cpu().numpy() == g['matches1']).mean() >= 0.999
+
+
+def test_all_pruned_image():
+    """gmatcher.py:257-264: when AGC removes every keypoint of an image the reference returns int32 -1 matches and
+    zero scores of shape (B, 0) / (B, N1')."""
+    from gims_b200 import Matching
+    data = make_pair(200, 180, seed=611, width=2000, height=2000)     # sparse: no component reaches min_size
+    data.update({'radius': 5, 'percentile': 7, 'min_size': 50, 'device': 'cuda'})
+    matching = Matching({'sinkhorn_iterations': 10}).eval().to('cuda')
+    with torch.no_grad():
+        pred = matching(data)
+    torch.cuda.synchronize()
+    assert set(pred) == {'matches0', 'matches1', 'matching_scores0', 'matching_scores1'}
+    assert pred['matches0'].shape == (1, 0) and pred['matches0'].dtype == torch.int32
+    assert pred['matching_scores1'].shape == (1, 0) and float(pred['matching_scores1'].sum()) == 0.0
+    assert data['keypoints0'].shape == (1, 0, 2) and data['kept_kpts0_indices'] == [[]]
+
+
+def test_batch_of_two_equal_sizes():
+    """Batch > 1 works in the reference only when every item keeps the same N' (torch.stack, gmatcher.py:244-249);
+    with min_size = 1 nothing is pruned.  Each item must equal its own single call."""
+    from gims_b200 import Matching
+    cfg = {'sinkhorn_iterations': 20, 'match_threshold': 0.005}
+    matching = Matching(cfg)
+    matching.gmodel.load_state_dict(make_state_dict(0, damped=True))
+    matching = matching.eval().to('cuda')
+    items = [make_pair(300, 280, seed=620 + k, width=300, height=240) for k in range(2)]
+    knobs = {'radius': 25, 'percentile': 7, 'min_size': 1, 'device': 'cuda'}
+    batch = {k: (torch.cat([it[k] for it in items]) if torch.is_tensor(items[0][k]) else items[0][k]) for k in items[0]}
+    batch.update(knobs)
+    with torch.no_grad():
+        pb = matching(batch)
+        singles = [matching({**it, **knobs}) for it in items]
+    torch.cuda.synchronize()
+    assert pb['matches0'].shape == (2, 300) and pb['descriptors1'].shape == (2, 256, 280)
+    assert pb['mdesc0'].shape == (2, 300, 256)
+    for k, ps in enumerate(singles):
+        assert torch.equal(pb['matches0'][k], ps['matches0'][0]) and torch.equal(pb['matches1'][k], ps['matches1'][0])
+        assert torch.allclose(pb['matching_scores0'][k], ps['matching_scores0'][0], rtol=1e-4, atol=1e-6)
 
 
 def test_concurrent_callers_match_sequential():

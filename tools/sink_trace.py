@@ -18,7 +18,7 @@ trace = torch.zeros(16 * 8 + 256 * 8, dtype=torch.int64, device=dev)
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 def run():
     _lib.check(L.gims_sinkhorn_match(_lib.ptr(coup), n0, n1, _lib.ptr(nd), 100, 0.2, _lib.ptr(ws), ws.numel(), _lib.ptr(uo), _lib.ptr(vo),
-                                     _lib.ptr(i0), _lib.ptr(i1), _lib.ptr(m0), _lib.ptr(m1), _lib.ptr(s0), _lib.ptr(s1), st), 'sinkhorn')
+                                     _lib.ptr(i0), _lib.ptr(i1), _lib.ptr(m0), _lib.ptr(m1), _lib.ptr(s0), _lib.ptr(s1), None, st), 'sinkhorn')
 run(); run(); torch.cuda.synchronize()
 L.gims_debug_sinkhorn_trace(C.c_void_p(trace.data_ptr()))
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
