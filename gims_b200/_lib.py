@@ -111,7 +111,8 @@ SIGNATURES = {
     'gims_debug_sinkhorn_trace': (C.c_int, [C.c_void_p]),
     'gims_split_tf32': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]),
     'gims_sinkhorn_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int]),
-    'gims_sinkhorn_match': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_void_p,
+    'gims_couplings_ld': (C.c_int, [C.c_int]),
+    'gims_sinkhorn_match': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_float, C.c_void_p,
                                       C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'gims_sinkhorn_max_columns': (C.c_int, []),

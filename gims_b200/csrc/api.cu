@@ -338,7 +338,7 @@ size_t carve_pair(PairWs& w, void* base, size_t cap, int n0, int n1, int edge_ca
   w.sage_out = a.take<float>(rows * kD);
   w.desc = a.take<float>(rows * kD);
   w.scratch = a.take<float>(gims_attn_scratch_floats((int)rows));
-  w.couplings = a.take<float>((size_t)(n0 + 1) * (n1 + 1));
+  w.couplings = a.take<float>((size_t)(n0 + 1) * coup_ld(n1));
   w.sink_bytes = gims_sinkhorn_workspace_bytes(n0, n1);
   w.sink = a.take<char>(w.sink_bytes);
   return align_up(a.off, 256);
@@ -420,7 +420,7 @@ extern "C" int gims_forward_pair(const gims_model* m, const gims_pair_inputs* in
   // a-13 .. a-15
   float* coup = o->couplings ? o->couplings : w.couplings;
   GIMS_TRY(gims_final_scores(m, w.desc, n0, n1, o->n_kept_dev, o->mdesc, coup, w.scratch, stream));
-  GIMS_TRY(gims_sinkhorn_match(coup, n0, n1, o->n_kept_dev, m->cfg.sinkhorn_iterations, m->cfg.match_threshold, w.sink,
+  GIMS_TRY(gims_sinkhorn_match(coup, coup_ld(n1), n0, n1, o->n_kept_dev, m->cfg.sinkhorn_iterations, m->cfg.match_threshold, w.sink,
                                w.sink_bytes, o->u, o->v, o->indices[0], o->indices[1], o->matches[0], o->matches[1],
                                o->mscores[0], o->mscores[1], o->status_dev, stream));
   return GIMS_OK;

@@ -126,6 +126,8 @@ int launch_attention_tc(const QkvPlanes& pl, float* out, int n0_max, int n1_max,
                         cudaStream_t st);
 int set_attention_trace(long long* dev_buf);
 int set_gemm_trace(long long* dev_buf);
+// row pitch (floats) of the couplings matrix (n0_max+1) x (n1_max+1): rows start 16-byte aligned
+static inline int coup_ld(int n1_max) { return (n1_max + 1 + 3) & ~3; }
 static inline int attn_vbase1(int n0_max) { return (n0_max + 63) & ~63; }
 static inline int attn_ldv(int n0_max, int n1_max) { return attn_vbase1(n0_max) + ((n1_max + 63) & ~63); }
 int launch_score_gemm_tc(const float* mdesc, int n0_max, int n1_max, const int* n_dev, float* planes, float* couplings,

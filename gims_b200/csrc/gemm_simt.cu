@@ -181,7 +181,7 @@ int launch_score_gemm(const float* mdesc, int n0_max, int n1_max, const int* n_d
   g.A0 = mdesc; g.lda0 = kD; g.K0 = kD;
   g.A1 = nullptr; g.lda1 = 0; g.K1 = 0;
   g.W = mdesc; g.ldw = kD; g.bias = nullptr; g.R = nullptr; g.ldr = 0;
-  g.Y = couplings; g.ldy = n1_max + 1;
+  g.Y = couplings; g.ldy = coup_ld(n1_max);
   g.N = n1_max; g.relu = 0; g.scale = 0.0625f;    // 1/sqrt(256), exact
   g.segs.base[0] = 0; g.segs.base[1] = n0_max; g.segs.nmax[0] = n0_max; g.segs.nmax[1] = n1_max;
   g.segs.n_dev = n_dev; g.segs.nseg = 2;
@@ -197,7 +197,7 @@ int launch_score_border(int n0_max, int n1_max, const int* n_dev, const float* b
   Segs s;
   s.base[0] = 0; s.base[1] = n0_max; s.nmax[0] = n0_max; s.nmax[1] = n1_max; s.n_dev = n_dev; s.nseg = 2;
   int m = (n0_max > n1_max ? n0_max : n1_max) + 1;
-  k_score_border<<<cdiv(m, 256), 256, 0, st>>>(couplings, n1_max + 1, s, bin_score);
+  k_score_border<<<cdiv(m, 256), 256, 0, st>>>(couplings, coup_ld(n1_max), s, bin_score);
   GIMS_LAUNCH_OK();
   return GIMS_OK;
 }

@@ -97,7 +97,7 @@ struct TcArgs {
   int N;                         // live output columns (score mode: from n_dev[1])
   int relu;
   float scale;                   // score mode
-  int score;                     // 1: Y is the couplings matrix (row-major, ldy = n1_max+1), W rows = image-1 rows
+  int score;                     // 1: Y is the couplings matrix (row-major, ldy = coup_ld(n1_max)), W rows = image-1 rows
   Segs segs;
   int tiles0;
   // qkv mode (N = 768): instead of Y the epilogue writes the tf32 planes the attention kernel consumes:
@@ -533,7 +533,7 @@ int launch_score_gemm_tc(const float* mdesc, int n0_max, int n1_max, const int* 
   GIMS_TRY(tc::make_tmap_f32_k32(&mWh, hi, rows, kD, kD, bn));
   GIMS_TRY(tc::make_tmap_f32_k32(&mWl, lo, rows, kD, kD, bn));
   TcArgs g;
-  g.K0 = kD; g.K1 = 0; g.bias = nullptr; g.R = nullptr; g.ldr = 0; g.Y = couplings; g.ldy = n1_max + 1; g.N = n1_max;
+  g.K0 = kD; g.K1 = 0; g.bias = nullptr; g.R = nullptr; g.ldr = 0; g.Y = couplings; g.ldy = coup_ld(n1_max); g.N = n1_max;
   g.relu = 0; g.scale = 0.0625f; g.score = 1;
   g.qkv = 0; g.qp = g.kp = g.vt = nullptr; g.ldv = 0; g.rows_total = (int)rows; g.vbase1 = 0;
   g.segs.base[0] = 0; g.segs.base[1] = n0_max; g.segs.nmax[0] = n0_max; g.segs.nmax[1] = n1_max; g.segs.n_dev = n_dev;

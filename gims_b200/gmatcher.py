@@ -323,7 +323,8 @@ class GMatcher(nn.Module):
             out['mscores%d' % s] = torch.empty(ns[s], **f32)
             out['indices%d' % s] = torch.empty(ns[s], **i32)
         if debug:
-            out['couplings'] = torch.empty(n0 + 1, n1 + 1, **f32)
+            out['couplings_buf'] = torch.empty(n0 + 1, L.gims_couplings_ld(n1), **f32)      # pitch of the C ABI
+            out['couplings'] = out['couplings_buf'][:, :n1 + 1]
             out['desc_gnn'] = torch.empty(n0 + n1, d, **f32)
             out['desc_in'] = torch.empty(n0 + n1, d, **f32)
         pin = _lib.PairInputs()
@@ -360,7 +361,7 @@ class GMatcher(nn.Module):
             po.indices[s] = out['indices%d' % s].data_ptr()
         po.mdesc = out['mdesc'].data_ptr()
         po.u, po.v = out['u'].data_ptr(), out['v'].data_ptr()
-        po.couplings = out['couplings'].data_ptr() if debug else None
+        po.couplings = out['couplings_buf'].data_ptr() if debug else None
         po.desc_gnn = out['desc_gnn'].data_ptr() if debug else None
         po.desc_in = out['desc_in'].data_ptr() if debug else None
         st = stream if stream is not None else torch.cuda.current_stream(dev)

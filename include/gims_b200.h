@@ -169,15 +169,19 @@ GIMS_API int gims_attn_layer_forward(const gims_model* m, int layer, float* desc
                             float* scratch, void* stream);
 
 /* ---- a-13: final_proj + score matrix (gmatcher.py:273-275) ----------------------------------
- * mdesc [rows][256] = final_proj(desc); couplings (n0_max+1) x ld, ld = n1_max+1:
+ * mdesc [rows][256] = final_proj(desc); couplings (n0_max+1) x ld, ld = gims_couplings_ld(n1_max) (n1_max+1 rounded up
+ * to a multiple of 4, so that every row starts 16-byte aligned):
  *   Z0[i][j] = <mdesc0_i, mdesc1_j>/16 for i<N0', j<N1'; bin_score on row N0' and column N1'
  *   (the torch.cat of gmatcher.py:59-60).  scratch: 2*(n0_max+n1_max)*256 floats (tf32 planes of mdesc for the
  *   tensor-core score GEMM) or NULL (CUDA-core score GEMM). */
+GIMS_API int gims_couplings_ld(int n1_max);
 GIMS_API int gims_final_scores(const gims_model* m, const float* desc, int n0_max, int n1_max, const int* n_dev,
                       float* mdesc, float* couplings, float* scratch, void* stream);
 
 /* ---- a-14 + a-15: log-domain Sinkhorn + mutual-NN matches (gmatcher.py:41-69, 284-294) ------
- * couplings as written by gims_final_scores.  Outputs (capacities n0_max / n1_max):
+ * couplings as written by gims_final_scores, row pitch `ld` floats (>= n1_max+1; the fast kernels for more than 2048
+ * keypoints need ld == gims_couplings_ld(n1_max) and a 16-byte aligned base, anything else runs the exact kernel).
+ * Outputs (capacities n0_max / n1_max):
  *   u [n0_max+1], v [n1_max+1]  final potentials (log_sinkhorn_iterations' u, v)
  *   indices0/1 int32  pre-threshold row/column argmax (gmatcher.py:284-285)
  *   matches0/1 int64 (-1 = unmatched), mscores0/1 fp32 (gmatcher.py:286-294)
@@ -186,7 +190,7 @@ GIMS_API int gims_final_scores(const gims_model* m, const float* desc, int n0_ma
  * (gims_sinkhorn_max_columns()). */
 GIMS_API int gims_sinkhorn_max_columns(void);
 GIMS_API size_t gims_sinkhorn_workspace_bytes(int n0_max, int n1_max);
-GIMS_API int gims_sinkhorn_match(const float* couplings, int n0_max, int n1_max, const int* n_dev, int iters,
+GIMS_API int gims_sinkhorn_match(const float* couplings, int ld, int n0_max, int n1_max, const int* n_dev, int iters,
                         float match_threshold, void* workspace, size_t workspace_bytes,
                         float* u, float* v, int* indices0, int* indices1,
                         int64_t* matches0, int64_t* matches1, float* mscores0, float* mscores1,
@@ -223,7 +227,7 @@ typedef struct {
   int*     indices[2];           /* [n]  pre-threshold argmax */
   float*   u;                    /* [n0+1] */
   float*   v;                    /* [n1+1] */
-  float*   couplings;            /* optional (may be NULL -> internal): (n0+1) x (n1+1) */
+  float*   couplings;            /* optional (may be NULL -> internal): (n0+1) x gims_couplings_ld(n1) */
   float*   desc_gnn;             /* optional: [(n0+n1)][256] descriptors after the attention stack */
   float*   desc_in;              /* optional: [(n0+n1)][256] SAGE + kenc (input of the attention stack) */
   unsigned* status_dev;          /* [1] GIMS_STATUS_* bits */

@@ -32,7 +32,7 @@ def _run_pair(model, data, debug=True):
                        data.get('min_size', 8), debug=debug)
     torch.cuda.synchronize()
     cnt = r['n_kept_dev'].cpu().numpy()
-    assert cnt[6] == 0, 'edge capacity overflow'
+    assert cnt[6] & 0xff == 0, 'error status %#x' % cnt[6]
     return r, cnt
 
 
@@ -123,6 +123,23 @@ def _rel(a, b):
     return np.abs(a - b) / np.maximum(1.0, np.abs(b))
 
 
+def _sinkhorn_f64(coup, iters):
+    """The reference's iteration (gmatcher.py:41-69) in float64 on the GPU, on OUR couplings: the exact-arithmetic
+    yardstick for the potentials."""
+    z = coup.double()
+    n0, n1 = z.shape[0] - 1, z.shape[1] - 1
+    norm = -np.log(n0 + n1)
+    lmu = torch.full((n0 + 1,), norm, dtype=torch.float64, device=z.device)
+    lnu = torch.full((n1 + 1,), norm, dtype=torch.float64, device=z.device)
+    lmu[-1] = np.log(n1) + norm
+    lnu[-1] = np.log(n0) + norm
+    u, v = torch.zeros_like(lmu), torch.zeros_like(lnu)
+    for _ in range(iters):
+        u = lmu - torch.logsumexp(z + v[None, :], 1)
+        v = lnu - torch.logsumexp(z + u[:, None], 0)
+    return u.cpu().numpy(), v.cpu().numpy()
+
+
 def _check_forward(rec, data, sd, cfg, ref, label):
     """ref: dict with the reference/oracle values (full or sub-sampled)."""
     model = _model(sd, cfg)
@@ -141,8 +158,19 @@ def _check_forward(rec, data, sd, cfg, ref, label):
     e_sc = _rel(scores[:sub[0], :sub[1]], ref['scores_sub']).max()
     msgs.append('scores %.2e' % e_sc)
     u, v = r['u'].cpu().numpy()[:n0 + 1], r['v'].cpu().numpy()[:n1 + 1]
-    e_u, e_v = _rel(u, ref['u']).max(), _rel(v, ref['v']).max()
-    msgs.append('u %.2e v %.2e' % (e_u, e_v))
+    # Potentials.  u and v are individually ill-conditioned: shifting every u_r by +c and every v_j by -c is a
+    # neutrally stable mode of the iteration (only u_r + v_j, i.e. Z, is well determined), so fp32 rounding drifts
+    # along it — the reference's own fp32 potentials deviate from a float64 run of the same iteration by up to
+    # ~6e-4 when the scores sit near 90.  Bars: (1) ours within 1e-4 * max(1, |.|) of the float64 iteration on our
+    # couplings; (2) ours within 1e-4 * max(1, |.|) + (the reference's own distance from that float64 run) of the reference.
+    u64, v64 = _sinkhorn_f64(r['couplings'][:n0 + 1, :n1 + 1], cfg['sinkhorn_iterations'])
+    e_u64, e_v64 = _rel(u, u64).max(), _rel(v, v64).max()
+    ref_u64, ref_v64 = np.abs(ref['u'] - u64).max(), np.abs(ref['v'] - v64).max()
+    e_u = (np.maximum(np.abs(u - ref['u']) - ref_u64, 0) / np.maximum(1.0, np.abs(ref['u']))).max()
+    e_v = (np.maximum(np.abs(v - ref['v']) - ref_v64, 0) / np.maximum(1.0, np.abs(ref['v']))).max()
+    msgs.append('u,v vs f64 %.2e %.2e; vs reference raw %.2e %.2e (reference vs f64: %.2e %.2e abs)' %
+                (e_u64, e_v64, _rel(u, ref['u']).max(), _rel(v, ref['v']).max(), ref_u64, ref_v64))
+    assert e_u64 <= 1e-4 and e_v64 <= 1e-4, msgs
     # Z of ours from our own potentials (the fused kernel never materialises it)
     norm = -np.log(np.float32(n0 + n1))
     z_ours = (coup[:n0 + 1, :n1 + 1] + u[:, None]) + v[None, :] - norm
@@ -224,24 +252,30 @@ def test_forward_stages_vs_oracle():
         assert err <= 2e-5
 
 
-@pytest.mark.parametrize('n0,n1,iters,scale', [(1, 1, 3, 1.0), (5, 9, 100, 1.0), (300, 257, 20, 5.0), (2048, 2048, 100, 1.0),
-                                                (1000, 3100, 10, 30.0), (4500, 4000, 4, 1.0), (4500, 4000, 100, 3.0),
-                                                (8200, 8100, 30, 1.0)])
-def test_sinkhorn_vs_oracle(n0, n1, iters, scale):
-    """a-14/a-15 alone on random couplings: resident (smem slab) and streamed regimes, ragged, tiny."""
+@pytest.mark.parametrize('n0,n1,iters,scale,aligned,offset', [
+    (1, 1, 3, 1.0, True, 0.0), (5, 9, 100, 1.0, True, 0.0), (300, 257, 20, 5.0, True, 0.0), (2048, 2048, 100, 1.0, True, 0.0),
+    (2048, 2040, 100, 2.6, True, 90.0),       # trained-like: scores ~ 90 +- 2.6 against a dustbin score of 0.7
+    (1000, 3100, 10, 30.0, True, 0.0), (4500, 4000, 4, 1.0, True, 0.0), (4500, 4000, 100, 3.0, True, 90.0),
+    (8200, 8100, 30, 1.0, True, 0.0),
+    (3000, 2500, 10, 2.0, False, 50.0),       # unaligned pitch: the exact kernel
+    (700, 650, 30, 60.0, True, 0.0),          # very spread scores
+])
+def test_sinkhorn_vs_oracle(n0, n1, iters, scale, aligned, offset):
+    """a-14/a-15 alone on random couplings: register-resident, streamed (L2 / HBM) and exact kernels, ragged, tiny."""
     import ctypes as C
     from gims_b200 import _lib
     from oracle import gims_oracle as orc
     L = _lib.lib()
     g = torch.Generator().manual_seed(n0 * 7 + n1)
-    scores = torch.randn(1, n0, n1, generator=g) * scale
+    scores = torch.randn(1, n0, n1, generator=g) * scale + offset
     alpha = torch.tensor(0.7)
     z, u, v, coup = orc.log_optimal_transport(scores, alpha, iters)
     m = orc.extract_matches(z, 0.0)
     dev = torch.device('cuda')
     # exercise device-side counts: allocate for larger maxima than the live sizes
     n0m, n1m = n0 + 3, n1 + 5
-    cbuf = torch.zeros(n0m + 1, n1m + 1, device=dev)
+    ld = L.gims_couplings_ld(n1m) if aligned else n1m + 1
+    cbuf = torch.zeros(n0m + 1, ld, device=dev)
     cbuf[:n0 + 1, :n1 + 1] = coup[0].to(dev)
     cbuf = cbuf.contiguous()
     nd = torch.tensor([n0, n1], dtype=torch.int32, device=dev)
@@ -251,7 +285,7 @@ def test_sinkhorn_vs_oracle(n0, n1, iters, scale):
     m0, m1 = torch.zeros(n0m, dtype=torch.int64, device=dev), torch.zeros(n1m, dtype=torch.int64, device=dev)
     s0, s1 = torch.zeros(n0m, device=dev), torch.zeros(n1m, device=dev)
     status = torch.zeros(1, dtype=torch.int32, device=dev)
-    _lib.check(L.gims_sinkhorn_match(_lib.ptr(cbuf), n0m, n1m, _lib.ptr(nd), iters, 0.0, _lib.ptr(ws), ws.numel(),
+    _lib.check(L.gims_sinkhorn_match(_lib.ptr(cbuf), ld, n0m, n1m, _lib.ptr(nd), iters, 0.0, _lib.ptr(ws), ws.numel(),
                                      _lib.ptr(uo), _lib.ptr(vo), _lib.ptr(i0), _lib.ptr(i1), _lib.ptr(m0), _lib.ptr(m1),
                                      _lib.ptr(s0), _lib.ptr(s1), _lib.ptr(status),
                                      C.c_void_p(torch.cuda.current_stream().cuda_stream)),
@@ -277,8 +311,8 @@ def test_sinkhorn_vs_oracle(n0, n1, iters, scale):
     keep = np.ones(n0, dtype=bool)
     keep[flip] = False
     ems = np.abs(ours_ms - ref_ms)[keep].max() if keep.any() else 0.0
-    print('\n[sinkhorn %dx%d it=%d] du %.2e dv %.2e agree %.4f/%.4f dms %.2e tie-flips %d' %
-          (n0, n1, iters, eu, ev, a0, a1, ems, len(flip)))
+    print('\n[sinkhorn %dx%d it=%d status %#x] du %.2e dv %.2e agree %.4f/%.4f dms %.2e tie-flips %d' %
+          (n0, n1, iters, st_word, eu, ev, a0, a1, ems, len(flip)))
     assert eu <= 1e-4 and ev <= 1e-4
     assert a0 >= 0.999 and a1 >= 0.999
     assert len(flip) <= max(2, n0 // 200)
@@ -350,7 +384,7 @@ def test_all_pruned_image():
     data.update({'radius': 5, 'percentile': 7, 'min_size': 50, 'device': 'cuda'})
     matching = Matching({'sinkhorn_iterations': 10}).eval().to('cuda')
     with torch.no_grad():
-        pred = matching(data)
+        pred = matching.gmodel(data)      # GMatcher mutates ITS argument (Matching passes it a copy, matching.py:25)
     torch.cuda.synchronize()
     assert set(pred) == {'matches0', 'matches1', 'matching_scores0', 'matching_scores1'}
     assert pred['matches0'].shape == (1, 0) and pred['matches0'].dtype == torch.int32

@@ -1,4 +1,5 @@
-"""Timeline of CTA 0 of k_sinkhorn (gims_debug_sinkhorn_trace) on a 2048x2048 problem."""
+"""Timeline of CTA 0 of the Sinkhorn kernel (gims_debug_sinkhorn_trace): `python tools/sink_trace.py [n] [offset]`
+(n keypoints per image, default 2048; offset = mean score, 90 mimics trained weights)."""
 import ctypes as C
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
@@ -6,8 +7,12 @@ import torch
 from gims_b200 import _lib
 L = _lib.lib()
 dev = torch.device('cuda')
-n0 = n1 = 2048
-coup = torch.randn(n0 + 1, n1 + 1, device=dev)
+n0 = n1 = int(sys.argv[1]) if len(sys.argv) > 1 else 2048
+offset = float(sys.argv[2]) if len(sys.argv) > 2 else 0.0
+ld = L.gims_couplings_ld(n1)
+coup = torch.randn(n0 + 1, ld, device=dev) * 2.6 + offset
+coup[n0, :] = 1.0
+coup[:, n1] = 1.0
 nd = torch.tensor([n0, n1], dtype=torch.int32, device=dev)
 ws = torch.empty(L.gims_sinkhorn_workspace_bytes(n0, n1), dtype=torch.uint8, device=dev)
 uo, vo = torch.zeros(n0 + 1, device=dev), torch.zeros(n1 + 1, device=dev)
@@ -17,7 +22,7 @@ s0, s1 = torch.zeros(n0, device=dev), torch.zeros(n1, device=dev)
 trace = torch.zeros(16 * 8 + 256 * 8, dtype=torch.int64, device=dev)
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 def run():
-    _lib.check(L.gims_sinkhorn_match(_lib.ptr(coup), n0, n1, _lib.ptr(nd), 100, 0.2, _lib.ptr(ws), ws.numel(), _lib.ptr(uo), _lib.ptr(vo),
+    _lib.check(L.gims_sinkhorn_match(_lib.ptr(coup), ld, n0, n1, _lib.ptr(nd), 100, 0.2, _lib.ptr(ws), ws.numel(), _lib.ptr(uo), _lib.ptr(vo),
                                      _lib.ptr(i0), _lib.ptr(i1), _lib.ptr(m0), _lib.ptr(m1), _lib.ptr(s0), _lib.ptr(s1), None, st), 'sinkhorn')
 run(); run(); torch.cuda.synchronize()
 L.gims_debug_sinkhorn_trace(C.c_void_p(trace.data_ptr()))
