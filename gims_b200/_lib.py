@@ -15,7 +15,9 @@ STATUS_SINKHORN_TIMEOUT = 2
 STATUS_ERROR_MASK = 0xff
 STATUS_SINKHORN_FAST = 0x100
 STATUS_SINKHORN_EXACT = 0x200
-GEMM_SIMT, GEMM_TC = 0, 1
+GEMM_SIMT, GEMM_TC, GEMM_TC_F16, GEMM_BF16 = 0, 1, 2, 3
+GEMM_MODES = {'simt': GEMM_SIMT, 'tf32': GEMM_TC, 'tc': GEMM_TC, 'f16': GEMM_TC_F16, 'bf16': GEMM_BF16}
+STATUS_FP16_RANGE = 4
 PROF = {'gemm': 1, 'attention': 2, 'sinkhorn': 3, 'score': 4, 'cosine': 5, 'sage_gather': 6}
 
 
@@ -48,6 +50,7 @@ class PairInputs(C.Structure):
         ('k_rank', C.c_longlong * 2),
         ('min_size', C.c_int),
         ('edge_cap', C.c_int),
+        ('gemm_mode', C.c_int),
     ]
 
 
@@ -98,7 +101,7 @@ SIGNATURES = {
                                     C.c_void_p, C.c_void_p, C.c_void_p]),
     'gims_attn_scratch_floats': (C.c_size_t, [C.c_int]),
     'gims_attn_layer_forward': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
-                                          C.c_void_p]),
+                                          C.c_void_p, C.c_void_p]),
     'gims_final_scores': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_void_p, C.c_void_p]),
     'gims_set_gemm_mode': (C.c_int, [C.c_int]),
@@ -140,7 +143,7 @@ def lib():
         fn.argtypes = args
     mode = os.environ.get('GIMS_GEMM_MODE')
     if mode:
-        handle.gims_set_gemm_mode(GEMM_SIMT if mode.lower() == 'simt' else GEMM_TC)
+        handle.gims_set_gemm_mode(GEMM_MODES[mode.lower()])
     _LIB = handle
     return _LIB
 

@@ -134,14 +134,14 @@ struct gims_model {
   const float* bfinal;
 };
 
-static std::atomic<int> g_gemm_mode{GIMS_GEMM_TC};
+static std::atomic<int> g_gemm_mode{GIMS_GEMM_TC_F16};
 
 extern "C" int gims_version(void) { return 100; }
 extern "C" const char* gims_last_error(void) { return g_err; }
 extern "C" long long gims_launch_count(void) { return g_launches.load(); }
 
 extern "C" int gims_set_gemm_mode(int mode) {
-  if (mode != GIMS_GEMM_SIMT && mode != GIMS_GEMM_TC) { set_error("gims_set_gemm_mode: bad mode %d", mode); return GIMS_ERR_ARG; }
+  if (mode < GIMS_GEMM_SIMT || mode > GIMS_GEMM_BF16) { set_error("gims_set_gemm_mode: bad mode %d", mode); return GIMS_ERR_ARG; }
   g_gemm_mode.store(mode);
   return GIMS_OK;
 }
@@ -193,19 +193,18 @@ static Segs two_segs(int n0_max, int n1_max, const int* n_dev) {
 
 // Y = epi(A W^T + bias): tcgen05 3xTF32 kernel when the shape allows and the mode asks for it, else fp32 SIMT.
 static int gemm(const float* A0, int lda0, int K0, const float* A1, int lda1, int K1, const Wt& W, const float* bias,
-                const float* R, int ldr, float* Y, int ldy, int N, int relu, Segs s, cudaStream_t st) {
+                const float* R, int ldr, float* Y, int ldy, int N, int relu, Segs s, int mode, cudaStream_t st) {
   GemmArgs g;
   g.A0 = A0; g.lda0 = lda0; g.K0 = K0; g.A1 = A1; g.lda1 = lda1; g.K1 = K1; g.W = W.w; g.bias = bias;
   g.R = R; g.ldr = ldr; g.Y = Y; g.ldy = ldy; g.N = N; g.relu = relu; g.segs = s;
   bool tc_ok = W.hi && W.lo && K0 % 32 == 0 && K1 % 32 == 0 && N % 32 == 0 && lda0 % 4 == 0 && (K1 == 0 || lda1 % 4 == 0);
-  if (g_gemm_mode.load() == GIMS_GEMM_TC && tc_ok) return launch_gemm_tc(g, W.hi, W.lo, st);
+  if (mode != GIMS_GEMM_SIMT && tc_ok) return launch_gemm_tc(g, W.hi, W.lo, st);
   return launch_gemm(g, st);
 }
 
 // a-9 ------------------------------------------------------------------------------------------
-extern "C" int gims_sage_forward(const gims_model* m, const float* feat, const int* indptr, const int* indices,
-                                 int n_max, const int* n_dev, float* out, float* scratch, void* stream) {
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+static int sage_fwd(const gims_model* m, const float* feat, const int* indptr, const int* indices, int n_max,
+                    const int* n_dev, float* out, float* scratch, int mode, cudaStream_t st) {
   if (!m || n_max < 1) { set_error("gims_sage_forward: bad arguments"); return GIMS_ERR_ARG; }
   const int H = kD / 2;
   float* y0 = scratch;                          // [n][256]  = feat @ [Wn0; Ws0]^T
@@ -214,21 +213,24 @@ extern "C" int gims_sage_forward(const gims_model* m, const float* feat, const i
   float* h2 = agg + (size_t)n_max * H;          // [n][128]   (total 2.5 * n * 256 floats)
   Segs s = one_seg(n_max, n_dev);
   // layer 0 (256 -> 128, fc_neigh before aggregation)
-  GIMS_TRY(gemm(feat, kD, kD, nullptr, 0, 0, m->sage_w[0], nullptr, nullptr, 0, y0, kD, kD, 0, s, st));
+  GIMS_TRY(gemm(feat, kD, kD, nullptr, 0, 0, m->sage_w[0], nullptr, nullptr, 0, y0, kD, kD, 0, s, mode, st));
   GIMS_TRY(launch_sage_aggregate(y0, kD, H, indptr, indices, n_max, n_dev, y0 + H, kD, m->sage_b[0], 1, h1, H, st));
   // layer 1 (128 -> 128, aggregate then fc_neigh)
   GIMS_TRY(launch_sage_aggregate(h1, H, H, indptr, indices, n_max, n_dev, nullptr, 0, nullptr, 0, agg, H, st));
-  GIMS_TRY(gemm(h1, H, H, agg, H, H, m->sage_w[1], m->sage_b[1], nullptr, 0, h2, H, H, 1, s, st));
+  GIMS_TRY(gemm(h1, H, H, agg, H, H, m->sage_w[1], m->sage_b[1], nullptr, 0, h2, H, H, 1, s, mode, st));
   // layer 2 (128 -> 256)
   GIMS_TRY(launch_sage_aggregate(h2, H, H, indptr, indices, n_max, n_dev, nullptr, 0, nullptr, 0, agg, H, st));
-  GIMS_TRY(gemm(h2, H, H, agg, H, H, m->sage_w[2], m->sage_b[2], nullptr, 0, out, kD, kD, 0, s, st));
+  GIMS_TRY(gemm(h2, H, H, agg, H, H, m->sage_w[2], m->sage_b[2], nullptr, 0, out, kD, kD, 0, s, mode, st));
   return GIMS_OK;
+}
+extern "C" int gims_sage_forward(const gims_model* m, const float* feat, const int* indptr, const int* indices,
+                                 int n_max, const int* n_dev, float* out, float* scratch, void* stream) {
+  return sage_fwd(m, feat, indptr, indices, n_max, n_dev, out, scratch, g_gemm_mode.load(), static_cast<cudaStream_t>(stream));
 }
 
 // a-8 + a-10 -----------------------------------------------------------------------------------
-extern "C" int gims_kenc_forward(const gims_model* m, const float* kpts, int n_max, const int* n_dev, float img_w,
-                                 float img_h, const float* add, float* desc, float* scratch, void* stream) {
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+static int kenc_fwd(const gims_model* m, const float* kpts, int n_max, const int* n_dev, float img_w, float img_h,
+                    const float* add, float* desc, float* scratch, int mode, cudaStream_t st) {
   if (!m || n_max < 1) { set_error("gims_kenc_forward: bad arguments"); return GIMS_ERR_ARG; }
   const gims_config& c = m->cfg;
   float* buf[2] = {scratch, scratch + (size_t)n_max * kD};
@@ -240,19 +242,22 @@ extern "C" int gims_kenc_forward(const gims_model* m, const float* kpts, int n_m
     bool last = (i == c.kenc_num - 1);
     float* y = last ? desc : buf[cur ^ 1];
     GIMS_TRY(gemm(buf[cur], cin, cin, nullptr, 0, 0, m->kenc_w[i], m->kenc_b[i], last ? add : nullptr, kD, y,
-                              last ? kD : cout, cout, last ? 0 : 1, s, st));
+                              last ? kD : cout, cout, last ? 0 : 1, s, mode, st));
     cur ^= 1;
   }
   return GIMS_OK;
+}
+extern "C" int gims_kenc_forward(const gims_model* m, const float* kpts, int n_max, const int* n_dev, float img_w,
+                                 float img_h, const float* add, float* desc, float* scratch, void* stream) {
+  return kenc_fwd(m, kpts, n_max, n_dev, img_w, img_h, add, desc, scratch, g_gemm_mode.load(), static_cast<cudaStream_t>(stream));
 }
 
 // a-11 + a-12 ----------------------------------------------------------------------------------
 // qkv (or its tf32 planes: 6 * rows * 256 + padding of the transposed V rows) | att | msg | hid
 extern "C" size_t gims_attn_scratch_floats(int rows) { return (size_t)rows * (6 * kD + kD + kD + 2 * kD) + 2 * 128 * kD; }
 
-extern "C" int gims_attn_layer_forward(const gims_model* m, int layer, float* desc, int n0_max, int n1_max,
-                                       const int* n_dev, float* scratch, void* stream) {
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+static int attn_layer(const gims_model* m, int layer, float* desc, int n0_max, int n1_max, const int* n_dev,
+                      float* scratch, unsigned* status_dev, int mode, cudaStream_t st) {
   if (!m || layer < 0 || layer >= m->cfg.num_layers) { set_error("gims_attn_layer_forward: bad layer %d", layer); return GIMS_ERR_ARG; }
   size_t rows = (size_t)n0_max + n1_max;
   int ldv = attn_ldv(n0_max, n1_max);      // <= rows + 126
@@ -261,39 +266,50 @@ extern "C" int gims_attn_layer_forward(const gims_model* m, int layer, float* de
   float* msg = att + rows * kD;            // [rows][256]
   float* hid = msg + rows * kD;            // [rows][512]
   Segs s = two_segs(n0_max, n1_max, n_dev);
-  if (g_gemm_mode.load() == GIMS_GEMM_TC) {
+  if (mode != GIMS_GEMM_SIMT) {
     QkvPlanes pl;
-    pl.qp = qkv; pl.kp = pl.qp + 2 * rows * kD; pl.vt = pl.kp + 2 * rows * kD; pl.ldv = ldv;
+    pl.qp = qkv; pl.kp = pl.qp + 2 * rows * kD; pl.vt = static_cast<float*>(pl.kp) + 2 * rows * kD; pl.ldv = ldv;
     pl.vbase1 = attn_vbase1(n0_max);
+    pl.fmt = mode == GIMS_GEMM_TC_F16 ? 0 : (mode == GIMS_GEMM_BF16 ? 1 : -1);
+    pl.planes = mode == GIMS_GEMM_BF16 ? 1 : 2;
+    pl.status = status_dev;
     GemmArgs g;
     g.A0 = desc; g.lda0 = kD; g.K0 = kD; g.A1 = nullptr; g.lda1 = 0; g.K1 = 0; g.W = m->wqkv[layer].w;
     g.bias = m->bqkv[layer]; g.R = nullptr; g.ldr = 0; g.Y = nullptr; g.ldy = 0; g.N = 3 * kD; g.relu = 0; g.segs = s;
     GIMS_TRY(launch_gemm_tc(g, m->wqkv[layer].hi, m->wqkv[layer].lo, st, &pl));
-    GIMS_TRY(launch_attention_tc(pl, att, n0_max, n1_max, n_dev, m->cfg.layer_is_cross[layer], st));
+    if (pl.fmt >= 0) GIMS_TRY(launch_attention_f16(pl, att, n0_max, n1_max, n_dev, m->cfg.layer_is_cross[layer], st));
+    else             GIMS_TRY(launch_attention_tc(pl, att, n0_max, n1_max, n_dev, m->cfg.layer_is_cross[layer], st));
   } else {
-    GIMS_TRY(gemm(desc, kD, kD, nullptr, 0, 0, m->wqkv[layer], m->bqkv[layer], nullptr, 0, qkv, 3 * kD, 3 * kD, 0, s, st));
+    GIMS_TRY(gemm(desc, kD, kD, nullptr, 0, 0, m->wqkv[layer], m->bqkv[layer], nullptr, 0, qkv, 3 * kD, 3 * kD, 0, s, mode, st));
     GIMS_TRY(launch_attention(qkv, att, n0_max, n1_max, n_dev, m->cfg.layer_is_cross[layer], st));
   }
   (void)msg;   // the merge conv is composed into W1 at pack time
-  GIMS_TRY(gemm(desc, kD, kD, att, kD, kD, m->w1[layer], m->b1[layer], nullptr, 0, hid, 2 * kD, 2 * kD, 1, s, st));
-  GIMS_TRY(gemm(hid, 2 * kD, 2 * kD, nullptr, 0, 0, m->w2[layer], m->b2[layer], desc, kD, desc, kD, kD, 0, s, st));
+  GIMS_TRY(gemm(desc, kD, kD, att, kD, kD, m->w1[layer], m->b1[layer], nullptr, 0, hid, 2 * kD, 2 * kD, 1, s, mode, st));
+  GIMS_TRY(gemm(hid, 2 * kD, 2 * kD, nullptr, 0, 0, m->w2[layer], m->b2[layer], desc, kD, desc, kD, kD, 0, s, mode, st));
   return GIMS_OK;
+}
+extern "C" int gims_attn_layer_forward(const gims_model* m, int layer, float* desc, int n0_max, int n1_max,
+                                       const int* n_dev, float* scratch, unsigned* status_dev, void* stream) {
+  return attn_layer(m, layer, desc, n0_max, n1_max, n_dev, scratch, status_dev, g_gemm_mode.load(), static_cast<cudaStream_t>(stream));
 }
 
 // a-13 -----------------------------------------------------------------------------------------
-extern "C" int gims_final_scores(const gims_model* m, const float* desc, int n0_max, int n1_max, const int* n_dev,
-                                 float* mdesc, float* couplings, float* scratch, void* stream) {
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
+static int final_scores(const gims_model* m, const float* desc, int n0_max, int n1_max, const int* n_dev, float* mdesc,
+                        float* couplings, float* scratch, int mode, cudaStream_t st) {
   if (!m) { set_error("gims_final_scores: null model"); return GIMS_ERR_ARG; }
   Segs s = two_segs(n0_max, n1_max, n_dev);
-  GIMS_TRY(gemm(desc, kD, kD, nullptr, 0, 0, m->wfinal, m->bfinal, nullptr, 0, mdesc, kD, kD, 0, s, st));
-  if (g_gemm_mode.load() == GIMS_GEMM_TC && scratch) {
+  GIMS_TRY(gemm(desc, kD, kD, nullptr, 0, 0, m->wfinal, m->bfinal, nullptr, 0, mdesc, kD, kD, 0, s, mode, st));
+  if (mode != GIMS_GEMM_SIMT && scratch) {
     GIMS_TRY(launch_score_gemm_tc(mdesc, n0_max, n1_max, n_dev, scratch, couplings, st));
     GIMS_TRY(launch_score_border(n0_max, n1_max, n_dev, m->bin_score, couplings, st));
   } else {
     GIMS_TRY(launch_score_gemm(mdesc, n0_max, n1_max, n_dev, m->bin_score, couplings, st));
   }
   return GIMS_OK;
+}
+extern "C" int gims_final_scores(const gims_model* m, const float* desc, int n0_max, int n1_max, const int* n_dev,
+                                 float* mdesc, float* couplings, float* scratch, void* stream) {
+  return final_scores(m, desc, n0_max, n1_max, n_dev, mdesc, couplings, scratch, g_gemm_mode.load(), static_cast<cudaStream_t>(stream));
 }
 
 // test / bring-up entry points ----------------------------------------------------------------
@@ -390,6 +406,8 @@ extern "C" int gims_forward_pair(const gims_model* m, const gims_pair_inputs* in
   size_t need = carve_pair(w, workspace, workspace_bytes, n0, n1, in->edge_cap);
   if (need > workspace_bytes) { set_error("gims_forward_pair: workspace %zu < %zu", workspace_bytes, need); return GIMS_ERR_WORKSPACE; }
   size_t rows = (size_t)n0 + n1;
+  const int mode = in->gemm_mode > 0 ? in->gemm_mode - 1 : g_gemm_mode.load();
+  if (mode < GIMS_GEMM_SIMT || mode > GIMS_GEMM_BF16) { set_error("gims_forward_pair: gemm_mode %d", in->gemm_mode); return GIMS_ERR_ARG; }
   GIMS_CUDA_OK(cudaMemsetAsync(o->status_dev, 0, sizeof(unsigned), st));
   // a-1 .. a-7: graphs + pruning, both images (gmatcher.py:233-252)
   for (int s = 0; s < 2; ++s) {
@@ -401,10 +419,10 @@ extern "C" int gims_forward_pair(const gims_model* m, const gims_pair_inputs* in
   // a-9, a-8, a-10: desc = SAGE(feat) + kenc(normalize(kpts))   (gmatcher.py:265-271)
   for (int s = 0; s < 2; ++s) {
     size_t base = s ? (size_t)n0 : 0;
-    GIMS_TRY(gims_sage_forward(m, o->feat[s], o->csr_indptr[s], o->csr_indices[s], in->n[s], o->n_kept_dev + s,
-                               w.sage_out + base * kD, w.scratch, stream));
-    GIMS_TRY(gims_kenc_forward(m, o->kpts[s], in->n[s], o->n_kept_dev + s, in->img_w[s], in->img_h[s],
-                               w.sage_out + base * kD, w.desc + base * kD, w.scratch, stream));
+    GIMS_TRY(sage_fwd(m, o->feat[s], o->csr_indptr[s], o->csr_indices[s], in->n[s], o->n_kept_dev + s,
+                      w.sage_out + base * kD, w.scratch, mode, st));
+    GIMS_TRY(kenc_fwd(m, o->kpts[s], in->n[s], o->n_kept_dev + s, in->img_w[s], in->img_h[s],
+                      w.sage_out + base * kD, w.desc + base * kD, w.scratch, mode, st));
   }
   if (o->desc_in) {
     k_copy_rows<<<(unsigned)((rows * kD / 4 + 255) / 256), 256, 0, st>>>(w.desc, o->desc_in, rows * kD / 4);
@@ -412,14 +430,14 @@ extern "C" int gims_forward_pair(const gims_model* m, const gims_pair_inputs* in
   }
   // a-11, a-12: attention stack (gmatcher.py:272)
   for (int l = 0; l < m->cfg.num_layers; ++l)
-    GIMS_TRY(gims_attn_layer_forward(m, l, w.desc, n0, n1, o->n_kept_dev, w.scratch, stream));
+    GIMS_TRY(attn_layer(m, l, w.desc, n0, n1, o->n_kept_dev, w.scratch, o->status_dev, mode, st));
   if (o->desc_gnn) {
     k_copy_rows<<<(unsigned)((rows * kD / 4 + 255) / 256), 256, 0, st>>>(w.desc, o->desc_gnn, rows * kD / 4);
     GIMS_LAUNCH_OK();
   }
   // a-13 .. a-15
   float* coup = o->couplings ? o->couplings : w.couplings;
-  GIMS_TRY(gims_final_scores(m, w.desc, n0, n1, o->n_kept_dev, o->mdesc, coup, w.scratch, stream));
+  GIMS_TRY(final_scores(m, w.desc, n0, n1, o->n_kept_dev, o->mdesc, coup, w.scratch, mode, st));
   GIMS_TRY(gims_sinkhorn_match(coup, coup_ld(n1), n0, n1, o->n_kept_dev, m->cfg.sinkhorn_iterations, m->cfg.match_threshold, w.sink,
                                w.sink_bytes, o->u, o->v, o->indices[0], o->indices[1], o->matches[0], o->matches[1],
                                o->mscores[0], o->mscores[1], o->status_dev, stream));

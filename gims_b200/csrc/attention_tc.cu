@@ -383,9 +383,10 @@ k_attention_tc(const __grid_constant__ CUtensorMap mapK, const __grid_constant__
 
 }  // namespace
 
+int set_attention16_trace(long long* dev_buf);
 int set_attention_trace(long long* dev_buf) {
   GIMS_CUDA_OK(cudaMemcpyToSymbol(g_attn_trace, &dev_buf, sizeof(dev_buf)));
-  return GIMS_OK;
+  return set_attention16_trace(dev_buf);
 }
 
 // planes as written by the qkv-mode GEMM epilogue (QkvPlanes, common.cuh)
@@ -396,8 +397,8 @@ int launch_attention_tc(const QkvPlanes& pl, float* out, int n0_max, int n1_max,
   // KT = 128 (GIMS_ATTN_KT=128) is correct but measured slower on B200 (56 vs 51 us per launch): the softmax warps need
   // ~1700 clk per 64-key tile, which is under the tensor pipe's 2170 clk at KT = 64 but not under its 1850 clk at 128.
   static const int kt = [] { const char* e = getenv("GIMS_ATTN_KT"); return (e && atoi(e) == 128) ? 128 : 64; }();
-  GIMS_TRY(tc::make_tmap_f32_k32(&mK, pl.kp, 2 * (uint64_t)rows, kD, kD, kt));
-  GIMS_TRY(tc::make_tmap_f32_k32(&mV, pl.vt, 2 * (uint64_t)kD, pl.ldv, pl.ldv, HD));
+  GIMS_TRY(tc::make_tmap_f32_k32(&mK, static_cast<const float*>(pl.kp), 2 * (uint64_t)rows, kD, kD, kt));
+  GIMS_TRY(tc::make_tmap_f32_k32(&mV, static_cast<const float*>(pl.vt), 2 * (uint64_t)kD, pl.ldv, pl.ldv, HD));
   AttnTcArgs a;
   a.qp = pl.qp;
   a.out = out;

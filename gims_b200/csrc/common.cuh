@@ -113,17 +113,23 @@ struct GemmArgs {
 int launch_gemm(const GemmArgs& a, cudaStream_t st);
 
 // tensor-core (tcgen05, 3xTF32) variants — gemm_tc.cu
-struct QkvPlanes {            // outputs of the QKV projection in the layout attention_tc.cu consumes
-  float* qp;                  // [rows_total][256] fp32, scaled by log2(e)/8 (room for two planes is reserved)
-  float* kp;                  // [2][rows_total][256]
-  float* vt;                  // [2][256][ldv]; key columns: image 0 at [0, n0), image 1 at [vbase1, vbase1 + n1)
-  int ldv;                    // multiple of 4
+struct QkvPlanes {            // outputs of the QKV projection in the layout the attention kernels consume
+  float* qp;                  // [rows_total][256] fp32, scaled by log2(e)/8
+  void* kp;                   // tf32: float [2][rows_total][256];  16-bit: [planes][rows_total][256]
+  void* vt;                   // tf32: float [2][256][ldv];         16-bit: [planes][256][ldv]
+                              // key columns: image 0 at [0, n0), image 1 at [vbase1, vbase1 + n1)
+  int ldv;                    // multiple of 64
   int vbase1;                 // round_up(n0_max, 64)
+  int fmt;                    // -1: tf32 hi / lo planes (attention_tc.cu); 0: fp16, 1: bf16 (attention_f16.cu)
+  int planes;                 // 16-bit: 2 = hi + lo (fp32-class), 1 = single plane (bf16 variant)
+  unsigned* status;           // fp16: GIMS_STATUS_FP16_RANGE is OR-ed in when a value reaches 32768 (may be null)
 };
 int launch_gemm_tc(const GemmArgs& a, const float* w_hi, const float* w_lo, cudaStream_t st,
                    const QkvPlanes* qkv = nullptr);
 int launch_attention_tc(const QkvPlanes& pl, float* out, int n0_max, int n1_max, const int* n_dev, int cross,
                         cudaStream_t st);
+int launch_attention_f16(const QkvPlanes& pl, float* out, int n0_max, int n1_max, const int* n_dev, int cross,
+                         cudaStream_t st);
 int set_attention_trace(long long* dev_buf);
 int set_gemm_trace(long long* dev_buf);
 // row pitch (floats) of the couplings matrix (n0_max+1) x (n1_max+1): rows start 16-byte aligned

@@ -53,6 +53,24 @@ int make_tmap_f32_k32(CUtensorMap* out, const float* base, uint64_t rows, uint64
   return GIMS_OK;
 }
 
+int make_tmap_16_k64(CUtensorMap* out, const void* base, int fmt, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows) {
+  EncodeTiledFn enc = get_encode_tiled();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return GIMS_ERR_CUDA; }
+  cuuint64_t dims[2] = {cols, rows};
+  cuuint64_t strides[1] = {ld * 2};
+  cuuint32_t box[2] = {64, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(out, fmt == 0 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base),
+                   dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                   CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled (16-bit) failed (%d) base=%p rows=%llu cols=%llu ld=%llu box_rows=%u", (int)r, base,
+              (unsigned long long)rows, (unsigned long long)cols, (unsigned long long)ld, box_rows);
+    return GIMS_ERR_CUDA;
+  }
+  return GIMS_OK;
+}
+
 }  // namespace tc
 
 namespace {
@@ -105,13 +123,15 @@ struct TcArgs {
   //   columns [256,512) -> Kp [2][rows_total][256]
   //   columns [512,768) -> Vt [2][256][ldv]          transposed; rows beyond the live count are zero-filled
   int qkv;
-  float* qp; float* kp; float* vt; int ldv; int rows_total; int vbase1;
+  float* qp; void* kp; void* vt; int ldv; int rows_total; int vbase1;
+  unsigned* status;              // 16-bit planes: overflow flag
 };
 
 // Optional pipeline trace (bring-up / profiling): CTA (0,0) stores clock64() stamps, see tools/gemm_trace.py.
 __device__ long long* g_gemm_trace = nullptr;
 
-// MODE 0: Y = act(acc + bias + R);  1: couplings (score GEMM);  2: Q / K / Vt tf32 planes (QKV projection)
+// MODE 0: Y = act(acc + bias + R);  1: couplings (score GEMM);  QKV projection: 2: Q / K / Vt tf32 planes,
+// 3: fp16 hi + lo planes, 4: one bf16 plane (K / Vt; Q stays fp32)
 template <int BN, int MODE>
 __global__ void __launch_bounds__(kThreadsTc, BN <= 64 ? 2 : 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
@@ -316,22 +336,41 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
       if (trace && t == 0 && cc < 2) trace[56 + 3 * cc] = clock64();
       const int c = c0 + cc * 32;
       if (c >= ncols) continue;                                // warp-uniform
-      if (MODE == 2 && c >= 2 * kD) {
+      if (MODE >= 2 && c >= 2 * kD) {
         // V: key column of this row in Vt; image 1 starts at a 64-aligned column (TMA box starts must be 16-byte
         // aligned in global memory).  Lanes = consecutive rows = consecutive addresses: coalesced as it is.
+        // Rows between the live count and the next multiple of 64 are ZERO-FILLED: the attention kernel multiplies them
+        // by P = 0, which must not meet a NaN / Inf left over from whatever used this workspace before.
         const int r = r0 + 32 * q + lane;
-        if (r < g.segs.nmax[seg]) {                            // never touch the other image's rows
+        if (r < ((g.segs.nmax[seg] + 63) & ~63)) {             // never touch the other image's columns
           const bool row_ok = r < rows;
           const int cc256 = c & 255;
           const size_t kcol = (size_t)(seg ? g.vbase1 : 0) + r;
-          float* hi = g.vt + (size_t)cc256 * g.ldv + kcol;
-          float* lo = hi + (size_t)kD * g.ldv;
+          if (MODE == 2) {
+            float* hi = static_cast<float*>(g.vt) + (size_t)cc256 * g.ldv + kcol;
+            float* lo = hi + (size_t)kD * g.ldv;
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            float h, l;
-            split_tf32(row_ok ? __uint_as_float(v[j]) + bias_s[cc * 32 + j] : 0.f, h, l);
-            hi[(size_t)j * g.ldv] = h;
-            lo[(size_t)j * g.ldv] = l;
+            for (int j = 0; j < 32; ++j) {
+              float h, l;
+              split_tf32(row_ok ? __uint_as_float(v[j]) + bias_s[cc * 32 + j] : 0.f, h, l);
+              hi[(size_t)j * g.ldv] = h;
+              lo[(size_t)j * g.ldv] = l;
+            }
+          } else {
+            constexpr int FMT = MODE == 4 ? 1 : 0;
+            uint16_t* hi = static_cast<uint16_t*>(g.vt) + (size_t)cc256 * g.ldv + kcol;
+            uint16_t* lo = hi + (size_t)kD * g.ldv;
+            bool ovf = false;
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const float x = row_ok ? __uint_as_float(v[j]) + bias_s[cc * 32 + j] : 0.f;
+              if (FMT == 0) ovf = ovf || fabsf(x) >= 32768.f;
+              uint32_t wh, wl;
+              if (MODE == 3) split16x2<FMT>(x, 0.f, wh, wl); else wh = pack16<FMT>(x, 0.f);
+              hi[(size_t)j * g.ldv] = (uint16_t)wh;
+              if (MODE == 3) lo[(size_t)j * g.ldv] = (uint16_t)wl;
+            }
+            if (ovf && g.status) atomicOr(g.status, GIMS_STATUS_FP16_RANGE);
           }
         }
         continue;
@@ -377,7 +416,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
         for (int i = 0; i < 8; ++i)
           if (4 * i < nvalid) rres[i] = *reinterpret_cast<const float4*>(rrow + (size_t)(4 * i) * g.ldr + (cc + 1) * 32);
       }
-      if (MODE == 2) {
+      if (MODE >= 2) {
         if (c < kD) {
           // Q: one fp32 plane, scaled by log2(e)/sqrt(64) (scores in the log2 domain); the attention kernel splits
           // its own query rows when it loads them into TMEM
@@ -388,8 +427,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
             if (4 * i < nvalid)
               *reinterpret_cast<float4*>(qd + (size_t)(4 * i) * kD) =
                   make_float4(o[i].x * sc, o[i].y * sc, o[i].z * sc, o[i].w * sc);
-        } else {
-          float* hi = g.kp + (size_t)(rbase + rfirst) * kD + (c & 255) + cj;
+        } else if (MODE == 2) {
+          float* hi = static_cast<float*>(g.kp) + (size_t)(rbase + rfirst) * kD + (c & 255) + cj;
           const size_t plane = (size_t)g.rows_total * kD;
 #pragma unroll
           for (int i = 0; i < 8; ++i) {
@@ -401,6 +440,30 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
               *reinterpret_cast<float4*>(hi + (size_t)(4 * i) * kD + plane) = l;
             }
           }
+        } else {
+          // K: 16-bit planes, four channels = one 8-byte store per plane
+          constexpr int FMT = MODE == 4 ? 1 : 0;
+          uint16_t* hi = static_cast<uint16_t*>(g.kp) + (size_t)(rbase + rfirst) * kD + (c & 255) + cj;
+          const size_t plane = (size_t)g.rows_total * kD;
+          bool ovf = false;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            uint2 h, l;
+            if (FMT == 0 && 4 * i < nvalid)
+              ovf = ovf || fmaxf(fmaxf(fabsf(o[i].x), fabsf(o[i].y)), fmaxf(fabsf(o[i].z), fabsf(o[i].w))) >= 32768.f;
+            if (MODE == 3) {
+              split16x2<FMT>(o[i].x, o[i].y, h.x, l.x);
+              split16x2<FMT>(o[i].z, o[i].w, h.y, l.y);
+            } else {
+              h.x = pack16<FMT>(o[i].x, o[i].y);
+              h.y = pack16<FMT>(o[i].z, o[i].w);
+            }
+            if (4 * i < nvalid) {
+              *reinterpret_cast<uint2*>(hi + (size_t)(4 * i) * kD) = h;
+              if (MODE == 3) *reinterpret_cast<uint2*>(hi + (size_t)(4 * i) * kD + plane) = l;
+            }
+          }
+          if (ovf && g.status) atomicOr(g.status, GIMS_STATUS_FP16_RANGE);
         }
       } else {
         float* yp = g.Y + (size_t)(rbase + rfirst) * g.ldy + c + cj;
@@ -478,7 +541,7 @@ int launch_gemm_tc(const GemmArgs& a, const float* w_hi, const float* w_lo, cuda
   }
   int total_rows = a.segs.nseg > 1 ? a.segs.base[1] + a.segs.nmax[1] : a.segs.nmax[0];
   int bn = pick_bn(a.N);
-  if (qkv && bn != 64) bn = 192;
+  if (qkv && (bn != 64 || qkv->fmt >= 0)) bn = 192;
   CUtensorMap mA0, mA1, mWh, mWl;
   GIMS_TRY(tc::make_tmap_f32_k32(&mA0, a.A0, total_rows, a.K0, a.lda0, BM));
   if (a.K1) GIMS_TRY(tc::make_tmap_f32_k32(&mA1, a.A1, total_rows, a.K1, a.lda1, BM));
@@ -488,16 +551,20 @@ int launch_gemm_tc(const GemmArgs& a, const float* w_hi, const float* w_lo, cuda
   TcArgs g;
   g.K0 = a.K0; g.K1 = a.K1; g.bias = a.bias; g.R = a.R; g.ldr = a.ldr; g.Y = a.Y; g.ldy = a.ldy; g.N = a.N;
   g.relu = a.relu; g.scale = 1.f; g.score = 0; g.segs = a.segs;
-  g.qkv = 0; g.qp = g.kp = g.vt = nullptr; g.ldv = 0; g.rows_total = total_rows; g.vbase1 = 0;
+  g.qkv = 0; g.qp = nullptr; g.kp = g.vt = nullptr; g.ldv = 0; g.rows_total = total_rows; g.vbase1 = 0; g.status = nullptr;
   if (qkv) {
     if (a.N != 3 * kD || !a.bias) { set_error("launch_gemm_tc: qkv mode needs N = 768 and a bias"); return GIMS_ERR_ARG; }
     g.qkv = 1; g.qp = qkv->qp; g.kp = qkv->kp; g.vt = qkv->vt; g.ldv = qkv->ldv; g.vbase1 = qkv->vbase1;
+    g.status = qkv->status;
   }
   g.tiles0 = cdiv(a.segs.nmax[0], BM);
   int tiles = g.tiles0 + (a.segs.nseg > 1 ? cdiv(a.segs.nmax[1], BM) : 0);
   if (tiles == 0) return GIMS_OK;
   int ct = cdiv(a.N, bn);
   if (qkv) {
+    if (qkv->fmt == 0 && qkv->planes == 2) return launch_tc<192, 3>(mA0, mA1, mWh, mWl, g, ct, tiles, GIMS_PROF_GEMM, st);
+    if (qkv->fmt == 1 && qkv->planes == 1) return launch_tc<192, 4>(mA0, mA1, mWh, mWl, g, ct, tiles, GIMS_PROF_GEMM, st);
+    if (qkv->fmt >= 0) { set_error("launch_gemm_tc: unsupported 16-bit plane format"); return GIMS_ERR_ARG; }
     if (bn == 64) return launch_tc<64, 2>(mA0, mA1, mWh, mWl, g, ct, tiles, GIMS_PROF_GEMM, st);
     return launch_tc<192, 2>(mA0, mA1, mWh, mWl, g, ct, tiles, GIMS_PROF_GEMM, st);
   }
@@ -535,7 +602,7 @@ int launch_score_gemm_tc(const float* mdesc, int n0_max, int n1_max, const int* 
   TcArgs g;
   g.K0 = kD; g.K1 = 0; g.bias = nullptr; g.R = nullptr; g.ldr = 0; g.Y = couplings; g.ldy = coup_ld(n1_max); g.N = n1_max;
   g.relu = 0; g.scale = 0.0625f; g.score = 1;
-  g.qkv = 0; g.qp = g.kp = g.vt = nullptr; g.ldv = 0; g.rows_total = (int)rows; g.vbase1 = 0;
+  g.qkv = 0; g.qp = nullptr; g.kp = g.vt = nullptr; g.ldv = 0; g.rows_total = (int)rows; g.vbase1 = 0; g.status = nullptr;
   g.segs.base[0] = 0; g.segs.base[1] = n0_max; g.segs.nmax[0] = n0_max; g.segs.nmax[1] = n1_max; g.segs.n_dev = n_dev;
   g.segs.nseg = 2;
   g.tiles0 = cdiv(n0_max, BM);

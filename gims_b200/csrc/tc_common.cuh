@@ -145,6 +145,15 @@ __device__ __forceinline__ void tmem_st_32x32(uint32_t taddr, const uint32_t (&r
       "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
       : "memory");
 }
+// 32 lanes x 16 columns of 32-bit, registers -> TMEM
+__device__ __forceinline__ void tmem_st_32x16(uint32_t taddr, const uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
 __device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
 // D[tmem] (+)= A[tmem] * B[smem]^T
@@ -157,6 +166,49 @@ __device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, u
       "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// ---- 16-bit operands (kind::f16): fp16 or bf16, fp32 accumulate, K = 16 per instruction ---------------------------
+// Instruction descriptor: same fields as the tf32 one; A / B format 0 = f16, 1 = bf16 (both operands must have the SAME
+// format: a mixed f16 x bf16 instruction traps as illegal on sm_100a — tools/micro/f16_mix.cu).
+__host__ __device__ constexpr uint32_t umma_idesc_f16(int m, int n, int fmt) {
+  return (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10) | ((uint32_t)(n >> 3) << 17) | ((uint32_t)(m >> 4) << 24);
+}
+// D[tmem] (+)= A[tmem] * B[smem]^T, A packed two 16-bit values per 32-bit TMEM column (even k in the low half)
+__device__ __forceinline__ void umma_f16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                            uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// two fp32 -> one 32-bit word of two 16-bit floats, `lo` in the low half; FMT 0 = f16, 1 = bf16 (round to nearest even)
+template <int FMT>
+__device__ __forceinline__ uint32_t pack16(float lo, float hi) {
+  uint32_t d;
+  if (FMT == 0) asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  else          asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(hi), "f"(lo));
+  return d;
+}
+template <int FMT>
+__device__ __forceinline__ void unpack16(uint32_t d, float& lo, float& hi) {
+  if (FMT == 0) {
+    asm("{\n\t.reg .f16 l, h;\n\tmov.b32 {l, h}, %2;\n\tcvt.f32.f16 %0, l;\n\tcvt.f32.f16 %1, h;\n\t}" : "=f"(lo), "=f"(hi) : "r"(d));
+  } else {
+    lo = __uint_as_float(d << 16);
+    hi = __uint_as_float(d & 0xffff0000u);
+  }
+}
+// x0, x1 -> packed hi plane word and packed lo plane word: x = hi + lo with hi = rn16(x), lo = rn16(x - hi)
+// (x - hi is exact in fp32).  fp16: |x - (hi + lo)| <= max(2^-22 |x|, 2^-25) for |x| < 65504.
+template <int FMT>
+__device__ __forceinline__ void split16x2(float x0, float x1, uint32_t& hi, uint32_t& lo) {
+  hi = pack16<FMT>(x0, x1);
+  float h0, h1;
+  unpack16<FMT>(hi, h0, h1);
+  lo = pack16<FMT>(x0 - h0, x1 - h1);
+}
+
 // Arrive on an mbarrier once every previously issued tcgen05.mma of this thread has completed.
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
@@ -181,6 +233,8 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
 EncodeTiledFn get_encode_tiled();
 // fp32 row-major [rows][cols] (row stride ld floats), box = box_rows x 32 floats, SWIZZLE_128B
 int make_tmap_f32_k32(CUtensorMap* out, const float* base, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
+// 16-bit row-major [rows][cols] (row stride ld elements, ld % 8 == 0), box = box_rows x 64 elements (128 bytes), SWIZZLE_128B
+int make_tmap_16_k64(CUtensorMap* out, const void* base, int fmt, uint64_t rows, uint64_t cols, uint64_t ld, uint32_t box_rows);
 
 }  // namespace tc
 }  // namespace gims

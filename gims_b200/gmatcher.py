@@ -284,7 +284,7 @@ class GMatcher(nn.Module):
             return ws
 
     def run_pair(self, kpts0, desc0, scores0, kpts1, desc1, scores1, shape0, shape1, radius=25, percentile=7,
-                 min_size=8, edge_cap=None, debug=False, stream=None, slot=0):
+                 min_size=8, edge_cap=None, debug=False, stream=None, slot=0, gemm_mode=None):
         """One pair on the device.  kpts (N,2), desc (D,N) channel-major, scores (N,) CUDA fp32 tensors.
         Enqueues everything on `stream` (default: current) and returns a dict of device tensors sized
         for the INPUT counts plus `n_kept_dev`; nothing synchronises.  `forward` slices them."""
@@ -342,6 +342,7 @@ class GMatcher(nn.Module):
         pin.radius = float(radius)
         pin.min_size = int(min_size)
         pin.edge_cap = int(edge_cap)
+        pin.gemm_mode = 0 if gemm_mode is None else int(gemm_mode) + 1        # 0 = the library default
         po = _lib.PairOutputs()
         cnt = out['n_kept_dev']
         po.n_kept_dev = cnt.data_ptr()
@@ -392,12 +393,12 @@ class GMatcher(nn.Module):
         batch = data['keypoints0'].shape[0]
         per_item = []
         for b in range(batch):
-            cap = None
+            cap, mode = None, None
             while True:
                 r = self.run_pair(data['keypoints0'][b], data['descriptors0'][b], data['scores0'][b],
                                   data['keypoints1'][b], data['descriptors1'][b], data['scores1'][b],
                                   data['image0'].shape, data['image1'].shape, radius, percentile, min_size,
-                                  edge_cap=cap)
+                                  edge_cap=cap, gemm_mode=mode)
                 meta = r['meta'].cpu()                  # the one device->host sync of the call: counts + kept indices
                 counts = meta[:8]
                 status = int(counts[6])
@@ -407,6 +408,12 @@ class GMatcher(nn.Module):
                     if r['edge_cap'] >= n_max * n_max:
                         raise _lib.GimsError('edge capacity overflow')
                     cap = min(r['edge_cap'] * 4, n_max * n_max)
+                    continue
+                if status & _lib.STATUS_FP16_RANGE:
+                    # an attention operand left the fp16 range (|x| >= 32768): redo this pair on the 3xTF32 kernels
+                    if mode == _lib.GEMM_TC:
+                        raise _lib.GimsError('fp16 range flag raised by the tf32 path')
+                    mode = _lib.GEMM_TC
                     continue
                 if status & _lib.STATUS_SINKHORN_TIMEOUT:
                     raise _lib.GimsError('Sinkhorn kernel: a grid-wide wait timed out (GPU shared / preempted?); '

@@ -53,6 +53,7 @@ extern "C" {
  * Error bits (the host side raises on them): */
 #define GIMS_STATUS_EDGE_OVERFLOW     1u   /* edge_cap exceeded: the graph is reported EMPTY (N' = 0), retry larger */
 #define GIMS_STATUS_SINKHORN_TIMEOUT  2u   /* a bounded poll inside k_sinkhorn expired: outputs are poisoned (NaN / -2) */
+#define GIMS_STATUS_FP16_RANGE        4u   /* GIMS_GEMM_TC_F16: an attention operand reached 32768 — rerun with GIMS_GEMM_TC */
 #define GIMS_STATUS_ERROR_MASK        0xffu
 /* Information bits: which Sinkhorn iteration the launch ran */
 #define GIMS_STATUS_SINKHORN_FAST   0x100u /* exp-free scaled-kernel iteration */
@@ -77,11 +78,19 @@ GIMS_API const char* gims_last_error(void);
 /* number of kernels this library has launched in the calling process (for bench `gpu_launches`) */
 GIMS_API long long   gims_launch_count(void);
 
-/* GEMM arithmetic of the dense contractions (process-wide):
- *   GIMS_GEMM_TC   tcgen05/TMEM/TMA tensor-core kernels, 3xTF32 error-compensated fp32 (default)
- *   GIMS_GEMM_SIMT fp32 FMA CUDA-core kernels (bit-for-bit fp32 products; used to validate the former) */
-#define GIMS_GEMM_SIMT 0
-#define GIMS_GEMM_TC   1
+/* Arithmetic of the dense contractions.  Process-wide default (gims_set_gemm_mode), or per call
+ * (gims_pair_inputs.gemm_mode):
+ *   GIMS_GEMM_SIMT    fp32 FMA CUDA-core kernels (bit-for-bit fp32 products; used to validate the others)
+ *   GIMS_GEMM_TC      tcgen05/TMEM/TMA tensor-core kernels, 3xTF32 error-compensated fp32 everywhere
+ *   GIMS_GEMM_TC_F16  (default) as GIMS_GEMM_TC, attention operands as fp16 hi + lo planes: the same error class
+ *                     (|x - hi - lo| <= max(2^-22 |x|, 2^-25)) at twice the tensor-pipe rate.  fp16 overflows at
+ *                     65504: a value >= 32768 raises GIMS_STATUS_FP16_RANGE and the caller reruns with GIMS_GEMM_TC.
+ *   GIMS_GEMM_BF16    the "bf16 variant": attention operands and the score GEMM in bf16 (8-bit mantissa), projections
+ *                     as GIMS_GEMM_TC.  NOT fp32 parity — reported separately (BASELINE.json north_star). */
+#define GIMS_GEMM_SIMT   0
+#define GIMS_GEMM_TC     1
+#define GIMS_GEMM_TC_F16 2
+#define GIMS_GEMM_BF16   3
 GIMS_API int gims_set_gemm_mode(int mode);
 GIMS_API int gims_get_gemm_mode(void);
 
@@ -166,7 +175,7 @@ GIMS_API int gims_kenc_forward(const gims_model* m, const float* kpts, int n_max
  * scratch: gims_attn_scratch_floats(n0_max + n1_max) floats. */
 GIMS_API size_t gims_attn_scratch_floats(int rows);
 GIMS_API int gims_attn_layer_forward(const gims_model* m, int layer, float* desc, int n0_max, int n1_max, const int* n_dev,
-                            float* scratch, void* stream);
+                            float* scratch, unsigned* status_dev /* may be NULL */, void* stream);
 
 /* ---- a-13: final_proj + score matrix (gmatcher.py:273-275) ----------------------------------
  * mdesc [rows][256] = final_proj(desc); couplings (n0_max+1) x ld, ld = gims_couplings_ld(n1_max) (n1_max+1 rounded up
@@ -208,6 +217,7 @@ typedef struct {
   long long k_rank[2];           /* see gims_agc_build */
   int   min_size;                /* data.get('min_size', 8) */
   int   edge_cap;                /* per-image capacity of csr_indices */
+  int   gemm_mode;               /* 0 = the library default (gims_set_gemm_mode), else GIMS_GEMM_* + 1 */
 } gims_pair_inputs;
 
 typedef struct {

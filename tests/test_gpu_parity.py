@@ -269,7 +269,10 @@ def test_sinkhorn_vs_oracle(n0, n1, iters, scale, aligned, offset):
     g = torch.Generator().manual_seed(n0 * 7 + n1)
     scores = torch.randn(1, n0, n1, generator=g) * scale + offset
     alpha = torch.tensor(0.7)
-    z, u, v, coup = orc.log_optimal_transport(scores, alpha, iters)
+    # yardstick: the reference's iteration evaluated in float64 on the same fp32 couplings (its fp32 evaluation drifts
+    # along the neutral u + c / v - c mode by more than our tolerance when the scores are large, see _check_forward)
+    z, u, v, coup = orc.log_optimal_transport(scores.double(), alpha.double(), iters)
+    z, u, v, coup = z.float(), u.float(), v.float(), coup.float()
     m = orc.extract_matches(z, 0.0)
     dev = torch.device('cuda')
     # exercise device-side counts: allocate for larger maxima than the live sizes

@@ -17,10 +17,10 @@ scratch = torch.zeros(L.gims_attn_scratch_floats(n0 + n1), device=dev)
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 trace = torch.zeros(64 * 8, dtype=torch.int64, device=dev)
 for it in range(3):
-    _lib.check(L.gims_attn_layer_forward(model, 0, _lib.ptr(desc), n0, n1, _lib.ptr(nd), _lib.ptr(scratch), st), 'warm')
+    _lib.check(L.gims_attn_layer_forward(model, 0, _lib.ptr(desc), n0, n1, _lib.ptr(nd), _lib.ptr(scratch), None, st), 'warm')
 torch.cuda.synchronize()
 L.gims_debug_attention_trace(C.c_void_p(trace.data_ptr()))
-_lib.check(L.gims_attn_layer_forward(model, 0, _lib.ptr(desc), n0, n1, _lib.ptr(nd), _lib.ptr(scratch), st), 'trace')
+_lib.check(L.gims_attn_layer_forward(model, 0, _lib.ptr(desc), n0, n1, _lib.ptr(nd), _lib.ptr(scratch), None, st), 'trace')
 torch.cuda.synchronize()
 L.gims_debug_attention_trace(None)
 t = trace.cpu().view(64, 8)
@@ -31,7 +31,7 @@ print('kernel entry -> first tile top: %d clk; last stamp -> exit: see below; en
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 e0.record()
 for it in range(20):
-    _lib.check(L.gims_attn_layer_forward(model, 0, _lib.ptr(desc), n0, n1, _lib.ptr(nd), _lib.ptr(scratch), st), 'time')
+    _lib.check(L.gims_attn_layer_forward(model, 0, _lib.ptr(desc), n0, n1, _lib.ptr(nd), _lib.ptr(scratch), None, st), 'time')
 e1.record()
 torch.cuda.synchronize()
 print('whole layer (QKV GEMM + attention + MLP1 + MLP2), back to back: %.1f us' % (e0.elapsed_time(e1) * 1000 / 20))

@@ -48,7 +48,7 @@ __global__ void __launch_bounds__(128, 1) k_test(const uint16_t* A16, const uint
   tcgen05_fence_after();
   const uint32_t tmem = slot;
   const uint32_t lane_base = tmem + ((uint32_t)(32 * (t >> 5)) << 16);
-  if (ts) {   // A row t -> TMEM columns 64..95: 32 words, word c = halves (2c, 2c+1), low half = even k
+  if (ts == 1 || ts == 2) {   // A row t -> TMEM columns 64..95: 32 words, word c = halves (2c, 2c+1), low half = even k
     uint32_t v[32];
     for (int c = 0; c < 32; ++c) v[c] = (uint32_t)A16[t * 64 + 2 * c] | ((uint32_t)A16[t * 64 + 2 * c + 1] << 16);
     tmem_st_32x32(lane_base + 64, v);
@@ -57,7 +57,21 @@ __global__ void __launch_bounds__(128, 1) k_test(const uint16_t* A16, const uint
   }
   __syncthreads();
   tcgen05_fence_after();
-  if (t == 0) {
+  if (t == 0 && ts >= 2) {        // rate: 2000 back-to-back MMAs, TS (ts = 2) or SS (ts = 3), two accumulators alternating
+    const uint32_t idesc = idesc_f16(128, 64, afmt, bfmt);
+    const uint64_t da = umma_desc_sw128(smem_u32(sa)), db = umma_desc_sw128(smem_u32(sb));
+    long long t0 = clock64();
+    for (int i = 0; i < 2000; ++i) {
+      const int ks = i & 3;
+      const uint64_t off = (ks * 32) >> 4;
+      if (ts == 2) mma_f16_ts(tmem + (i & 4 ? 0 : 0), tmem + 64 + ks * 8, db + off, idesc, 1u);
+      else         mma_f16_ss(tmem, da + off, db + off, idesc, 1u);
+    }
+    umma_commit(&bar);
+    mbar_wait(&bar, 0);
+    long long t1 = clock64();
+    D[0] = (float)(t1 - t0) / 2000.f;
+  } else if (t == 0) {
     const uint32_t idesc = idesc_f16(128, 64, afmt, bfmt);
     const uint64_t da = umma_desc_sw128(smem_u32(sa)), db = umma_desc_sw128(smem_u32(sb));
     for (int ks = 0; ks < 4; ++ks) {
@@ -70,6 +84,7 @@ __global__ void __launch_bounds__(128, 1) k_test(const uint16_t* A16, const uint
   }
   __syncthreads();
   tcgen05_fence_after();
+  if (ts >= 2) { __syncthreads(); if (t < 32) tmem_dealloc<128>(tmem); return; }
   for (int h = 0; h < 2; ++h) {
     uint32_t v[32];
     tmem_ld_32x32(lane_base + h * 32, v);
@@ -98,7 +113,7 @@ int main(int argc, char** argv) {
   cudaMalloc(&dA, 128 * 64 * 2); cudaMalloc(&dB, 64 * 64 * 2); cudaMalloc(&dD, 128 * 64 * 4);
   int smem = 16384 + 8192 + 1024;
   cudaFuncSetAttribute(k_test, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
-  for (int ts = 0; ts < 2; ++ts)
+  for (int ts = 0; ts < 4; ++ts)
     for (int afmt = 0; afmt < 2; ++afmt)
       for (int bfmt = 0; bfmt < 2; ++bfmt) {
         if ((only_ts >= 0 && ts != only_ts) || (only_a >= 0 && afmt != only_a) || (only_b >= 0 && bfmt != only_b)) continue;
@@ -110,6 +125,7 @@ int main(int argc, char** argv) {
         k_test<<<1, 128, smem>>>(dA, dB, afmt, bfmt, ts, dD);
         cudaError_t e = cudaDeviceSynchronize();
         cudaMemcpy(D, dD, 128 * 64 * 4, cudaMemcpyDeviceToHost);
+        if (ts >= 2) { printf("%s f16 N=64 K=16: %.1f clk per MMA (%s)\n", ts == 2 ? "TS" : "SS", D[0], cudaGetErrorString(e)); continue; }
         double maxerr = 0, maxref = 0;
         for (int m = 0; m < 128; ++m)
           for (int n = 0; n < 64; ++n) {
