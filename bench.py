@@ -67,6 +67,7 @@ def base_config(args, world):
     return {'workload': workload_name(args), 'kpts_per_image': args.kpts, 'weights': args.weights,
             'sinkhorn_iterations': 100, 'agc_radius_percentile_minsize': [25, 7, 8],
             'pairs_per_step_per_gpu': args.pairs_per_step, 'streams': args.streams,
+            'pairs_per_launch': args.pairs_per_launch,
             'l2': 'input pool of %d distinct pairs (%.0f MB) > L2' % (args.pool, args.pool * pair_input_bytes(args.kpts) / 1e6),
             'parallelism': 'pair-parallel x%d, no collective' % world}
 
@@ -317,6 +318,98 @@ def cpu_baseline(args):
             'sample': '%d pair(s) at %d kp, %s, torch %d threads' % (n, args.kpts, what, cores)}
 
 
+def load_caller_carhynet(dev):
+    """The CALLER's descriptor object of the pipeline config: the reference's CAR_HyNet (random init — the trained
+    weights are not in the reference tree) from the git-ignored copy under baseline/_ref, wrapped like
+    carhynet/models.py:639-670 `HyNetnetFeature2D` (whose __init__ hard-loads ./weights/car_hynet.pth)."""
+    ref_root = os.path.join(ROOT, 'baseline', '_ref')
+    if not os.path.isfile(os.path.join(ref_root, 'carhynet', 'models.py')):
+        return None
+    if ref_root not in sys.path:
+        sys.path.insert(0, ref_root)
+    import importlib
+    hm = importlib.import_module('carhynet.models')
+    torch.manual_seed(0)
+    car = object.__new__(hm.HyNetnetFeature2D)
+    car.G_dim, car.do_cuda, car.device, car.batch_size = 128, True, dev, 512
+    car.model = hm.CAR_HyNet().to(dev).eval()
+    return car
+
+
+def run_pipeline(args):
+    """BASELINE configs[2].  One JSON line: pairs/s of the whole `matching({'image0', 'image1', 'carhynet', ...})` call
+    (eval_homography.py:177: AGC r/p/m 15/2/7, 20 Sinkhorn iterations) and its stage split."""
+    from gims_b200 import Matching, _lib, frontend
+    from gims_b200.synth import make_textured_image, warp_image
+    dev = torch.device('cuda', int(os.environ.get('LOCAL_RANK', 0)))
+    torch.cuda.set_device(dev)
+    car = load_caller_carhynet(dev)
+    if car is None:
+        print(json.dumps({'metric': 'pipeline_pairs_per_sec_800x600', 'unavailable': 'baseline/_ref/carhynet is missing '
+                          '(run __graft_entry__.build() where /root/reference exists)'}))
+        return
+    max_kp = args.kpts
+    matching = Matching({'sinkhorn_iterations': 20, 'match_threshold': 0.2, 'max_keypoints': max_kp})
+    matching.gmodel.load_state_dict(make_state_dict(0, damped=(args.weights == 'damped')))
+    matching = matching.eval().to(dev)
+    n_pairs = max(3, args.steps)
+    pairs = []
+    for i in range(n_pairs + 1):
+        img0 = make_textured_image(600, 800, seed=100 + i)
+        img1, _ = warp_image(img0, seed=200 + i)
+        pairs.append((img0[None], img1[None]))                 # (1, H, W, 3) as frame2tensor(color=True) gives
+    def call(p):
+        with torch.no_grad():
+            pred = matching({'delaunay': False, 'image0': p[0], 'image1': p[1], 'carhynet': car, 'device': dev,
+                             'radius': 15, 'percentile': 2, 'min_size': 7})
+        out = {k: v[0].cpu().numpy() for k, v in pred.items()}       # eval_homography.py:181
+        return out
+    call(pairs[0])
+    torch.cuda.synchronize(dev)
+    t0 = time.perf_counter()
+    kept = []
+    for p in pairs[1:]:
+        out = call(p)
+        kept.append((int(out['keypoints0'].shape[0]), int(out['keypoints1'].shape[0]), int((out['matches0'] >= 0).sum())))
+    torch.cuda.synchronize(dev)
+    dt = (time.perf_counter() - t0) / n_pairs
+    # stage split on the last pair
+    t = {}
+    a = time.perf_counter()
+    kps = [frontend.detect(im[0], max_kp) for im in pairs[-1]]
+    t['sift_detect_host_ms'] = 1e3 * (time.perf_counter() - a)
+    a = time.perf_counter()
+    patches = [frontend.extract_patches(k, frontend.gaussian_pyramid(im[0])) for k, im in zip(kps, pairs[-1])]
+    t['pyramid_patches_host_ms'] = 1e3 * (time.perf_counter() - a)
+    torch.cuda.synchronize(dev)
+    a = time.perf_counter()
+    descs = [frontend.describe(p, car, dev) for p in patches]
+    torch.cuda.synchronize(dev)
+    t['carhynet_gpu_ms'] = 1e3 * (time.perf_counter() - a)
+    data = {'device': dev, 'radius': 15, 'percentile': 2, 'min_size': 7, 'image0': pairs[-1][0], 'image1': pairs[-1][1]}
+    for s, (k, d) in enumerate(zip(kps, descs)):
+        data['keypoints%d' % s] = torch.tensor([x.pt for x in k], device=dev)[None]
+        data['scores%d' % s] = torch.tensor([x.response for x in k], device=dev)[None]
+        data['descriptors%d' % s] = torch.cat([d, d], 1).t()[None].contiguous()
+    with torch.no_grad():
+        matching(dict(data))
+    torch.cuda.synchronize(dev)
+    a = time.perf_counter()
+    for _ in range(5):
+        with torch.no_grad():
+            pred = matching(dict(data))
+        pred['matches0'].cpu()
+    t['matcher_gpu_ms'] = 1e3 * (time.perf_counter() - a) / 5
+    print(json.dumps({
+        'metric': 'pipeline_pairs_per_sec_800x600', 'value': 1.0 / dt, 'unit': UNIT, 'n_gpus': 1, 'steps': n_pairs,
+        'ms_per_pair': 1e3 * dt, 'higher_is_better': True, 'dtype': 'f32', 'data': 'synthetic',
+        'config': {'workload': 'BASELINE configs[2]: eval_homography-shaped pipeline, synthetic 800x600 colour image pairs, '
+                               'cv2 SIFT (max_keypoints %d) + 64->32 px patches on the host, random-init CAR_HyNet on the GPU, '
+                               'matcher with AGC r/p/m 15/2/7 and 20 Sinkhorn iterations; one caller, sequential pairs' % max_kp},
+        'kept_keypoints_and_matches': kept, 'stage_ms_last_pair': {k: round(v, 2) for k, v in t.items()},
+        'reference_published': '14.2-17.2 s per pair (README.md:116-120, unstated GPU, trained weights, all keypoints)'}))
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument('--gpus', type=int, default=1)
@@ -332,7 +425,18 @@ def main():
     ap.add_argument('--no-e2e', action='store_true')
     ap.add_argument('--prof-kernel', default='attention')
     ap.add_argument('--weights', default='random', choices=['random', 'damped'])
+    ap.add_argument('--pairs-per-launch', type=int, default=2,
+                    help='pairs stacked into one gims_forward_pairs call (shared GEMM / attention launches)')
+    ap.add_argument('--gemm-mode', default=None, choices=['simt', 'tf32', 'f16', 'bf16'],
+                    help='arithmetic of the dense contractions (default: f16 = fp16 hi+lo attention operands, fp32 parity); '
+                         'bf16 is the separately reported bf16 variant')
+    ap.add_argument('--pipeline', action='store_true',
+                    help='BASELINE configs[2]: eval_homography-shaped pipeline (synthetic 800x600 image pairs -> SIFT + '
+                         'patches on the host -> CAR-HyNet on the GPU -> matcher), the literal call of eval_homography.py:177')
     args = ap.parse_args()
+    if args.pipeline:
+        run_pipeline(args)
+        return
     METRIC = metric_name(args.kpts)
     adjust_sizes(args)
 
@@ -354,6 +458,10 @@ def main():
     if world > 1:
         dist.init_process_group('nccl', device_id=dev)
     L = _lib.lib()
+    if args.gemm_mode:
+        L.gims_set_gemm_mode(_lib.GEMM_MODES[args.gemm_mode])
+    gemm_mode_name = {0: 'simt (fp32 CUDA cores)', 1: 'tf32x3', 2: 'f16x2 attention operands + tf32x3 projections',
+                      3: 'bf16 attention operands + tf32x3 projections (bf16 variant, not fp32 parity)'}[L.gims_get_gemm_mode()]
 
     cfg = {'sinkhorn_iterations': 100, 'match_threshold': 0.2}
     matching = Matching(cfg)
@@ -371,7 +479,7 @@ def main():
                      'scores0': d['scores0'][0].to(dev), 'scores1': d['scores1'][0].to(dev),
                      'shape0': d['image0'].shape, 'shape1': d['image1'].shape})
     in_bytes = sum(v.numel() * 4 for k, v in pool[0].items() if torch.is_tensor(v))
-    runner = PairBatchRunner(gm, n_streams=args.streams)
+    runner = PairBatchRunner(gm, n_streams=args.streams, pairs_per_launch=args.pairs_per_launch)
     cursor = [0]
 
     def step():
@@ -416,7 +524,7 @@ def main():
         peaks = load_peaks()
         L.gims_profile_begin(_lib.PROF[args.prof_kernel], 4096)
         torch.cuda.synchronize(dev)
-        outs1 = PairBatchRunner(gm, n_streams=1).run([pool[i % len(pool)] for i in range(min(P, 4))])
+        outs1 = PairBatchRunner(gm, n_streams=1, pairs_per_launch=args.pairs_per_launch).run([pool[i % len(pool)] for i in range(2 * args.pairs_per_launch)])
         torch.cuda.synchronize(dev)
         tot, cnt = C.c_double(0), C.c_int(0)
         L.gims_profile_end(C.byref(tot), C.byref(cnt))
@@ -430,7 +538,7 @@ def main():
                 except Exception:      # noqa: BLE001 - the extra denominator is optional
                     tf32_peak = None
                 # QK^T + PV over 4 heads x 64: 4*D*nq*nk per image; averaged over self / cross layers
-                flops = 2.0 * 256 * (n0k + n1k) ** 2
+                flops = 2.0 * 256 * (n0k + n1k) ** 2 * args.pairs_per_launch     # one launch serves the whole batch
                 ach = flops / avg_s / 1e12
                 traffic, traffic_src = ncu_traffic('k_attention_tc') if args.kpts == 2048 else (None, None)
                 peak = peaks['bf16_tflops_sustained']
@@ -460,12 +568,12 @@ def main():
     # --- the other kernel classes, timed the same way (one stream, CUDA events inside the library) -------------
     other = {}
     if rank == 0 and roof is not None:
-        npair = min(P, 4)
+        npair = 2 * args.pairs_per_launch
         d = 256
         for cls in ('gemm', 'sinkhorn', 'cosine'):
             L.gims_profile_begin(_lib.PROF[cls], 4096)
             torch.cuda.synchronize(dev)
-            PairBatchRunner(gm, n_streams=1).run([pool[i % len(pool)] for i in range(npair)])
+            PairBatchRunner(gm, n_streams=1, pairs_per_launch=args.pairs_per_launch).run([pool[i % len(pool)] for i in range(npair)])
             torch.cuda.synchronize(dev)
             tot, cnt = C.c_double(0), C.c_int(0)
             L.gims_profile_end(C.byref(tot), C.byref(cnt))
@@ -556,6 +664,7 @@ def main():
             'ms_per_step': ms / args.steps, 'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None,
             'dtype': 'f32', 'data': 'synthetic',
             'config': base_config(args, world), 'kept_keypoints': counts[:2], 'sinkhorn_path': sink_path,
+            'arithmetic': gemm_mode_name,
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches) * world, 'gpu_launches_per_rank': int(launches),
             'roofline': roof, 'roofline_other': other,
             'pair_gflop': pair_flops(counts[0], counts[1]) / 1e9,

@@ -10,6 +10,7 @@ from .build import LIB_PATH
 MAX_LAYERS = 64
 MAX_KENC = 8
 MAX_KPTS = 16384
+MAX_BATCH = 4
 STATUS_EDGE_OVERFLOW = 1
 STATUS_SINKHORN_TIMEOUT = 2
 STATUS_ERROR_MASK = 0xff
@@ -122,6 +123,9 @@ SIGNATURES = {
     'gims_pair_workspace_bytes': (C.c_size_t, [C.c_void_p, C.c_int, C.c_int, C.c_int]),
     'gims_forward_pair': (C.c_int, [C.c_void_p, C.POINTER(PairInputs), C.POINTER(PairOutputs), C.c_void_p,
                                     C.c_size_t, C.c_void_p]),
+    'gims_batch_workspace_bytes': (C.c_size_t, [C.c_int, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int]),
+    'gims_forward_pairs': (C.c_int, [C.c_void_p, C.c_int, C.POINTER(PairInputs), C.POINTER(PairOutputs), C.c_void_p,
+                                     C.c_size_t, C.c_void_p]),
 }
 
 _LIB = None

@@ -184,13 +184,6 @@ extern "C" int gims_model_create(const gims_config* c, const float* packed, cons
 
 extern "C" void gims_model_destroy(gims_model* m) { delete m; }
 
-static Segs one_seg(int n_max, const int* n_dev) {
-  Segs s; s.base[0] = 0; s.base[1] = 0; s.nmax[0] = n_max; s.nmax[1] = 0; s.n_dev = n_dev; s.nseg = 1; return s;
-}
-static Segs two_segs(int n0_max, int n1_max, const int* n_dev) {
-  Segs s; s.base[0] = 0; s.base[1] = n0_max; s.nmax[0] = n0_max; s.nmax[1] = n1_max; s.n_dev = n_dev; s.nseg = 2; return s;
-}
-
 // Y = epi(A W^T + bias): tcgen05 3xTF32 kernel when the shape allows and the mode asks for it, else fp32 SIMT.
 static int gemm(const float* A0, int lda0, int K0, const float* A1, int lda1, int K1, const Wt& W, const float* bias,
                 const float* R, int ldr, float* Y, int ldy, int N, int relu, Segs s, int mode, cudaStream_t st) {
@@ -253,23 +246,28 @@ extern "C" int gims_kenc_forward(const gims_model* m, const float* kpts, int n_m
 }
 
 // a-11 + a-12 ----------------------------------------------------------------------------------
-// qkv (or its tf32 planes: 6 * rows * 256 + padding of the transposed V rows) | att | msg | hid
-extern "C" size_t gims_attn_scratch_floats(int rows) { return (size_t)rows * (6 * kD + kD + kD + 2 * kD) + 2 * 128 * kD; }
+// qkv (or its planes: 6 * rows * 256 floats + padding of the transposed V rows) | att | msg | hid
+static size_t attn_scratch_floats(size_t rows, int nseg) {
+  return rows * (6 * kD + kD + kD + 2 * kD) + (size_t)nseg * 128 * kD;
+}
+extern "C" size_t gims_attn_scratch_floats(int rows) { return attn_scratch_floats((size_t)rows, 2); }
 
-static int attn_layer(const gims_model* m, int layer, float* desc, int n0_max, int n1_max, const int* n_dev,
-                      float* scratch, unsigned* status_dev, int mode, cudaStream_t st) {
+// One AttentionalPropagation layer for every segment of `s` (2 per pair, pair-major: segment i ^ 1 is the other image)
+static int attn_layer(const gims_model* m, int layer, float* desc, const Segs& s, float* scratch, unsigned* status_dev,
+                      int mode, cudaStream_t st) {
   if (!m || layer < 0 || layer >= m->cfg.num_layers) { set_error("gims_attn_layer_forward: bad layer %d", layer); return GIMS_ERR_ARG; }
-  size_t rows = (size_t)n0_max + n1_max;
-  int ldv = attn_ldv(n0_max, n1_max);      // <= rows + 126
+  if (s.nseg < 2 || (s.nseg & 1)) { set_error("gims_attn_layer_forward: segments must come in pairs"); return GIMS_ERR_ARG; }
+  const size_t rows = (size_t)segs_rows(s);
   float* qkv = scratch;                    // [rows][768]  (SIMT)  |  Qp, Kp, Vt planes (tensor cores)
-  float* att = qkv + rows * 6 * kD + 2 * 128 * kD;   // [rows][256]
+  float* att = qkv + rows * 6 * kD + (size_t)s.nseg * 128 * kD;   // [rows][256]
   float* msg = att + rows * kD;            // [rows][256]
   float* hid = msg + rows * kD;            // [rows][512]
-  Segs s = two_segs(n0_max, n1_max, n_dev);
+  const int cross = m->cfg.layer_is_cross[layer];
   if (mode != GIMS_GEMM_SIMT) {
     QkvPlanes pl;
-    pl.qp = qkv; pl.kp = pl.qp + 2 * rows * kD; pl.vt = static_cast<float*>(pl.kp) + 2 * rows * kD; pl.ldv = ldv;
-    pl.vbase1 = attn_vbase1(n0_max);
+    pl.qp = qkv; pl.kp = pl.qp + 2 * rows * kD; pl.vt = static_cast<float*>(pl.kp) + 2 * rows * kD;
+    pl.ldv = attn_vt_layout(s, pl.vbase);  // <= rows + 63 * nseg
+    for (int i = s.nseg; i < kMaxSegs; ++i) pl.vbase[i] = 0;
     pl.fmt = mode == GIMS_GEMM_TC_F16 ? 0 : (mode == GIMS_GEMM_BF16 ? 1 : -1);
     pl.planes = mode == GIMS_GEMM_BF16 ? 1 : 2;
     pl.status = status_dev;
@@ -277,11 +275,11 @@ static int attn_layer(const gims_model* m, int layer, float* desc, int n0_max, i
     g.A0 = desc; g.lda0 = kD; g.K0 = kD; g.A1 = nullptr; g.lda1 = 0; g.K1 = 0; g.W = m->wqkv[layer].w;
     g.bias = m->bqkv[layer]; g.R = nullptr; g.ldr = 0; g.Y = nullptr; g.ldy = 0; g.N = 3 * kD; g.relu = 0; g.segs = s;
     GIMS_TRY(launch_gemm_tc(g, m->wqkv[layer].hi, m->wqkv[layer].lo, st, &pl));
-    if (pl.fmt >= 0) GIMS_TRY(launch_attention_f16(pl, att, n0_max, n1_max, n_dev, m->cfg.layer_is_cross[layer], st));
-    else             GIMS_TRY(launch_attention_tc(pl, att, n0_max, n1_max, n_dev, m->cfg.layer_is_cross[layer], st));
+    if (pl.fmt >= 0) GIMS_TRY(launch_attention_f16(pl, att, s, cross, st));
+    else             GIMS_TRY(launch_attention_tc(pl, att, s, cross, st));
   } else {
     GIMS_TRY(gemm(desc, kD, kD, nullptr, 0, 0, m->wqkv[layer], m->bqkv[layer], nullptr, 0, qkv, 3 * kD, 3 * kD, 0, s, mode, st));
-    GIMS_TRY(launch_attention(qkv, att, n0_max, n1_max, n_dev, m->cfg.layer_is_cross[layer], st));
+    GIMS_TRY(launch_attention(qkv, att, s, cross, st));
   }
   (void)msg;   // the merge conv is composed into W1 at pack time
   GIMS_TRY(gemm(desc, kD, kD, att, kD, kD, m->w1[layer], m->b1[layer], nullptr, 0, hid, 2 * kD, 2 * kD, 1, s, mode, st));
@@ -290,15 +288,16 @@ static int attn_layer(const gims_model* m, int layer, float* desc, int n0_max, i
 }
 extern "C" int gims_attn_layer_forward(const gims_model* m, int layer, float* desc, int n0_max, int n1_max,
                                        const int* n_dev, float* scratch, unsigned* status_dev, void* stream) {
-  return attn_layer(m, layer, desc, n0_max, n1_max, n_dev, scratch, status_dev, g_gemm_mode.load(), static_cast<cudaStream_t>(stream));
+  return attn_layer(m, layer, desc, two_segs(n0_max, n1_max, n_dev), scratch, status_dev, g_gemm_mode.load(),
+                    static_cast<cudaStream_t>(stream));
 }
 
 // a-13 -----------------------------------------------------------------------------------------
-static int final_scores(const gims_model* m, const float* desc, int n0_max, int n1_max, const int* n_dev, float* mdesc,
-                        float* couplings, float* scratch, int mode, cudaStream_t st) {
-  if (!m) { set_error("gims_final_scores: null model"); return GIMS_ERR_ARG; }
-  Segs s = two_segs(n0_max, n1_max, n_dev);
-  GIMS_TRY(gemm(desc, kD, kD, nullptr, 0, 0, m->wfinal, m->bfinal, nullptr, 0, mdesc, kD, kD, 0, s, mode, st));
+static int final_proj(const gims_model* m, const float* desc, const Segs& s, float* mdesc, int mode, cudaStream_t st) {
+  return gemm(desc, kD, kD, nullptr, 0, 0, m->wfinal, m->bfinal, nullptr, 0, mdesc, kD, kD, 0, s, mode, st);
+}
+static int score_matrix(const gims_model* m, const float* mdesc, int n0_max, int n1_max, const int* n_dev, float* couplings,
+                        float* scratch, int mode, cudaStream_t st) {
   if (mode != GIMS_GEMM_SIMT && scratch) {
     GIMS_TRY(launch_score_gemm_tc(mdesc, n0_max, n1_max, n_dev, scratch, couplings, st));
     GIMS_TRY(launch_score_border(n0_max, n1_max, n_dev, m->bin_score, couplings, st));
@@ -306,6 +305,12 @@ static int final_scores(const gims_model* m, const float* desc, int n0_max, int 
     GIMS_TRY(launch_score_gemm(mdesc, n0_max, n1_max, n_dev, m->bin_score, couplings, st));
   }
   return GIMS_OK;
+}
+static int final_scores(const gims_model* m, const float* desc, int n0_max, int n1_max, const int* n_dev, float* mdesc,
+                        float* couplings, float* scratch, int mode, cudaStream_t st) {
+  if (!m) { set_error("gims_final_scores: null model"); return GIMS_ERR_ARG; }
+  GIMS_TRY(final_proj(m, desc, two_segs(n0_max, n1_max, n_dev), mdesc, mode, st));
+  return score_matrix(m, mdesc, n0_max, n1_max, n_dev, couplings, scratch, mode, st);
 }
 extern "C" int gims_final_scores(const gims_model* m, const float* desc, int n0_max, int n1_max, const int* n_dev,
                                  float* mdesc, float* couplings, float* scratch, void* stream) {
@@ -335,47 +340,68 @@ extern "C" int gims_split_tf32(const float* x, float* hi, float* lo, size_t n, v
   return launch_split_planes(x, hi, lo, n, static_cast<cudaStream_t>(stream));
 }
 
-// whole pair -----------------------------------------------------------------------------------
 namespace {
-struct PairWs {
+__global__ void k_or_status(const unsigned* __restrict__ src, unsigned* __restrict__ dst, unsigned mask) {
+  const unsigned v = *src & mask;
+  if (v) atomicOr(dst, v);
+}
+int launch_or_status(const unsigned* src, unsigned* dst, unsigned mask, cudaStream_t st) {
+  k_or_status<<<1, 1, 0, st>>>(src, dst, mask);
+  GIMS_LAUNCH_OK();
+  return GIMS_OK;
+}
+}  // namespace
+
+// whole pairs ----------------------------------------------------------------------------------
+// A batch of up to GIMS_MAX_BATCH pairs goes through the dense stages TOGETHER: the rows of all images are stacked in one
+// activation buffer (image 0 of pair 0, image 1 of pair 0, image 0 of pair 1, ...), so that each projection GEMM and each
+// attention layer is ONE launch over all of them (2 P row segments).  The graph stages, the score matrix and the Sinkhorn
+// kernel run per pair on the same stream and share one scratch area each.
+namespace {
+struct BatchWs {
   void* agc;        size_t agc_bytes;
   float* sage_out;  // [rows][256]
   float* desc;      // [rows][256]
-  float* scratch;   // attention scratch (also SAGE / kenc scratch)
+  float* mdesc;     // [rows][256]
+  float* scratch;   // attention scratch (also SAGE / kenc / score-plane scratch)
   float* couplings;
   void* sink;       size_t sink_bytes;
 };
-size_t carve_pair(PairWs& w, void* base, size_t cap, int n0, int n1, int edge_cap) {
+size_t carve_batch(BatchWs& w, void* base, size_t cap, int n_pairs, const int* n0, const int* n1, int edge_cap) {
   Arena a(base, cap);
-  size_t rows = (size_t)n0 + n1;
-  int nmax = n0 > n1 ? n0 : n1;
+  size_t rows = 0, coup = 0, sink = 0;
+  int nmax = 0;
+  for (int p = 0; p < n_pairs; ++p) {
+    rows += (size_t)n0[p] + n1[p];
+    nmax = n0[p] > nmax ? n0[p] : nmax; nmax = n1[p] > nmax ? n1[p] : nmax;
+    size_t c = (size_t)(n0[p] + 1) * coup_ld(n1[p]);
+    coup = c > coup ? c : coup;
+    size_t sb = gims_sinkhorn_workspace_bytes(n0[p], n1[p]);
+    sink = sb > sink ? sb : sink;
+  }
   w.agc_bytes = gims_agc_workspace_bytes(nmax, edge_cap);
   w.agc = a.take<char>(w.agc_bytes);
   w.sage_out = a.take<float>(rows * kD);
   w.desc = a.take<float>(rows * kD);
-  w.scratch = a.take<float>(gims_attn_scratch_floats((int)rows));
-  w.couplings = a.take<float>((size_t)(n0 + 1) * coup_ld(n1));
-  w.sink_bytes = gims_sinkhorn_workspace_bytes(n0, n1);
-  w.sink = a.take<char>(w.sink_bytes);
+  w.mdesc = a.take<float>(rows * kD);
+  w.scratch = a.take<float>(attn_scratch_floats(rows, 2 * n_pairs));
+  w.couplings = a.take<float>(coup);
+  w.sink_bytes = sink;
+  w.sink = a.take<char>(sink);
   return align_up(a.off, 256);
 }
 __global__ void k_copy_rows(const float* __restrict__ src, float* __restrict__ dst, size_t n4) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n4) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
 }
-}  // namespace
-
-extern "C" size_t gims_pair_workspace_bytes(const gims_model* m, int n0, int n1, int edge_cap) {
-  (void)m;
-  PairWs w;
-  return carve_pair(w, nullptr, 0, n0, n1, edge_cap);
+int copy_rows(const float* src, float* dst, size_t floats, cudaStream_t st) {
+  k_copy_rows<<<(unsigned)((floats / 4 + 255) / 256), 256, 0, st>>>(src, dst, floats / 4);
+  GIMS_LAUNCH_OK();
+  return GIMS_OK;
 }
 
-extern "C" int gims_forward_pair(const gims_model* m, const gims_pair_inputs* in, const gims_pair_outputs* o,
-                                 void* workspace, size_t workspace_bytes, void* stream) {
-  cudaStream_t st = static_cast<cudaStream_t>(stream);
-  if (!m || !in || !o || !workspace) { set_error("gims_forward_pair: null argument"); return GIMS_ERR_ARG; }
-  int n0 = in->n[0], n1 = in->n[1];
+int validate_pair(const gims_pair_inputs* in, const gims_pair_outputs* o) {
+  const int n0 = in->n[0], n1 = in->n[1];
   // validate everything BEFORE the first launch: a late error would leave half a forward enqueued
   if (n0 < 2 || n1 < 2 || n0 > GIMS_MAX_KPTS || n1 > GIMS_MAX_KPTS) {
     set_error("gims_forward_pair: keypoint counts (%d, %d) outside [2, %d]", n0, n1, GIMS_MAX_KPTS);
@@ -402,44 +428,97 @@ extern "C" int gims_forward_pair(const gims_model* m, const gims_pair_inputs* in
       return GIMS_ERR_ARG;
     }
   }
-  PairWs w;
-  size_t need = carve_pair(w, workspace, workspace_bytes, n0, n1, in->edge_cap);
-  if (need > workspace_bytes) { set_error("gims_forward_pair: workspace %zu < %zu", workspace_bytes, need); return GIMS_ERR_WORKSPACE; }
-  size_t rows = (size_t)n0 + n1;
-  const int mode = in->gemm_mode > 0 ? in->gemm_mode - 1 : g_gemm_mode.load();
-  if (mode < GIMS_GEMM_SIMT || mode > GIMS_GEMM_BF16) { set_error("gims_forward_pair: gemm_mode %d", in->gemm_mode); return GIMS_ERR_ARG; }
-  GIMS_CUDA_OK(cudaMemsetAsync(o->status_dev, 0, sizeof(unsigned), st));
-  // a-1 .. a-7: graphs + pruning, both images (gmatcher.py:233-252)
-  for (int s = 0; s < 2; ++s) {
-    GIMS_TRY(gims_agc_build(in->kpts[s], in->desc[s], in->desc_channel_major, in->scores[s], in->n[s], in->radius,
-                            in->k_rank[s], in->min_size, w.agc, w.agc_bytes, o->kept_idx[s], o->n_kept_dev + s,
-                            o->csr_indptr[s], o->csr_indices[s], in->edge_cap, o->n_edges_dev + s, o->kpts[s], o->feat[s],
-                            o->scores[s], o->thr_dev + s, o->n_comp_dev + s, o->status_dev, stream));
-  }
-  // a-9, a-8, a-10: desc = SAGE(feat) + kenc(normalize(kpts))   (gmatcher.py:265-271)
-  for (int s = 0; s < 2; ++s) {
-    size_t base = s ? (size_t)n0 : 0;
-    GIMS_TRY(sage_fwd(m, o->feat[s], o->csr_indptr[s], o->csr_indices[s], in->n[s], o->n_kept_dev + s,
-                      w.sage_out + base * kD, w.scratch, mode, st));
-    GIMS_TRY(kenc_fwd(m, o->kpts[s], in->n[s], o->n_kept_dev + s, in->img_w[s], in->img_h[s],
-                      w.sage_out + base * kD, w.desc + base * kD, w.scratch, mode, st));
-  }
-  if (o->desc_in) {
-    k_copy_rows<<<(unsigned)((rows * kD / 4 + 255) / 256), 256, 0, st>>>(w.desc, o->desc_in, rows * kD / 4);
-    GIMS_LAUNCH_OK();
-  }
-  // a-11, a-12: attention stack (gmatcher.py:272)
-  for (int l = 0; l < m->cfg.num_layers; ++l)
-    GIMS_TRY(attn_layer(m, l, w.desc, n0, n1, o->n_kept_dev, w.scratch, o->status_dev, mode, st));
-  if (o->desc_gnn) {
-    k_copy_rows<<<(unsigned)((rows * kD / 4 + 255) / 256), 256, 0, st>>>(w.desc, o->desc_gnn, rows * kD / 4);
-    GIMS_LAUNCH_OK();
-  }
-  // a-13 .. a-15
-  float* coup = o->couplings ? o->couplings : w.couplings;
-  GIMS_TRY(final_scores(m, w.desc, n0, n1, o->n_kept_dev, o->mdesc, coup, w.scratch, mode, st));
-  GIMS_TRY(gims_sinkhorn_match(coup, coup_ld(n1), n0, n1, o->n_kept_dev, m->cfg.sinkhorn_iterations, m->cfg.match_threshold, w.sink,
-                               w.sink_bytes, o->u, o->v, o->indices[0], o->indices[1], o->matches[0], o->matches[1],
-                               o->mscores[0], o->mscores[1], o->status_dev, stream));
   return GIMS_OK;
+}
+}  // namespace
+
+extern "C" size_t gims_batch_workspace_bytes(int n_pairs, const int* n0_host, const int* n1_host, int edge_cap) {
+  if (n_pairs < 1 || n_pairs > GIMS_MAX_BATCH || !n0_host || !n1_host) return 0;
+  BatchWs w;
+  return carve_batch(w, nullptr, 0, n_pairs, n0_host, n1_host, edge_cap);
+}
+
+extern "C" size_t gims_pair_workspace_bytes(const gims_model* m, int n0, int n1, int edge_cap) {
+  (void)m;
+  return gims_batch_workspace_bytes(1, &n0, &n1, edge_cap);
+}
+
+extern "C" int gims_forward_pairs(const gims_model* m, int n_pairs, const gims_pair_inputs* in, const gims_pair_outputs* out,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+  cudaStream_t st = static_cast<cudaStream_t>(stream);
+  if (!m || !in || !out || !workspace) { set_error("gims_forward_pairs: null argument"); return GIMS_ERR_ARG; }
+  if (n_pairs < 1 || n_pairs > GIMS_MAX_BATCH) { set_error("gims_forward_pairs: n_pairs %d outside [1, %d]", n_pairs, GIMS_MAX_BATCH); return GIMS_ERR_ARG; }
+  int n0[GIMS_MAX_BATCH], n1[GIMS_MAX_BATCH], edge_cap = 0;
+  const int mode = in[0].gemm_mode > 0 ? in[0].gemm_mode - 1 : g_gemm_mode.load();
+  if (mode < GIMS_GEMM_SIMT || mode > GIMS_GEMM_BF16) { set_error("gims_forward_pairs: gemm_mode %d", in[0].gemm_mode); return GIMS_ERR_ARG; }
+  for (int p = 0; p < n_pairs; ++p) {
+    GIMS_TRY(validate_pair(in + p, out + p));
+    if (in[p].gemm_mode != in[0].gemm_mode) { set_error("gims_forward_pairs: the pairs of a batch must share gemm_mode"); return GIMS_ERR_ARG; }
+    n0[p] = in[p].n[0]; n1[p] = in[p].n[1];
+    edge_cap = in[p].edge_cap > edge_cap ? in[p].edge_cap : edge_cap;
+  }
+  BatchWs w;
+  size_t need = carve_batch(w, workspace, workspace_bytes, n_pairs, n0, n1, edge_cap);
+  if (need > workspace_bytes) { set_error("gims_forward_pairs: workspace %zu < %zu", workspace_bytes, need); return GIMS_ERR_WORKSPACE; }
+  // the stacked row segments: 2 p = image 0 of pair p, 2 p + 1 = image 1
+  Segs segs = {};
+  segs.nseg = 2 * n_pairs;
+  int row = 0;
+  for (int p = 0; p < n_pairs; ++p)
+    for (int s = 0; s < 2; ++s) {
+      segs.base[2 * p + s] = row;
+      segs.nmax[2 * p + s] = in[p].n[s];
+      segs.n_ptr[2 * p + s] = out[p].n_kept_dev + s;
+      row += in[p].n[s];
+    }
+  const size_t rows = (size_t)row;
+  // a-1 .. a-7: graphs + pruning (gmatcher.py:233-252), then a-9, a-8, a-10: desc = SAGE(feat) + kenc(normalize(kpts))
+  // (gmatcher.py:265-271), image by image into the stacked buffer
+  for (int p = 0; p < n_pairs; ++p) {
+    const gims_pair_inputs* ip = in + p;
+    const gims_pair_outputs* o = out + p;
+    GIMS_CUDA_OK(cudaMemsetAsync(o->status_dev, 0, sizeof(unsigned), st));
+    for (int s = 0; s < 2; ++s) {
+      GIMS_TRY(gims_agc_build(ip->kpts[s], ip->desc[s], ip->desc_channel_major, ip->scores[s], ip->n[s], ip->radius,
+                              ip->k_rank[s], ip->min_size, w.agc, w.agc_bytes, o->kept_idx[s], o->n_kept_dev + s,
+                              o->csr_indptr[s], o->csr_indices[s], ip->edge_cap, o->n_edges_dev + s, o->kpts[s], o->feat[s],
+                              o->scores[s], o->thr_dev + s, o->n_comp_dev + s, o->status_dev, stream));
+      const size_t base = (size_t)segs.base[2 * p + s];
+      GIMS_TRY(sage_fwd(m, o->feat[s], o->csr_indptr[s], o->csr_indices[s], ip->n[s], o->n_kept_dev + s,
+                        w.sage_out + base * kD, w.scratch, mode, st));
+      GIMS_TRY(kenc_fwd(m, o->kpts[s], ip->n[s], o->n_kept_dev + s, ip->img_w[s], ip->img_h[s],
+                        w.sage_out + base * kD, w.desc + base * kD, w.scratch, mode, st));
+    }
+    if (o->desc_in) {
+      const size_t base = (size_t)segs.base[2 * p], cnt = (size_t)ip->n[0] + ip->n[1];
+      GIMS_TRY(copy_rows(w.desc + base * kD, o->desc_in, cnt * kD, st));
+    }
+  }
+  // a-11, a-12: attention stack (gmatcher.py:272) — one launch per stage and layer for the whole batch.  The fp16-range
+  // flag of the batch is raised in pair 0's status word and copied to the others below.
+  for (int l = 0; l < m->cfg.num_layers; ++l)
+    GIMS_TRY(attn_layer(m, l, w.desc, segs, w.scratch, out[0].status_dev, mode, st));
+  // a-13: final_proj for every row at once
+  GIMS_TRY(final_proj(m, w.desc, segs, w.mdesc, mode, st));
+  (void)rows;
+  for (int p = 0; p < n_pairs; ++p) {
+    const gims_pair_inputs* ip = in + p;
+    const gims_pair_outputs* o = out + p;
+    const size_t base = (size_t)segs.base[2 * p], cnt = (size_t)ip->n[0] + ip->n[1];
+    if (o->desc_gnn) GIMS_TRY(copy_rows(w.desc + base * kD, o->desc_gnn, cnt * kD, st));
+    GIMS_TRY(copy_rows(w.mdesc + base * kD, o->mdesc, cnt * kD, st));
+    if (p > 0) GIMS_TRY(launch_or_status(out[0].status_dev, o->status_dev, GIMS_STATUS_FP16_RANGE, st));
+    // a-13 .. a-15 per pair
+    float* coup = o->couplings ? o->couplings : w.couplings;
+    GIMS_TRY(score_matrix(m, w.mdesc + base * kD, ip->n[0], ip->n[1], o->n_kept_dev, coup, w.scratch, mode, st));
+    GIMS_TRY(gims_sinkhorn_match(coup, coup_ld(ip->n[1]), ip->n[0], ip->n[1], o->n_kept_dev, m->cfg.sinkhorn_iterations,
+                                 m->cfg.match_threshold, w.sink, w.sink_bytes, o->u, o->v, o->indices[0], o->indices[1],
+                                 o->matches[0], o->matches[1], o->mscores[0], o->mscores[1], o->status_dev, stream));
+  }
+  return GIMS_OK;
+}
+
+extern "C" int gims_forward_pair(const gims_model* m, const gims_pair_inputs* in, const gims_pair_outputs* o,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+  return gims_forward_pairs(m, 1, in, o, workspace, workspace_bytes, stream);
 }

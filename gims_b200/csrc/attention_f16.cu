@@ -76,7 +76,7 @@ struct Attn16Args {
   Segs segs;
   int cross;
   int rows_total;             // plane stride of Kp in rows
-  int vbase1;                 // first Vt key column of image 1
+  int vbase[kMaxSegs];        // first Vt key column of each segment
   unsigned* status;           // GIMS_STATUS_FP16_RANGE is OR-ed in on overflow (fp16 only); may be null
 };
 
@@ -98,7 +98,7 @@ k_attention_f16(const __grid_constant__ CUtensorMap mapK, const __grid_constant_
   extern __shared__ uint8_t smem_raw[];
   using Cfg = Cfg16<PLANES>;
   const int img = blockIdx.z, head = blockIdx.y;
-  const int src = a.cross ? 1 - img : img;
+  const int src = a.cross ? (img ^ 1) : img;
   // counts come from device memory; the shuffle makes them provably warp-uniform for the compiler, so that the
   // single-thread TMA / MMA loops below compile to uniform-datapath code (no per-operand R2UR moves)
   const int nq = __shfl_sync(0xffffffffu, seg_count(a.segs, img), 0);
@@ -214,7 +214,7 @@ k_attention_f16(const __grid_constant__ CUtensorMap mapK, const __grid_constant_
       auto load_v = [&](int j, int s) {                       // Vt box: 64 channels x 64 keys per plane
         mbar_arrive_expect_tx(&v_full[s], Cfg::kStageBytes);
         for (int pl = 0; pl < PLANES; ++pl)
-          tma_load_2d(v_smem + s * Cfg::kStageBytes + pl * kPlaneBytes, &mapVt, &v_full[s], (src ? a.vbase1 : 0) + j * TKV, pl * kD + head * HD);
+          tma_load_2d(v_smem + s * Cfg::kStageBytes + pl * kPlaneBytes, &mapVt, &v_full[s], a.vbase[src] + j * TKV, pl * kD + head * HD);
       };
       if (t == 0)
         for (int j = 0; j < kStages && j < ntiles; ++j) load_v(j, j);
@@ -404,9 +404,8 @@ int set_attention16_trace(long long* dev_buf) {
 }
 
 // planes as written by the 16-bit qkv-mode GEMM epilogue (QkvPlanes with fmt >= 0, common.cuh)
-int launch_attention_f16(const QkvPlanes& pl, float* out, int n0_max, int n1_max, const int* n_dev, int cross,
-                         cudaStream_t st) {
-  const int rows = n0_max + n1_max;
+int launch_attention_f16(const QkvPlanes& pl, float* out, const Segs& segs, int cross, cudaStream_t st) {
+  const int rows = segs_rows(segs);
   if (pl.fmt < 0 || (pl.planes != 1 && pl.planes != 2) || pl.ldv % 8) {
     set_error("launch_attention_f16: bad plane description (fmt %d, planes %d, ldv %d)", pl.fmt, pl.planes, pl.ldv);
     return GIMS_ERR_ARG;
@@ -417,14 +416,12 @@ int launch_attention_f16(const QkvPlanes& pl, float* out, int n0_max, int n1_max
   Attn16Args a;
   a.qp = pl.qp;
   a.out = out;
-  a.segs.base[0] = 0; a.segs.base[1] = n0_max; a.segs.nmax[0] = n0_max; a.segs.nmax[1] = n1_max; a.segs.n_dev = n_dev;
-  a.segs.nseg = 2;
+  a.segs = segs;
   a.cross = cross;
   a.rows_total = rows;
-  a.vbase1 = pl.vbase1;
+  for (int i = 0; i < kMaxSegs; ++i) a.vbase[i] = pl.vbase[i];
   a.status = pl.status;
-  const int nmax = n0_max > n1_max ? n0_max : n1_max;
-  dim3 grid(cdiv(nmax, NQT * TQ), kHeads, 2);
+  dim3 grid(cdiv(segs_nmax(segs), NQT * TQ), kHeads, segs.nseg);
   ProfScope prof(GIMS_PROF_ATTENTION, st);
   if (pl.planes == 2 && pl.fmt == 0) return launch16<2, 0>(mK, mV, a, grid, st);
   if (pl.planes == 1 && pl.fmt == 1) return launch16<1, 1>(mK, mV, a, grid, st);

@@ -27,7 +27,7 @@ __global__ void __launch_bounds__(256) k_attention_simt(const float* __restrict_
   extern __shared__ __align__(16) unsigned char smem_raw[];
   AttnSmem& sm = *reinterpret_cast<AttnSmem*>(smem_raw);
   int img = blockIdx.z, head = blockIdx.y;
-  int src = cross ? 1 - img : img;
+  int src = cross ? (img ^ 1) : img;
   int nq = seg_count(segs, img), nk = seg_count(segs, src);
   int q0 = blockIdx.x * TQ;
   if (q0 >= nq) return;
@@ -141,15 +141,11 @@ __global__ void __launch_bounds__(256) k_attention_simt(const float* __restrict_
 
 }  // namespace
 
-int launch_attention(const float* qkv, float* out, int n0_max, int n1_max, const int* n_dev, int cross,
-                     cudaStream_t st) {
+int launch_attention(const float* qkv, float* out, const Segs& s, int cross, cudaStream_t st) {
   GIMS_CUDA_OK(cudaFuncSetAttribute(k_attention_simt, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     (int)sizeof(AttnSmem)));
-  Segs s;
-  s.base[0] = 0; s.base[1] = n0_max; s.nmax[0] = n0_max; s.nmax[1] = n1_max; s.n_dev = n_dev; s.nseg = 2;
-  int nmax = n0_max > n1_max ? n0_max : n1_max;
   ProfScope prof(GIMS_PROF_ATTENTION, st);
-  k_attention_simt<<<dim3(cdiv(nmax, TQ), kHeads, 2), 256, sizeof(AttnSmem), st>>>(qkv, out, s, cross);
+  k_attention_simt<<<dim3(cdiv(segs_nmax(s), TQ), kHeads, s.nseg), 256, sizeof(AttnSmem), st>>>(qkv, out, s, cross);
   GIMS_LAUNCH_OK();
   return GIMS_OK;
 }

@@ -67,7 +67,7 @@ struct AttnTcArgs {
   Segs segs;
   int cross;
   int rows_total;             // plane stride of Qp/Kp in rows
-  int vbase1;                 // first Vt key column of image 1
+  int vbase[kMaxSegs];        // first Vt key column of each segment
 };
 
 // 2^x for x <= 0 (softmax arguments): one MUFU, flushes results below 2^-126 to zero
@@ -91,7 +91,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap mapK, const __grid_constant__
     g_attn_trace[40 * 8 + 2] = (long long)gt;
   }
   const int img = blockIdx.z, head = blockIdx.y;
-  const int src = a.cross ? 1 - img : img;
+  const int src = a.cross ? (img ^ 1) : img;
   // counts come from device memory; the shuffle makes them provably warp-uniform for the compiler, so that the
   // single-thread TMA / MMA loops below compile to uniform-datapath code (no per-operand R2UR moves)
   const int nq = __shfl_sync(0xffffffffu, seg_count(a.segs, img), 0);
@@ -151,7 +151,7 @@ k_attention_tc(const __grid_constant__ CUtensorMap mapK, const __grid_constant__
                         pl * a.rows_total + key0);
         if (++sk == Cfg::kStagesK) { sk = 0; phk ^= 1; }
       }
-      const int vcol0 = (src ? a.vbase1 : 0) + j * TKV;       // key column in the Vt planes (multiple of 64)
+      const int vcol0 = a.vbase[src] + j * TKV;       // key column in the Vt planes (multiple of 64)
       mbar_wait(&v_empty[sv], phv ^ 1);
       mbar_arrive_expect_tx(&v_full[sv], kKStageBytes);
       for (int pl = 0; pl < 2; ++pl)
@@ -390,9 +390,8 @@ int set_attention_trace(long long* dev_buf) {
 }
 
 // planes as written by the qkv-mode GEMM epilogue (QkvPlanes, common.cuh)
-int launch_attention_tc(const QkvPlanes& pl, float* out, int n0_max, int n1_max, const int* n_dev, int cross,
-                        cudaStream_t st) {
-  int rows = n0_max + n1_max;
+int launch_attention_tc(const QkvPlanes& pl, float* out, const Segs& segs, int cross, cudaStream_t st) {
+  int rows = segs_rows(segs);
   CUtensorMap mK, mV;
   // KT = 128 (GIMS_ATTN_KT=128) is correct but measured slower on B200 (56 vs 51 us per launch): the softmax warps need
   // ~1700 clk per 64-key tile, which is under the tensor pipe's 2170 clk at KT = 64 but not under its 1850 clk at 128.
@@ -402,13 +401,11 @@ int launch_attention_tc(const QkvPlanes& pl, float* out, int n0_max, int n1_max,
   AttnTcArgs a;
   a.qp = pl.qp;
   a.out = out;
-  a.segs.base[0] = 0; a.segs.base[1] = n0_max; a.segs.nmax[0] = n0_max; a.segs.nmax[1] = n1_max; a.segs.n_dev = n_dev;
-  a.segs.nseg = 2;
+  a.segs = segs;
   a.cross = cross;
   a.rows_total = rows;
-  a.vbase1 = pl.vbase1;
-  int nmax = n0_max > n1_max ? n0_max : n1_max;
-  dim3 grid(cdiv(nmax, TQ), kHeads, 2);
+  for (int i = 0; i < kMaxSegs; ++i) a.vbase[i] = pl.vbase[i];
+  dim3 grid(cdiv(segs_nmax(segs), TQ), kHeads, segs.nseg);
   ProfScope prof(GIMS_PROF_ATTENTION, st);
   if (kt == 64) {
     GIMS_CUDA_OK(cudaFuncSetAttribute(k_attention_tc<64>, cudaFuncAttributeMaxDynamicSharedMemorySize, AttnCfg<64>::kSmem));

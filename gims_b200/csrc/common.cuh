@@ -83,18 +83,34 @@ struct Arena {
   bool ok() const { return off <= cap; }
 };
 
-// Row segments of the two images inside one stacked activation buffer:
-// image s lives in rows [base[s], base[s] + count), count = n_dev ? n_dev[s] : nmax[s].
+// Row segments inside one stacked activation buffer: segment i lives in rows [base[i], base[i] + count),
+// count = n_ptr[i] ? min(*n_ptr[i], nmax[i]) : nmax[i] (live counts are device scalars).  A pair contributes two segments
+// (image 0, image 1); a batch of P pairs stacks 2 P of them, pair-major, so that segment s ^ 1 is the other image of the
+// same pair.
+constexpr int kMaxSegs = 8;          // up to 4 pairs per launch
 struct Segs {
-  int base[2];
-  int nmax[2];
-  const int* n_dev;   // may be null
+  int base[kMaxSegs];
+  int nmax[kMaxSegs];
+  const int* n_ptr[kMaxSegs];        // may be null
   int nseg;
 };
 
 __device__ __forceinline__ int seg_count(const Segs& s, int i) {
-  return s.n_dev ? min(s.n_dev[i], s.nmax[i]) : s.nmax[i];
+  return s.n_ptr[i] ? min(*s.n_ptr[i], s.nmax[i]) : s.nmax[i];
 }
+static inline Segs one_seg(int n_max, const int* n_dev) {
+  Segs s = {};
+  s.nmax[0] = n_max; s.n_ptr[0] = n_dev; s.nseg = 1;
+  return s;
+}
+static inline Segs two_segs(int n0_max, int n1_max, const int* n_dev) {
+  Segs s = {};
+  s.base[1] = n0_max; s.nmax[0] = n0_max; s.nmax[1] = n1_max;
+  s.n_ptr[0] = n_dev; s.n_ptr[1] = n_dev ? n_dev + 1 : nullptr; s.nseg = 2;
+  return s;
+}
+static inline int segs_rows(const Segs& s) { return s.nseg ? s.base[s.nseg - 1] + s.nmax[s.nseg - 1] : 0; }
+static inline int segs_nmax(const Segs& s) { int m = 0; for (int i = 0; i < s.nseg; ++i) m = s.nmax[i] > m ? s.nmax[i] : m; return m; }
 
 // ---------------------------------------------------------------------------------------------
 // internal (non-ABI) launchers shared between translation units
@@ -117,25 +133,27 @@ struct QkvPlanes {            // outputs of the QKV projection in the layout the
   float* qp;                  // [rows_total][256] fp32, scaled by log2(e)/8
   void* kp;                   // tf32: float [2][rows_total][256];  16-bit: [planes][rows_total][256]
   void* vt;                   // tf32: float [2][256][ldv];         16-bit: [planes][256][ldv]
-                              // key columns: image 0 at [0, n0), image 1 at [vbase1, vbase1 + n1)
+                              // key columns of segment s at [vbase[s], vbase[s] + n_s)
   int ldv;                    // multiple of 64
-  int vbase1;                 // round_up(n0_max, 64)
+  int vbase[kMaxSegs];        // first key column of segment s: sum of round_up(nmax, 64) of the segments before it
   int fmt;                    // -1: tf32 hi / lo planes (attention_tc.cu); 0: fp16, 1: bf16 (attention_f16.cu)
   int planes;                 // 16-bit: 2 = hi + lo (fp32-class), 1 = single plane (bf16 variant)
   unsigned* status;           // fp16: GIMS_STATUS_FP16_RANGE is OR-ed in when a value reaches 32768 (may be null)
 };
 int launch_gemm_tc(const GemmArgs& a, const float* w_hi, const float* w_lo, cudaStream_t st,
                    const QkvPlanes* qkv = nullptr);
-int launch_attention_tc(const QkvPlanes& pl, float* out, int n0_max, int n1_max, const int* n_dev, int cross,
-                        cudaStream_t st);
-int launch_attention_f16(const QkvPlanes& pl, float* out, int n0_max, int n1_max, const int* n_dev, int cross,
-                         cudaStream_t st);
+int launch_attention_tc(const QkvPlanes& pl, float* out, const Segs& segs, int cross, cudaStream_t st);
+int launch_attention_f16(const QkvPlanes& pl, float* out, const Segs& segs, int cross, cudaStream_t st);
 int set_attention_trace(long long* dev_buf);
 int set_gemm_trace(long long* dev_buf);
 // row pitch (floats) of the couplings matrix (n0_max+1) x (n1_max+1): rows start 16-byte aligned
 static inline int coup_ld(int n1_max) { return (n1_max + 1 + 3) & ~3; }
-static inline int attn_vbase1(int n0_max) { return (n0_max + 63) & ~63; }
-static inline int attn_ldv(int n0_max, int n1_max) { return attn_vbase1(n0_max) + ((n1_max + 63) & ~63); }
+// key-column layout of the transposed V planes: fills vbase[], returns ldv
+static inline int attn_vt_layout(const Segs& s, int* vbase) {
+  int c = 0;
+  for (int i = 0; i < s.nseg; ++i) { vbase[i] = c; c += (s.nmax[i] + 63) & ~63; }
+  return c;
+}
 int launch_score_gemm_tc(const float* mdesc, int n0_max, int n1_max, const int* n_dev, float* planes, float* couplings,
                          cudaStream_t st);
 int launch_split_planes(const float* x, float* hi, float* lo, size_t n, cudaStream_t st);
@@ -147,8 +165,7 @@ int launch_score_gemm(const float* mdesc, int n0_max, int n1_max, const int* n_d
                       float* couplings, cudaStream_t st);
 
 // flash attention over the stacked QKV buffer [rows][768] (Q|K|V, each head-major h*64+d)
-int launch_attention(const float* qkv, float* out, int n0_max, int n1_max, const int* n_dev, int cross,
-                     cudaStream_t st);
+int launch_attention(const float* qkv, float* out, const Segs& segs, int cross, cudaStream_t st);
 
 int launch_sage_aggregate(const float* src, int lds, int width, const int* indptr, const int* indices,
                           int n_max, const int* n_dev, const float* self_add, int ldself, const float* bias,

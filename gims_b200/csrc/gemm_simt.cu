@@ -30,7 +30,7 @@ struct GemmKernArgs {
   int relu;
   float scale;
   Segs segs;
-  int tiles0;               // row tiles of segment 0
+  int tile_end[kMaxSegs];   // cumulative number of row tiles up to and including segment s
 };
 
 template <int MODE>
@@ -40,8 +40,11 @@ __global__ void __launch_bounds__(256) k_gemm_simt(GemmKernArgs g) {
 
   int seg, tile;
   if (MODE == kModeScore) { seg = 0; tile = blockIdx.y; }
-  else if ((int)blockIdx.y < g.tiles0) { seg = 0; tile = blockIdx.y; }
-  else { seg = 1; tile = blockIdx.y - g.tiles0; }
+  else {
+    seg = 0;
+    while (seg + 1 < g.segs.nseg && (int)blockIdx.y >= g.tile_end[seg]) ++seg;
+    tile = blockIdx.y - (seg ? g.tile_end[seg - 1] : 0);
+  }
   int rows = seg_count(g.segs, seg);
   int ncols = g.N;
   if (MODE == kModeScore) ncols = seg_count(g.segs, 1);
@@ -166,8 +169,8 @@ int launch_gemm(const GemmArgs& a, cudaStream_t st) {
   g.A1 = a.A1; g.lda1 = a.lda1; g.K1 = a.K1;
   g.W = a.W; g.ldw = K; g.bias = a.bias; g.R = a.R; g.ldr = a.ldr; g.Y = a.Y; g.ldy = a.ldy;
   g.N = a.N; g.relu = a.relu; g.scale = 1.f; g.segs = a.segs;
-  g.tiles0 = cdiv(a.segs.nmax[0], BM);
-  int tiles = g.tiles0 + (a.segs.nseg > 1 ? cdiv(a.segs.nmax[1], BM) : 0);
+  int tiles = 0;
+  for (int i = 0; i < a.segs.nseg; ++i) { tiles += cdiv(a.segs.nmax[i], BM); g.tile_end[i] = tiles; }
   if (tiles == 0) return GIMS_OK;
   ProfScope prof(GIMS_PROF_GEMM, st);
   k_gemm_simt<kModeLinear><<<dim3(cdiv(a.N, BN), tiles), 256, 0, st>>>(g);
@@ -183,19 +186,17 @@ int launch_score_gemm(const float* mdesc, int n0_max, int n1_max, const int* n_d
   g.W = mdesc; g.ldw = kD; g.bias = nullptr; g.R = nullptr; g.ldr = 0;
   g.Y = couplings; g.ldy = coup_ld(n1_max);
   g.N = n1_max; g.relu = 0; g.scale = 0.0625f;    // 1/sqrt(256), exact
-  g.segs.base[0] = 0; g.segs.base[1] = n0_max; g.segs.nmax[0] = n0_max; g.segs.nmax[1] = n1_max;
-  g.segs.n_dev = n_dev; g.segs.nseg = 2;
-  g.tiles0 = cdiv(n0_max, BM);
+  g.segs = two_segs(n0_max, n1_max, n_dev);
+  g.tile_end[0] = cdiv(n0_max, BM);
   ProfScope prof(GIMS_PROF_SCORE, st);
-  k_gemm_simt<kModeScore><<<dim3(cdiv(n1_max, BN), g.tiles0), 256, 0, st>>>(g);
+  k_gemm_simt<kModeScore><<<dim3(cdiv(n1_max, BN), g.tile_end[0]), 256, 0, st>>>(g);
   GIMS_LAUNCH_OK();
   return launch_score_border(n0_max, n1_max, n_dev, bin_score, couplings, st);
 }
 
 int launch_score_border(int n0_max, int n1_max, const int* n_dev, const float* bin_score, float* couplings,
                         cudaStream_t st) {
-  Segs s;
-  s.base[0] = 0; s.base[1] = n0_max; s.nmax[0] = n0_max; s.nmax[1] = n1_max; s.n_dev = n_dev; s.nseg = 2;
+  Segs s = two_segs(n0_max, n1_max, n_dev);
   int m = (n0_max > n1_max ? n0_max : n1_max) + 1;
   k_score_border<<<cdiv(m, 256), 256, 0, st>>>(couplings, coup_ld(n1_max), s, bin_score);
   GIMS_LAUNCH_OK();

@@ -117,13 +117,13 @@ struct TcArgs {
   float scale;                   // score mode
   int score;                     // 1: Y is the couplings matrix (row-major, ldy = coup_ld(n1_max)), W rows = image-1 rows
   Segs segs;
-  int tiles0;
+  int tile_end[kMaxSegs];        // cumulative number of row tiles up to and including segment s
   // qkv mode (N = 768): instead of Y the epilogue writes the tf32 planes the attention kernel consumes:
   //   columns [0,256)   -> Qp [rows_total][256]     fp32 (acc + bias) * log2(e)/8
   //   columns [256,512) -> Kp [2][rows_total][256]
   //   columns [512,768) -> Vt [2][256][ldv]          transposed; rows beyond the live count are zero-filled
   int qkv;
-  float* qp; void* kp; void* vt; int ldv; int rows_total; int vbase1;
+  float* qp; void* kp; void* vt; int ldv; int rows_total; int vbase[kMaxSegs];
   unsigned* status;              // 16-bit planes: overflow flag
 };
 
@@ -147,8 +147,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
   // ---- tile coordinates (uniform per CTA) -------------------------------------------------------
   int seg, tile;
   if (MODE == 1) { seg = 0; tile = blockIdx.y; }
-  else if ((int)blockIdx.y < g.tiles0) { seg = 0; tile = blockIdx.y; }
-  else { seg = 1; tile = blockIdx.y - g.tiles0; }
+  else {
+    seg = 0;
+    while (seg + 1 < g.segs.nseg && (int)blockIdx.y >= g.tile_end[seg]) ++seg;
+    tile = blockIdx.y - (seg ? g.tile_end[seg - 1] : 0);
+  }
   const int rows = __shfl_sync(0xffffffffu, seg_count(g.segs, seg), 0);
   const int ncols = MODE == 1 ? __shfl_sync(0xffffffffu, seg_count(g.segs, 1), 0) : g.N;
   const int r0 = tile * BM, c0 = blockIdx.x * BN;
@@ -345,7 +348,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
         if (r < ((g.segs.nmax[seg] + 63) & ~63)) {             // never touch the other image's columns
           const bool row_ok = r < rows;
           const int cc256 = c & 255;
-          const size_t kcol = (size_t)(seg ? g.vbase1 : 0) + r;
+          const size_t kcol = (size_t)g.vbase[seg] + r;
           if (MODE == 2) {
             float* hi = static_cast<float*>(g.vt) + (size_t)cc256 * g.ldv + kcol;
             float* lo = hi + (size_t)kD * g.ldv;
@@ -539,7 +542,7 @@ int launch_gemm_tc(const GemmArgs& a, const float* w_hi, const float* w_lo, cuda
     set_error("launch_gemm_tc: unsupported shape K0=%d K1=%d N=%d", a.K0, a.K1, a.N);
     return GIMS_ERR_ARG;
   }
-  int total_rows = a.segs.nseg > 1 ? a.segs.base[1] + a.segs.nmax[1] : a.segs.nmax[0];
+  int total_rows = segs_rows(a.segs);
   int bn = pick_bn(a.N);
   if (qkv && (bn != 64 || qkv->fmt >= 0)) bn = 192;
   CUtensorMap mA0, mA1, mWh, mWl;
@@ -551,14 +554,16 @@ int launch_gemm_tc(const GemmArgs& a, const float* w_hi, const float* w_lo, cuda
   TcArgs g;
   g.K0 = a.K0; g.K1 = a.K1; g.bias = a.bias; g.R = a.R; g.ldr = a.ldr; g.Y = a.Y; g.ldy = a.ldy; g.N = a.N;
   g.relu = a.relu; g.scale = 1.f; g.score = 0; g.segs = a.segs;
-  g.qkv = 0; g.qp = nullptr; g.kp = g.vt = nullptr; g.ldv = 0; g.rows_total = total_rows; g.vbase1 = 0; g.status = nullptr;
+  g.qkv = 0; g.qp = nullptr; g.kp = g.vt = nullptr; g.ldv = 0; g.rows_total = total_rows; g.status = nullptr;
+  for (int i = 0; i < kMaxSegs; ++i) g.vbase[i] = 0;
   if (qkv) {
     if (a.N != 3 * kD || !a.bias) { set_error("launch_gemm_tc: qkv mode needs N = 768 and a bias"); return GIMS_ERR_ARG; }
-    g.qkv = 1; g.qp = qkv->qp; g.kp = qkv->kp; g.vt = qkv->vt; g.ldv = qkv->ldv; g.vbase1 = qkv->vbase1;
+    g.qkv = 1; g.qp = qkv->qp; g.kp = qkv->kp; g.vt = qkv->vt; g.ldv = qkv->ldv;
+    for (int i = 0; i < kMaxSegs; ++i) g.vbase[i] = qkv->vbase[i];
     g.status = qkv->status;
   }
-  g.tiles0 = cdiv(a.segs.nmax[0], BM);
-  int tiles = g.tiles0 + (a.segs.nseg > 1 ? cdiv(a.segs.nmax[1], BM) : 0);
+  int tiles = 0;
+  for (int i = 0; i < a.segs.nseg; ++i) { tiles += cdiv(a.segs.nmax[i], BM); g.tile_end[i] = tiles; }
   if (tiles == 0) return GIMS_OK;
   int ct = cdiv(a.N, bn);
   if (qkv) {
@@ -602,11 +607,11 @@ int launch_score_gemm_tc(const float* mdesc, int n0_max, int n1_max, const int* 
   TcArgs g;
   g.K0 = kD; g.K1 = 0; g.bias = nullptr; g.R = nullptr; g.ldr = 0; g.Y = couplings; g.ldy = coup_ld(n1_max); g.N = n1_max;
   g.relu = 0; g.scale = 0.0625f; g.score = 1;
-  g.qkv = 0; g.qp = nullptr; g.kp = g.vt = nullptr; g.ldv = 0; g.rows_total = (int)rows; g.vbase1 = 0; g.status = nullptr;
-  g.segs.base[0] = 0; g.segs.base[1] = n0_max; g.segs.nmax[0] = n0_max; g.segs.nmax[1] = n1_max; g.segs.n_dev = n_dev;
-  g.segs.nseg = 2;
-  g.tiles0 = cdiv(n0_max, BM);
-  return launch_tc<bn, 1>(mA, mA, mWh, mWl, g, cdiv(n1_max, bn), g.tiles0, GIMS_PROF_SCORE, st);
+  g.qkv = 0; g.qp = nullptr; g.kp = g.vt = nullptr; g.ldv = 0; g.rows_total = (int)rows; g.status = nullptr;
+  for (int i = 0; i < kMaxSegs; ++i) { g.vbase[i] = 0; g.tile_end[i] = 0; }
+  g.segs = two_segs(n0_max, n1_max, n_dev);
+  g.tile_end[0] = cdiv(n0_max, BM);
+  return launch_tc<bn, 1>(mA, mA, mWh, mWl, g, cdiv(n1_max, bn), g.tile_end[0], GIMS_PROF_SCORE, st);
 }
 
 }  // namespace gims

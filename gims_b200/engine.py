@@ -17,10 +17,11 @@ def shard_pairs(n_pairs, world_size, rank):
 class PairBatchRunner:
     """Runs batches of device-resident pairs through `GMatcher.run_pair` on a ring of streams."""
 
-    def __init__(self, gmatcher, n_streams=4):
+    def __init__(self, gmatcher, n_streams=4, pairs_per_launch=1):
         self.gm = gmatcher
         self.dev = gmatcher.bin_score.device
         self.streams = [torch.cuda.Stream(device=self.dev) for _ in range(n_streams)]
+        self.pairs_per_launch = max(1, int(pairs_per_launch))      # pairs stacked into one gims_forward_pairs call
         self._models = [gmatcher]
 
     def run(self, pairs, radius=25, percentile=7, min_size=8, keep=('matches0', 'mscores0', 'n_kept_dev')):
@@ -31,16 +32,19 @@ class PairBatchRunner:
         start = torch.cuda.Event()
         start.record(cur)
         outs = []
-        for i, p in enumerate(pairs):
+        ppl = self.pairs_per_launch
+        groups = [pairs[i:i + ppl] for i in range(0, len(pairs), ppl)]
+        for i, grp in enumerate(groups):
             s = self.streams[i % len(self.streams)]
             if i < len(self.streams):
                 s.wait_event(start)
+            items = [(p['keypoints0'], p['descriptors0'], p['scores0'], p['keypoints1'], p['descriptors1'], p['scores1'],
+                      p['shape0'], p['shape1']) for p in grp]
             with torch.cuda.stream(s):
-                r = self.gm.run_pair(p['keypoints0'], p['descriptors0'], p['scores0'], p['keypoints1'],
-                                     p['descriptors1'], p['scores1'], p['shape0'], p['shape1'], radius, percentile,
-                                     min_size, stream=s, slot=i % len(self.streams))
-            outs.append({k: r[k] for k in keep})
-            self._last = r
+                rs = self.gm.run_pairs(items, radius, percentile, min_size, stream=s, slot=i % len(self.streams))
+            for r in rs:
+                outs.append({k: r[k] for k in keep})
+                self._last = r
         self.join()
         return outs
 

@@ -1,0 +1,160 @@
+"""Front-end hand-off: keypoints + CAR-HyNet descriptors for `Matching.forward` when the caller
+passes images instead of keypoints — the call every script of the reference makes (eval_homography.py:177,
+eval_matches.py:152-156, tools/parameter_search.py:150-154).
+
+Mirrors `sift_forward` (utils/common.py:837-893): OpenCV SIFT detection, OpenCV-SIFT Gaussian pyramid
+(utils/library.py:234-293), one oriented 64x64 patch per keypoint taken from the pyramid level the keypoint was found on
+(utils/library.py:84-110), resized to 32x32 (INTER_AREA) and scaled to [0, 1], CAR-HyNet descriptor of every patch, the
+128-d descriptor duplicated to 256-d (utils/common.py:891).
+
+What is different from the reference, and why:
+  * detection and patch extraction stay on the host (OpenCV; they are the reference's own CPU stages, next row §8f-2);
+  * the descriptor network runs on the device the matcher lives on and its output NEVER leaves it: the reference
+    round-trips every batch through `.cpu().detach().numpy()` (carhynet/models.py:656-665) and uploads again at
+    utils/common.py:890-892.  The 128 -> 256 duplication and the (N, D) -> (D, N) layout of `descriptors{0,1}` are
+    views / one small device copy.
+The caller's `carhynet` object is used as it is: anything with a `.model` (the torch module) is run directly; an object
+that only offers the reference's `compute_sift(patches, kps, color)` is called through that method.
+"""
+import math
+
+import numpy as np
+import torch
+
+# the constants sift_forward hard-codes (utils/common.py:838-848)
+SIFT_CONFIG = dict(nfeatures=None, nOctaveLayers=3, contrastThreshold=0.001, edgeThreshold=80, sigma=1.6)
+PATCH_SUPPORT = 64      # ComputePatches(radius_size=64): side of the sampled window
+PATCH_SIZE = 32         # CAR-HyNet input
+FIRST_OCTAVE = -1       # OpenCV SIFT doubles the image first
+LAYERS = 3              # nOctaveLayers
+
+
+def _cv2():
+    import cv2
+    return cv2
+
+
+def detect(image, max_keypoints=-1):
+    """cv2 SIFT keypoints of one image (H, W[, 3]), strongest `max_keypoints` first if that limit is positive
+    (utils/common.py:851-861, 710-718)."""
+    cv2 = _cv2()
+    sift = cv2.SIFT_create(nfeatures=SIFT_CONFIG['nfeatures'], nOctaveLayers=SIFT_CONFIG['nOctaveLayers'],
+                           contrastThreshold=SIFT_CONFIG['contrastThreshold'], edgeThreshold=SIFT_CONFIG['edgeThreshold'],
+                           sigma=SIFT_CONFIG['sigma'])
+    kps = sift.detect(image, None)
+    if 0 < max_keypoints < len(kps):
+        order = np.argsort([k.response for k in kps])[::-1]
+        kps = [kps[i] for i in order[:max_keypoints]]
+    return kps
+
+
+def gaussian_pyramid(image):
+    """The scale space OpenCV's SIFT builds (utils/library.py:234-293): the image doubled (linear), then per octave
+    LAYERS + 3 levels, level i blurred from level i-1 with the incremental sigma, each next octave seeded by the
+    nearest-neighbour decimation of level LAYERS of the previous one.  Colour images keep their channels."""
+    cv2 = _cv2()
+    base = cv2.resize(image, (0, 0), fx=2, fy=2, interpolation=cv2.INTER_LINEAR_EXACT)
+    rows, cols = base.shape[:2]
+    n_octaves = int(np.round(np.log(np.float32(min(cols, rows))) / np.log(2.0) - 2) - FIRST_OCTAVE)
+    per_octave = LAYERS + 3
+    k = np.float32(2.0 ** (1.0 / LAYERS))
+    sigma0 = SIFT_CONFIG['sigma']
+    inc = [sigma0]
+    for i in range(1, per_octave):
+        prev = (k ** np.float32(i - 1)) * sigma0
+        total = prev * k
+        inc.append(math.sqrt(total * total - prev * prev))
+    levels = []
+    for o in range(n_octaves):
+        for i in range(per_octave):
+            if o == 0 and i == 0:
+                img = base
+            elif i == 0:
+                img = cv2.resize(levels[(o - 1) * per_octave + LAYERS], (0, 0), fx=0.5, fy=0.5, interpolation=cv2.INTER_NEAREST)
+            else:
+                img = cv2.GaussianBlur(levels[o * per_octave + i - 1], (0, 0), sigmaX=inc[i], sigmaY=inc[i])
+            levels.append(img)
+    return levels
+
+
+def _unpack_octave(kp):
+    """cv2 packs octave / layer into KeyPoint.octave (utils/library.py:16-35)."""
+    octave = kp.octave & 0xFF
+    layer = (kp.octave >> 8) & 0xFF
+    if octave >= 128:
+        octave -= 256
+    scale = 1.0 / (1 << octave) if octave >= 0 else float(1 << -octave)
+    return octave, layer, scale
+
+
+def extract_patches(kps, levels, support=PATCH_SUPPORT, out_size=PATCH_SIZE):
+    """(N, out_size, out_size[, C]) float32 in [0, 1]: for each keypoint the window of half-width size*scale/2 * (support-1)/2
+    around it on its own pyramid level, rotated by its orientation (bicubic, constant border), then area-resampled
+    (utils/library.py:84-110, utils/common.py:882-884)."""
+    cv2 = _cv2()
+    r = (support - 1) / 2
+    dim = int(2 * r + 1)
+    out = []
+    for kp in kps:
+        octave, layer, scale = _unpack_octave(kp)
+        step = kp.size * scale * 0.5
+        centre = np.array(kp.pt) * scale
+        angle = 360.0 - kp.angle
+        if abs(angle - 360.0) < 1.19209e-07:
+            angle = 0.0
+        phi = np.deg2rad(angle)
+        s, c = np.sin(phi), np.cos(phi)
+        rot = np.float32([[c, -s], [s, c]]) / step
+        shift = np.matmul(rot, centre)
+        affine = np.hstack([rot, [[r - shift[0]], [r - shift[1]]]])
+        level = levels[(octave - FIRST_OCTAVE) * (LAYERS + 3) + layer]
+        patch = cv2.warpAffine(level, affine, (dim, dim), flags=cv2.INTER_CUBIC, borderMode=cv2.BORDER_CONSTANT)
+        out.append(cv2.resize(patch.astype(np.float32), (out_size, out_size), interpolation=cv2.INTER_AREA))
+    if not out:
+        return np.zeros((0, out_size, out_size), dtype=np.float32)
+    return np.array(out) / 255.0
+
+
+def describe(patches, carhynet, device, batch_size=512):
+    """(N, 128) descriptors ON `device`.  `patches`: (N, 32, 32, 3) colour or (N, 32, 32) grey, float in [0, 1]."""
+    n = len(patches)
+    model = getattr(carhynet, 'model', None)
+    if not isinstance(model, torch.nn.Module) and isinstance(carhynet, torch.nn.Module):
+        model = carhynet
+    if model is None:
+        # only the reference's host interface is available (carhynet/models.py:667-670): use it, upload once
+        _, d = carhynet.compute_sift(patches, list(range(n)), patches.ndim == 4)
+        return torch.as_tensor(np.asarray(d, dtype=np.float32).reshape(n, -1), device=device)
+    batch_size = int(getattr(carhynet, 'batch_size', batch_size))
+    p = next(model.parameters(), None)
+    mdev = p.device if p is not None else torch.device(device)
+    x = torch.from_numpy(np.ascontiguousarray(patches, dtype=np.float32))
+    x = x.permute(0, 3, 1, 2) if x.dim() == 4 else x.unsqueeze(1)
+    outs = []
+    with torch.no_grad():
+        for i in range(0, n, batch_size):
+            chunk = x[i:i + batch_size]
+            chunk = chunk.pin_memory().to(mdev, non_blocking=True) if mdev.type == 'cuda' else chunk.to(mdev)
+            outs.append(model(chunk).reshape(chunk.shape[0], -1))
+    d = torch.cat(outs) if outs else torch.zeros(0, 128, device=mdev)
+    return d.to(device)
+
+
+def sift_forward(data, device):
+    """Same dict in / dict out as utils/common.py:837-893: `data['image']` iterates over images, `data['carhynet']` is the
+    caller's descriptor object; returns lists (one entry per image) of device tensors
+    `keypoints` (N, 2) fp32 pixel xy, `scores` (N,) fp32 SIFT responses, `descriptors` (256, N) fp32."""
+    max_kp = data.get('max_keypoints', -1)
+    kpts, scores, descs = [], [], []
+    for img in data['image']:
+        img = np.asarray(img)
+        kps = detect(img, max_kp)
+        levels = gaussian_pyramid(img)
+        patches = extract_patches(kps, levels)
+        d = describe(patches, data['carhynet'], device)                        # (N, 128), on the device
+        pts = np.array([k.pt for k in kps], dtype=np.float32).reshape(-1, 2)
+        resp = np.array([k.response for k in kps], dtype=np.float32)
+        kpts.append(torch.from_numpy(pts).to(device))
+        scores.append(torch.from_numpy(resp).to(device))
+        descs.append(torch.cat([d, d], dim=1).t().contiguous())                # utils/common.py:891
+    return {'keypoints': kpts, 'scores': scores, 'descriptors': descs}

@@ -263,35 +263,30 @@ class GMatcher(nn.Module):
             k = length - 1
         return k
 
-    def _workspace(self, n0, n1, edge_cap, dev, slot=0):
-        """One GROW-ONLY workspace per (device, stream slot): sized for the largest (n0, n1, edge_cap) seen so far on
-        that slot (rounded up, so that real data with a different keypoint count per pair does not reallocate on
-        every call).  The library carves it for the actual sizes of each call."""
+    def _workspace(self, sizes, edge_cap, dev, slot=0):
+        """One GROW-ONLY workspace per (device, stream slot), sized for the largest batch seen so far on that slot
+        (rounded up, so that real data with a different keypoint count per pair does not reallocate on every call).
+        `sizes`: [(n0, n1), ...] of the batch.  The library carves it for the actual sizes of each call."""
         key = (str(dev), slot)
+        n = len(sizes)
+        a0 = (C.c_int * n)(*[-(-s[0] // 256) * 256 for s in sizes])
+        a1 = (C.c_int * n)(*[-(-s[1] // 256) * 256 for s in sizes])
+        need = _lib.lib().gims_batch_workspace_bytes(n, a0, a1, int(edge_cap))
         with _HANDLE_LOCK:
-            ent = self._ws.get(key)
-            if ent is not None and ent[1] >= n0 and ent[2] >= n1 and ent[3] >= edge_cap:
-                return ent[0]
-            c0 = max(-(-n0 // 256) * 256, ent[1] if ent else 0)
-            c1 = max(-(-n1 // 256) * 256, ent[2] if ent else 0)
-            ce = max(edge_cap, ent[3] if ent else 0)
-            nbytes = _lib.lib().gims_pair_workspace_bytes(None, c0, c1, ce)
-            if ent is not None:
+            ws = self._ws.get(key)
+            if ws is not None and ws.numel() >= need:
+                return ws
+            if ws is not None:
                 self._ws[key] = None          # release the old block before taking the larger one
-                del ent
-            ws = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
-            self._ws[key] = [ws, c0, c1, ce]
+                del ws
+            ws = torch.zeros(need, dtype=torch.uint8, device=dev)
+            self._ws[key] = ws
             return ws
 
-    def run_pair(self, kpts0, desc0, scores0, kpts1, desc1, scores1, shape0, shape1, radius=25, percentile=7,
-                 min_size=8, edge_cap=None, debug=False, stream=None, slot=0, gemm_mode=None):
-        """One pair on the device.  kpts (N,2), desc (D,N) channel-major, scores (N,) CUDA fp32 tensors.
-        Enqueues everything on `stream` (default: current) and returns a dict of device tensors sized
-        for the INPUT counts plus `n_kept_dev`; nothing synchronises.  `forward` slices them."""
+    def _prepare(self, kpts0, desc0, scores0, kpts1, desc1, scores1, shape0, shape1, radius, percentile, min_size,
+                 edge_cap, debug, gemm_mode, dev):
+        """Output tensors + the C descriptors of one pair."""
         L = _lib.lib()
-        dev = self.bin_score.device          # host inputs are copied here (the H2D of the e2e path)
-        if dev.type != 'cuda':
-            raise _lib.GimsError('GMatcher must live on a CUDA device (no CPU path): call .to("cuda")')
         n0, n1 = int(kpts0.shape[0]), int(kpts1.shape[0])
         if n0 < 2 or n1 < 2:
             raise ValueError('each image needs at least 2 keypoints (the reference fails earlier, agc.py:439)')
@@ -365,20 +360,50 @@ class GMatcher(nn.Module):
         po.couplings = out['couplings_buf'].data_ptr() if debug else None
         po.desc_gnn = out['desc_gnn'].data_ptr() if debug else None
         po.desc_in = out['desc_in'].data_ptr() if debug else None
+        out['_inputs'] = keep          # keep the staged inputs alive until the stream has consumed them
+        out['edge_cap'] = edge_cap
+        return pin, po, out
+
+    def run_pairs(self, items, radius=25, percentile=7, min_size=8, edge_cap=None, debug=False, stream=None, slot=0,
+                  gemm_mode=None):
+        """A batch of up to `_lib.MAX_BATCH` pairs through ONE `gims_forward_pairs` call (every projection GEMM and
+        attention layer is one launch for the whole batch).  `items`: tuples (kpts0 (N,2), desc0 (D,N), scores0 (N,),
+        kpts1, desc1, scores1, shape0, shape1) of tensors (host tensors are copied to the device here).  Enqueues
+        everything on `stream` (default: current) and returns one dict of device tensors per pair, sized for the INPUT
+        counts, plus `n_kept_dev`; nothing synchronises."""
+        L = _lib.lib()
+        dev = self.bin_score.device          # host inputs are copied here (the H2D of the e2e path)
+        if dev.type != 'cuda':
+            raise _lib.GimsError('GMatcher must live on a CUDA device (no CPU path): call .to("cuda")')
+        n = len(items)
+        if not 1 <= n <= _lib.MAX_BATCH:
+            raise ValueError('a batch holds 1..%d pairs' % _lib.MAX_BATCH)
+        pins = (_lib.PairInputs * n)()
+        pos = (_lib.PairOutputs * n)()
+        outs = []
+        for i, it in enumerate(items):
+            pin, po, out = self._prepare(*it, radius, percentile, min_size, edge_cap, debug, gemm_mode, dev)
+            pins[i], pos[i] = pin, po
+            outs.append(out)
         st = stream if stream is not None else torch.cuda.current_stream(dev)
-        # one workspace per stream: calls on one stream are ordered, calls on different streams (several pairs in
+        # one workspace per stream: calls on one stream are ordered, calls on different streams (several batches in
         # flight, or several host threads calling forward() concurrently) must not share scratch memory
-        ws = self._workspace(n0, n1, edge_cap, dev, (slot, st.cuda_stream))
+        cap = max(o['edge_cap'] for o in outs)
+        ws = self._workspace([(int(it[0].shape[0]), int(it[3].shape[0])) for it in items], cap, dev, (slot, st.cuda_stream))
         model = self._acquire()
         try:
             with torch.cuda.device(dev):
-                _lib.check(L.gims_forward_pair(model, C.byref(pin), C.byref(po), _lib.ptr(ws), ws.numel(),
-                                               C.c_void_p(st.cuda_stream)), 'gims_forward_pair')
+                _lib.check(L.gims_forward_pairs(model, n, pins, pos, _lib.ptr(ws), ws.numel(),
+                                                C.c_void_p(st.cuda_stream)), 'gims_forward_pairs')
         finally:
             self._release(model)
-        out['_inputs'] = keep          # keep the staged inputs alive until the stream has consumed them
-        out['edge_cap'] = edge_cap
-        return out
+        return outs
+
+    def run_pair(self, kpts0, desc0, scores0, kpts1, desc1, scores1, shape0, shape1, radius=25, percentile=7,
+                 min_size=8, edge_cap=None, debug=False, stream=None, slot=0, gemm_mode=None):
+        """One pair on the device (see `run_pairs`).  kpts (N,2), desc (D,N) channel-major, scores (N,) fp32 tensors."""
+        return self.run_pairs([(kpts0, desc0, scores0, kpts1, desc1, scores1, shape0, shape1)], radius, percentile,
+                              min_size, edge_cap, debug, stream, slot, gemm_mode)[0]
 
     def forward(self, data, **kwargs):
         if kwargs.get('mode', 'test') == 'train':

@@ -1,15 +1,16 @@
 """Host-side mirror of the reference's `Matching` front-end (models/matching.py:8-30)."""
 import torch
 
+from .frontend import sift_forward
 from .gmatcher import GMatcher
 
 
 class Matching(torch.nn.Module):
     """Image Matching Frontend — same constructor and dict-in/dict-out call as the reference.
 
-    The SIFT + CAR-HyNet front-end (`sift_forward`, utils/common.py:837-893) that the reference runs
-    when `keypoints{0,1}` are absent is outside this build's scope (SURVEY.md §8f "next" row 1):
-    callers supply keypoints/descriptors/scores, which is the path matching.py:17,21 takes as well.
+    With `keypoints{0,1}` in `data` the matcher runs on them directly (matching.py:17,21); without, the images go
+    through `sift_forward` first (matching.py:18-24 -> utils/common.py:837-893; here gims_b200/frontend.py: OpenCV SIFT
+    and patches on the host, the caller's CAR-HyNet on the device, descriptors never leave it).
     """
 
     def __init__(self, config={}):
@@ -19,9 +20,12 @@ class Matching(torch.nn.Module):
 
     def forward(self, data):
         pred = {}
-        if 'keypoints0' not in data or 'keypoints1' not in data:
-            raise NotImplementedError('feature extraction (sift_forward + CAR-HyNet) is not part of the B200 hot '
-                                      'path; pass keypoints*/descriptors*/scores* as matching.py:17,21 allow')
+        for s in ('0', '1'):
+            if 'keypoints' + s not in data:
+                dev = data.get('device', self.gmodel.bin_score.device)
+                out = sift_forward({'image': data['image' + s], 'max_keypoints': self.max_keypoints,
+                                    'carhynet': data['carhynet']}, device=dev)
+                pred = {**pred, **{k + s: v for k, v in out.items()}}
         data = {**data, **pred}
         for k in data:
             if isinstance(data[k], (list, tuple)):

@@ -124,3 +124,33 @@ def make_state_dict(seed=0, peaked=False, damped=False, config=None):
             sd['gnn.layers.%d.mlp.3.weight' % l] = sd['gnn.layers.%d.mlp.3.weight' % l] * 0.05
         sd['final_proj.weight'] = sd['final_proj.weight'] * 64.0
     return sd
+
+
+def make_textured_image(height=600, width=800, seed=0, n_shapes=260, noise=0.6):
+    """Synthetic colour image (H, W, 3) uint8 with enough structure for a few thousand SIFT keypoints — stands in for
+    the COCO images of eval_homography.py (BASELINE configs[2]; there is no dataset offline)."""
+    import cv2
+    import numpy as np
+    rng = np.random.default_rng(seed)
+    img = np.full((height, width, 3), 40.0, dtype=np.float32)
+    for _ in range(n_shapes):
+        c = (int(rng.integers(0, width)), int(rng.integers(0, height)))
+        col = tuple(float(x) for x in rng.integers(30, 255, 3))
+        kind = rng.random()
+        if kind < 0.4:
+            cv2.circle(img, c, int(rng.integers(3, 28)), col, -1)
+        elif kind < 0.8:
+            cv2.rectangle(img, c, (c[0] + int(rng.integers(4, 60)), c[1] + int(rng.integers(4, 60))), col, -1)
+        else:
+            cv2.line(img, c, (int(rng.integers(0, width)), int(rng.integers(0, height))), col, int(rng.integers(1, 4)))
+    img = cv2.GaussianBlur(img, (0, 0), 0.8) + rng.normal(0, noise, img.shape).astype(np.float32)
+    return np.clip(img, 0, 255).astype(np.uint8)
+
+
+def warp_image(img, seed=0):
+    """The second image of a homography pair (eval_homography.py warps image0 with a random homography)."""
+    import cv2
+    import numpy as np
+    h, w = img.shape[:2]
+    hmat = _random_homography(torch.Generator().manual_seed(int(seed)), w, h).numpy()
+    return cv2.warpPerspective(img, hmat, (w, h)), hmat.astype(np.float32)

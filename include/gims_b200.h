@@ -46,6 +46,7 @@ extern "C" {
 #define GIMS_NUM_HEADS       4   /* hard-coded in the reference too (gmatcher.py:131) */
 #define GIMS_MAX_LAYERS     64
 #define GIMS_MAX_KENC        8
+#define GIMS_MAX_BATCH       4   /* pairs per gims_forward_pairs call */
 #define GIMS_MAX_KPTS    16384   /* per image: the AGC cosine matrix is n^2 fp32 (1 GiB), the Sinkhorn kernel keeps
                                     2(n+1) floats of potentials in shared memory */
 
@@ -246,6 +247,15 @@ typedef struct {
 GIMS_API size_t gims_pair_workspace_bytes(const gims_model* m, int n0, int n1, int edge_cap);
 GIMS_API int gims_forward_pair(const gims_model* m, const gims_pair_inputs* in_host, const gims_pair_outputs* out_host,
                       void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- a batch of pairs: same results as n_pairs calls of gims_forward_pair, but the rows of all images are stacked and
+ * every projection GEMM / attention layer is ONE launch for the whole batch (fewer, fuller launches).  `in_host` /
+ * `out_host` are arrays of n_pairs (<= GIMS_MAX_BATCH) descriptors; the pairs may have different sizes but must share
+ * gemm_mode.  `out_host[p].mdesc` holds image 1 at row in_host[p].n[0], as for a single pair.
+ * workspace: gims_batch_workspace_bytes(n_pairs, n0[], n1[], max edge_cap). */
+GIMS_API size_t gims_batch_workspace_bytes(int n_pairs, const int* n0_host, const int* n1_host, int edge_cap);
+GIMS_API int gims_forward_pairs(const gims_model* m, int n_pairs, const gims_pair_inputs* in_host,
+                       const gims_pair_outputs* out_host, void* workspace, size_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }
