@@ -540,20 +540,27 @@ def main():
                 # QK^T + PV over 4 heads x 64: 4*D*nq*nk per image; averaged over self / cross layers
                 flops = 2.0 * 256 * (n0k + n1k) ** 2 * args.pairs_per_launch     # one launch serves the whole batch
                 ach = flops / avg_s / 1e12
-                traffic, traffic_src = ncu_traffic('k_attention_tc') if args.kpts == 2048 else (None, None)
+                mode = L.gims_get_gemm_mode()
+                kname = 'k_attention_tc' if mode == _lib.GEMM_TC else 'k_attention_f16'
+                traffic, traffic_src = (None, None)
+                if args.kpts == 2048 and args.pairs_per_launch == 2 and mode == _lib.GEMM_TC_F16:
+                    traffic, traffic_src = ncu_traffic(kname)
                 peak = peaks['bf16_tflops_sustained']
-                # fp32 parity = 3 tf32 MMAs per product on a pipe whose tf32 rate is half the bf16 rate: an fp32-exact
-                # kernel cannot exceed 1/6 of the bf16 peak; `frac` is against the full bf16 peak as the contract asks
-                roof = {'kernel': 'k_attention_tc', 'bound': 'tensor', 'achieved': ach, 'peak': peak,
+                # fp32 parity = error-compensated products: 3 kind::f16 MMAs per product (fp16 hi + lo planes) -> an
+                # fp32-exact kernel cannot exceed 1/3 of the bf16 peak (1/6 with the 3xTF32 kernels, 1 for the bf16 variant);
+                # `frac` is against the full bf16 peak as the contract asks
+                mmas = {_lib.GEMM_TC: 6.0, _lib.GEMM_TC_F16: 3.0, _lib.GEMM_BF16: 1.0}.get(mode, 3.0)
+                roof = {'kernel': kname, 'bound': 'tensor', 'achieved': ach, 'peak': peak,
                         'unit': 'TFLOP/s', 'frac': ach / peak, 'traffic': traffic,
-                        'traffic_source': ('dram__bytes_read+write per launch, %s (algorithmic: Q 4.2 MB + K, Vt tf32 '
-                                           'planes 16.7 MB)' % traffic_src) if traffic else 'no ncu capture at this size',
-                        'ceiling_frac': 1.0 / 6.0, 'frac_of_ceiling': ach / peak * 6.0,
+                        'traffic_source': ('dram__bytes_read+write per launch, %s (algorithmic per 2-pair launch: Q fp32 8.4 MB + '
+                                           'K and Vt fp16 hi/lo planes 16.8 MB)' % traffic_src) if traffic else
+                                          'no ncu capture for this configuration',
+                        'ceiling_frac': 1.0 / mmas, 'frac_of_ceiling': ach / peak * mmas,
                         'tf32_dense_tflops_measured': tf32_peak,
-                        'frac_of_measured_tf32_over_3': (ach / (tf32_peak / 3.0)) if tf32_peak else None,
-                        'ceiling_note': '3xTF32 error compensation (fp32 parity): 3 MMAs per product at the tf32 rate',
+                        'ceiling_note': '%d bf16-rate-equivalent MMAs per fp32 product (error compensation); tensor-pipe work '
+                                        'actually issued = achieved x %d = %.0f TFLOP/s' % (mmas, mmas, ach * mmas),
                         'peak_source': peaks['_source'] + ' bf16 sustained', 'launches_timed': cnt.value,
-                        'avg_launch_ms': avg_s * 1e3, 'flops_per_launch': flops}
+                        'avg_launch_ms': avg_s * 1e3, 'flops_per_launch': flops, 'pairs_per_launch': args.pairs_per_launch}
             elif args.prof_kernel == 'sinkhorn':
                 byts = 4.0 * (n0k + 1) * (n1k + 1)
                 ach = byts / avg_s / 1e9
