@@ -108,8 +108,8 @@ SIGNATURES = {
     'gims_set_gemm_mode': (C.c_int, [C.c_int]),
     'gims_get_gemm_mode': (C.c_int, []),
     'gims_linear': (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
-                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_int, C.c_int,
-                              C.c_int, C.c_void_p, C.c_int, C.c_void_p]),
+                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_void_p,
+                              C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
     'gims_debug_attention_trace': (C.c_int, [C.c_void_p]),
     'gims_debug_gemm_trace': (C.c_int, [C.c_void_p]),
     'gims_debug_sinkhorn_trace': (C.c_int, [C.c_void_p]),

@@ -114,6 +114,10 @@ struct Wt {                    // one weight matrix [N][K]: fp32 + its tensor-co
   const float* w;
   const float* hi;             // tf32(W)
   const float* lo;             // W - tf32(W)
+  const void* h16;             // fp16(W * 2^e)
+  const void* l16;             // fp16(W * 2^e - h16)
+  const float* sinv;           // 2^-e
+  WPlanes planes() const { WPlanes p; p.hi32 = hi; p.lo32 = lo; p.h16 = h16; p.l16 = l16; p.sinv = sinv; return p; }
 };
 
 struct gims_model {
@@ -135,6 +139,11 @@ struct gims_model {
 };
 
 static std::atomic<int> g_gemm_mode{GIMS_GEMM_TC_F16};
+// projection GEMM operands: fp16 hi + lo in the f16 / bf16 modes (GIMS_GEMM_F16_PROJ=0 keeps them on 3xTF32)
+static int gemm_prec(int mode) {
+  static const int on = [] { const char* e = getenv("GIMS_GEMM_F16_PROJ"); return e ? atoi(e) : 1; }();
+  return (on && (mode == GIMS_GEMM_TC_F16 || mode == GIMS_GEMM_BF16)) ? 1 : 0;
+}
 
 extern "C" int gims_version(void) { return 100; }
 extern "C" const char* gims_last_error(void) { return g_err; }
@@ -149,8 +158,8 @@ extern "C" int gims_get_gemm_mode(void) { return g_gemm_mode.load(); }
 
 extern "C" int gims_packed_blob_count(const gims_config* c) {
   if (!c) return -1;
-  // every weight matrix contributes 3 blobs (W, W_hi, W_lo), every bias 1
-  return 1 + 4 * c->kenc_num + 4 * 3 + 12 * c->num_layers + 4;
+  // every weight matrix contributes 6 blobs (W, tf32 hi / lo, fp16 hi / lo, 2^-e), every bias 1
+  return 1 + 7 * c->kenc_num + 7 * 3 + 21 * c->num_layers + 7;
 }
 
 extern "C" int gims_model_create(const gims_config* c, const float* packed, const int64_t* off, int n_off,
@@ -169,7 +178,7 @@ extern "C" int gims_model_create(const gims_config* c, const float* packed, cons
   m->cfg = *c;
   int k = 0;
   auto next = [&]() { return packed + off[k++]; };
-  auto next_w = [&]() { Wt w; w.w = next(); w.hi = next(); w.lo = next(); return w; };
+  auto next_w = [&]() { Wt w; w.w = next(); w.hi = next(); w.lo = next(); w.h16 = next(); w.l16 = next(); w.sinv = next(); return w; };
   m->bin_score = next();
   for (int i = 0; i < c->kenc_num; ++i) { m->kenc_w[i] = next_w(); m->kenc_b[i] = next(); }
   for (int i = 0; i < 3; ++i) { m->sage_w[i] = next_w(); m->sage_b[i] = next(); }
@@ -184,14 +193,16 @@ extern "C" int gims_model_create(const gims_config* c, const float* packed, cons
 
 extern "C" void gims_model_destroy(gims_model* m) { delete m; }
 
-// Y = epi(A W^T + bias): tcgen05 3xTF32 kernel when the shape allows and the mode asks for it, else fp32 SIMT.
+// Y = epi(A W^T + bias): tcgen05 kernel when the shape allows and the mode asks for it (fp16 hi+lo operands in the f16 / bf16
+// modes, 3xTF32 otherwise), else fp32 SIMT.
 static int gemm(const float* A0, int lda0, int K0, const float* A1, int lda1, int K1, const Wt& W, const float* bias,
-                const float* R, int ldr, float* Y, int ldy, int N, int relu, Segs s, int mode, cudaStream_t st) {
+                const float* R, int ldr, float* Y, int ldy, int N, int relu, Segs s, int mode, cudaStream_t st,
+                unsigned* status = nullptr) {
   GemmArgs g;
   g.A0 = A0; g.lda0 = lda0; g.K0 = K0; g.A1 = A1; g.lda1 = lda1; g.K1 = K1; g.W = W.w; g.bias = bias;
-  g.R = R; g.ldr = ldr; g.Y = Y; g.ldy = ldy; g.N = N; g.relu = relu; g.segs = s;
+  g.R = R; g.ldr = ldr; g.Y = Y; g.ldy = ldy; g.N = N; g.relu = relu; g.segs = s; g.status = status;
   bool tc_ok = W.hi && W.lo && K0 % 32 == 0 && K1 % 32 == 0 && N % 32 == 0 && lda0 % 4 == 0 && (K1 == 0 || lda1 % 4 == 0);
-  if (mode != GIMS_GEMM_SIMT && tc_ok) return launch_gemm_tc(g, W.hi, W.lo, st);
+  if (mode != GIMS_GEMM_SIMT && tc_ok) return launch_gemm_tc(g, W.planes(), gemm_prec(mode), st);
   return launch_gemm(g, st);
 }
 
@@ -274,7 +285,8 @@ static int attn_layer(const gims_model* m, int layer, float* desc, const Segs& s
     GemmArgs g;
     g.A0 = desc; g.lda0 = kD; g.K0 = kD; g.A1 = nullptr; g.lda1 = 0; g.K1 = 0; g.W = m->wqkv[layer].w;
     g.bias = m->bqkv[layer]; g.R = nullptr; g.ldr = 0; g.Y = nullptr; g.ldy = 0; g.N = 3 * kD; g.relu = 0; g.segs = s;
-    GIMS_TRY(launch_gemm_tc(g, m->wqkv[layer].hi, m->wqkv[layer].lo, st, &pl));
+    g.status = status_dev;
+    GIMS_TRY(launch_gemm_tc(g, m->wqkv[layer].planes(), gemm_prec(mode), st, &pl));
     if (pl.fmt >= 0) GIMS_TRY(launch_attention_f16(pl, att, s, cross, st));
     else             GIMS_TRY(launch_attention_tc(pl, att, s, cross, st));
   } else {
@@ -282,8 +294,8 @@ static int attn_layer(const gims_model* m, int layer, float* desc, const Segs& s
     GIMS_TRY(launch_attention(qkv, att, s, cross, st));
   }
   (void)msg;   // the merge conv is composed into W1 at pack time
-  GIMS_TRY(gemm(desc, kD, kD, att, kD, kD, m->w1[layer], m->b1[layer], nullptr, 0, hid, 2 * kD, 2 * kD, 1, s, mode, st));
-  GIMS_TRY(gemm(hid, 2 * kD, 2 * kD, nullptr, 0, 0, m->w2[layer], m->b2[layer], desc, kD, desc, kD, kD, 0, s, mode, st));
+  GIMS_TRY(gemm(desc, kD, kD, att, kD, kD, m->w1[layer], m->b1[layer], nullptr, 0, hid, 2 * kD, 2 * kD, 1, s, mode, st, status_dev));
+  GIMS_TRY(gemm(hid, 2 * kD, 2 * kD, nullptr, 0, 0, m->w2[layer], m->b2[layer], desc, kD, desc, kD, kD, 0, s, mode, st, status_dev));
   return GIMS_OK;
 }
 extern "C" int gims_attn_layer_forward(const gims_model* m, int layer, float* desc, int n0_max, int n1_max,
@@ -293,13 +305,14 @@ extern "C" int gims_attn_layer_forward(const gims_model* m, int layer, float* de
 }
 
 // a-13 -----------------------------------------------------------------------------------------
-static int final_proj(const gims_model* m, const float* desc, const Segs& s, float* mdesc, int mode, cudaStream_t st) {
-  return gemm(desc, kD, kD, nullptr, 0, 0, m->wfinal, m->bfinal, nullptr, 0, mdesc, kD, kD, 0, s, mode, st);
+static int final_proj(const gims_model* m, const float* desc, const Segs& s, float* mdesc, int mode, cudaStream_t st,
+                      unsigned* status = nullptr) {
+  return gemm(desc, kD, kD, nullptr, 0, 0, m->wfinal, m->bfinal, nullptr, 0, mdesc, kD, kD, 0, s, mode, st, status);
 }
 static int score_matrix(const gims_model* m, const float* mdesc, int n0_max, int n1_max, const int* n_dev, float* couplings,
-                        float* scratch, int mode, cudaStream_t st) {
+                        float* scratch, int mode, cudaStream_t st, unsigned* status = nullptr) {
   if (mode != GIMS_GEMM_SIMT && scratch) {
-    GIMS_TRY(launch_score_gemm_tc(mdesc, n0_max, n1_max, n_dev, scratch, couplings, st));
+    GIMS_TRY(launch_score_gemm_tc(mdesc, n0_max, n1_max, n_dev, scratch, couplings, gemm_prec(mode), status, st));
     GIMS_TRY(launch_score_border(n0_max, n1_max, n_dev, m->bin_score, couplings, st));
   } else {
     GIMS_TRY(launch_score_gemm(mdesc, n0_max, n1_max, n_dev, m->bin_score, couplings, st));
@@ -319,15 +332,20 @@ extern "C" int gims_final_scores(const gims_model* m, const float* desc, int n0_
 
 // test / bring-up entry points ----------------------------------------------------------------
 extern "C" int gims_linear(const float* A0, int lda0, int K0, const float* A1, int lda1, int K1, const float* W,
-                           const float* W_hi, const float* W_lo, const float* bias, const float* R, int ldr, float* Y,
-                           int ldy, int N, int relu, int rows_max, const int* rows_dev, int mode, void* stream) {
+                           const float* W_hi, const float* W_lo, const void* W_h16, const void* W_l16, const float* W_sinv,
+                           const float* bias, const float* R, int ldr, float* Y,
+                           int ldy, int N, int relu, int rows_max, const int* rows_dev, int mode, unsigned* status_dev,
+                           void* stream) {
   cudaStream_t st = static_cast<cudaStream_t>(stream);
   GemmArgs g;
   g.A0 = A0; g.lda0 = lda0; g.K0 = K0; g.A1 = A1; g.lda1 = lda1; g.K1 = K1; g.W = W; g.bias = bias;
-  g.R = R; g.ldr = ldr; g.Y = Y; g.ldy = ldy; g.N = N; g.relu = relu; g.segs = one_seg(rows_max, rows_dev);
-  if (mode == GIMS_GEMM_TC) {
+  g.R = R; g.ldr = ldr; g.Y = Y; g.ldy = ldy; g.N = N; g.relu = relu; g.segs = one_seg(rows_max, rows_dev); g.status = status_dev;
+  if (mode != GIMS_GEMM_SIMT) {
     if (!W_hi || !W_lo) { set_error("gims_linear: tensor-core mode needs W_hi / W_lo"); return GIMS_ERR_ARG; }
-    return launch_gemm_tc(g, W_hi, W_lo, st);
+    WPlanes p; p.hi32 = W_hi; p.lo32 = W_lo; p.h16 = W_h16; p.l16 = W_l16; p.sinv = W_sinv;
+    const int prec = (mode == GIMS_GEMM_TC_F16 || mode == GIMS_GEMM_BF16) ? 1 : 0;
+    if (prec && (!W_h16 || !W_l16 || !W_sinv)) { set_error("gims_linear: fp16 mode needs W_h16 / W_l16 / W_sinv"); return GIMS_ERR_ARG; }
+    return launch_gemm_tc(g, p, prec, st);
   }
   return launch_gemm(g, st);
 }
@@ -499,7 +517,7 @@ extern "C" int gims_forward_pairs(const gims_model* m, int n_pairs, const gims_p
   for (int l = 0; l < m->cfg.num_layers; ++l)
     GIMS_TRY(attn_layer(m, l, w.desc, segs, w.scratch, out[0].status_dev, mode, st));
   // a-13: final_proj for every row at once
-  GIMS_TRY(final_proj(m, w.desc, segs, w.mdesc, mode, st));
+  GIMS_TRY(final_proj(m, w.desc, segs, w.mdesc, mode, st, out[0].status_dev));
   (void)rows;
   for (int p = 0; p < n_pairs; ++p) {
     const gims_pair_inputs* ip = in + p;
@@ -510,7 +528,7 @@ extern "C" int gims_forward_pairs(const gims_model* m, int n_pairs, const gims_p
     if (p > 0) GIMS_TRY(launch_or_status(out[0].status_dev, o->status_dev, GIMS_STATUS_FP16_RANGE, st));
     // a-13 .. a-15 per pair
     float* coup = o->couplings ? o->couplings : w.couplings;
-    GIMS_TRY(score_matrix(m, w.mdesc + base * kD, ip->n[0], ip->n[1], o->n_kept_dev, coup, w.scratch, mode, st));
+    GIMS_TRY(score_matrix(m, w.mdesc + base * kD, ip->n[0], ip->n[1], o->n_kept_dev, coup, w.scratch, mode, st, o->status_dev));
     GIMS_TRY(gims_sinkhorn_match(coup, coup_ld(ip->n[1]), ip->n[0], ip->n[1], o->n_kept_dev, m->cfg.sinkhorn_iterations,
                                  m->cfg.match_threshold, w.sink, w.sink_bytes, o->u, o->v, o->indices[0], o->indices[1],
                                  o->matches[0], o->matches[1], o->mscores[0], o->mscores[1], o->status_dev, stream));

@@ -125,8 +125,18 @@ struct GemmArgs {
   int N;
   int relu;
   Segs segs;
+  unsigned* status;                        // fp16-operand kernels: GIMS_STATUS_FP16_RANGE is OR-ed in (may be null)
 };
 int launch_gemm(const GemmArgs& a, cudaStream_t st);
+
+// tensor-core planes of one weight matrix [N][K] (gims_b200/packing.py)
+struct WPlanes {
+  const float* hi32;            // tf32(W)
+  const float* lo32;            // W - tf32(W)
+  const void* h16;              // fp16(W * 2^e)
+  const void* l16;              // fp16(W * 2^e - h16)
+  const float* sinv;            // one float: 2^-e
+};
 
 // tensor-core (tcgen05, 3xTF32) variants — gemm_tc.cu
 struct QkvPlanes {            // outputs of the QKV projection in the layout the attention kernels consume
@@ -140,8 +150,7 @@ struct QkvPlanes {            // outputs of the QKV projection in the layout the
   int planes;                 // 16-bit: 2 = hi + lo (fp32-class), 1 = single plane (bf16 variant)
   unsigned* status;           // fp16: GIMS_STATUS_FP16_RANGE is OR-ed in when a value reaches 32768 (may be null)
 };
-int launch_gemm_tc(const GemmArgs& a, const float* w_hi, const float* w_lo, cudaStream_t st,
-                   const QkvPlanes* qkv = nullptr);
+int launch_gemm_tc(const GemmArgs& a, const WPlanes& w, int prec, cudaStream_t st, const QkvPlanes* qkv = nullptr);
 int launch_attention_tc(const QkvPlanes& pl, float* out, const Segs& segs, int cross, cudaStream_t st);
 int launch_attention_f16(const QkvPlanes& pl, float* out, const Segs& segs, int cross, cudaStream_t st);
 int set_attention_trace(long long* dev_buf);
@@ -155,7 +164,7 @@ static inline int attn_vt_layout(const Segs& s, int* vbase) {
   return c;
 }
 int launch_score_gemm_tc(const float* mdesc, int n0_max, int n1_max, const int* n_dev, float* planes, float* couplings,
-                         cudaStream_t st);
+                         int prec, unsigned* status, cudaStream_t st);
 int launch_split_planes(const float* x, float* hi, float* lo, size_t n, cudaStream_t st);
 int launch_score_border(int n0_max, int n1_max, const int* n_dev, const float* bin_score, float* couplings,
                         cudaStream_t st);

@@ -79,25 +79,34 @@ using namespace tc;
 
 constexpr int BM = 128, BK = 32;
 constexpr int kThreadsTc = 224;   // 4 data warps + TMA warp + two MMA issuer warps
+// PREC 1 adds a second group of 4 data warps (warps 7..10): converting a 64-deep k-block of the A tile to fp16 hi / lo takes
+// one thread per row ~1000 clk against 770 clk of MMAs; two threads per row (one per 32-float box) put the loop back on the
+// tensor pipe, and the two groups share the epilogue chunks.
+__host__ __device__ constexpr int tc_threads(int prec) { return prec ? kThreadsTc + 128 : kThreadsTc; }
 
-template <int BN>
+// PREC 0: 3xTF32 (operands split into tf32 hi / lo, k-blocks of 32).  PREC 1: fp16 hi + lo (the same error class at twice the
+// tensor-pipe rate, see attention_f16.cu): k-blocks of 64 — the raw fp32 A tile is two 32-float boxes, the W planes are 16-bit
+// tiles with 128-byte rows (64 elements), K = 16 per MMA.
+template <int BN, int PREC>
 struct TcCfg {
-  static constexpr int kABytes = BM * BK * 4;            // 16 KB raw fp32 A tile
-  static constexpr int kWBytes = BN * BK * 4;
+  static constexpr int kBlockK = PREC ? 64 : 32;         // k-block depth in elements
+  static constexpr int kABytes = BM * kBlockK * 4;       // raw fp32 A tile: 16 KB per 32-float box
+  static constexpr int kWBytes = PREC ? BN * 64 * 2 : BN * BK * 4;
   static constexpr int kStageBytes = kABytes + 2 * kWBytes;
-  static constexpr int kStages = (BN <= 64) ? 3 : (BN <= 128 ? 4 : 3);      // BN = 64: 96 KB, two CTAs per SM
+  static constexpr int kStages = PREC ? (BN <= 64 ? 2 : (BN <= 128 ? 3 : 2))
+                                      : ((BN <= 64) ? 3 : (BN <= 128 ? 4 : 3));      // BN = 64: <= 98 KB, two CTAs per SM
   // Two issuer threads (even / odd k-blocks), each with its own accumulators: a single issuer leaves the tensor pipe
   // idle for ~40 % of the time around its commits (profiles/r01_gemm_pipeline_trace.txt).
   static constexpr int kIssuers = 2;
   // The tensor core rounds the fp32 accumulator toward zero on every accumulation, so the error of one accumulation
-  // chain grows linearly with its length.  Splitting the k-blocks over two accumulators halves the chains; at
-  // BN = 64 TMEM also has room for separate accumulators for the two small correction products (kFold = false),
-  // which takes their 2/3 of the roundings off the main chains.  The epilogue adds the accumulators in fp32 (RN).
+  // chain grows linearly with its length.  Splitting the k-blocks over two accumulators halves the chains; the epilogue
+  // adds the accumulators in fp32 (RN).
   static constexpr bool kFold = true;
   static constexpr int kMainAcc = 2;
   static constexpr int kCorrAcc = kFold ? 0 : kIssuers;
   static constexpr int kAccCols = (kMainAcc + kCorrAcc) * BN;
-  // The A operand lives in TMEM: a ring of k-block slots, 32 columns A_hi + 32 columns A_lo each.
+  // The A operand lives in TMEM: a ring of k-block slots, 32 columns A_hi + 32 columns A_lo each (tf32: 32 values per
+  // plane, fp16: 64 values packed two per column).
   static constexpr int kTmemCols = (BN <= 64) ? 256 : 512;                  // BN = 64: two CTAs per SM
   static constexpr int kRing = (kTmemCols - kAccCols) / 64 >= 4 ? 4 : 2;
   static constexpr int kRingCol = kAccCols;
@@ -124,7 +133,8 @@ struct TcArgs {
   //   columns [512,768) -> Vt [2][256][ldv]          transposed; rows beyond the live count are zero-filled
   int qkv;
   float* qp; void* kp; void* vt; int ldv; int rows_total; int vbase[kMaxSegs];
-  unsigned* status;              // 16-bit planes: overflow flag
+  unsigned* status;              // 16-bit planes / fp16 operands: overflow flag
+  const float* wscale_inv;       // PREC 1: the W planes hold W * 2^e; the accumulators are multiplied by *wscale_inv = 2^-e
 };
 
 // Optional pipeline trace (bring-up / profiling): CTA (0,0) stores clock64() stamps, see tools/gemm_trace.py.
@@ -132,11 +142,11 @@ __device__ long long* g_gemm_trace = nullptr;
 
 // MODE 0: Y = act(acc + bias + R);  1: couplings (score GEMM);  QKV projection: 2: Q / K / Vt tf32 planes,
 // 3: fp16 hi + lo planes, 4: one bf16 plane (K / Vt; Q stays fp32)
-template <int BN, int MODE>
-__global__ void __launch_bounds__(kThreadsTc, BN <= 64 ? 2 : 1)
+template <int BN, int MODE, int PREC>
+__global__ void __launch_bounds__(tc_threads(PREC), (BN <= 64 && !PREC) ? 2 : 1)
 k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
           const __grid_constant__ CUtensorMap mapWhi, const __grid_constant__ CUtensorMap mapWlo, TcArgs g) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, PREC>;
   extern __shared__ uint8_t smem_raw[];
   long long* trace = (blockIdx.x | blockIdx.y) == 0 && (threadIdx.x & 31) == 0 ? g_gemm_trace : nullptr;
   if (trace && threadIdx.x == 0) {
@@ -173,7 +183,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
   // the highest warp ids: the arbiter favours high warp ids, and a starved issuer starves the tensor pipe.
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   constexpr int kWarpTma = 4, kWarpMma = 5;          // issuer t (0 or 1) is lane 0 of warp kWarpMma + t
-  const int nkb = (g.K0 + g.K1) / BK;
+  const int nkb = (g.K0 + g.K1) / Cfg::kBlockK;
 
   if (warp == kWarpTma && lane == 0) {
     tma_prefetch_desc(&mapA0);
@@ -185,7 +195,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
       mbar_init(&empty[s], 1);
     }
     for (int s = 0; s < Cfg::kRing; ++s) {
-      mbar_init(&conv[s], 4);        // one arrival per splitter warp
+      mbar_init(&conv[s], PREC ? 8 : 4);   // one arrival per splitter warp
       mbar_init(&tfree[s], 1);
     }
     mbar_init(accum_full, (Cfg::kIssuers == 2 && nkb >= 2) ? 2 : 1);   // one commit per issuer that has k-blocks
@@ -198,9 +208,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
       mbar_wait(&empty[tma_s], tma_ph ^ 1);
       uint8_t* st = stage_ptr(tma_s);
       mbar_arrive_expect_tx(&full[tma_s], Cfg::kABytes + 2 * Cfg::kWBytes);
-      const int k = tma_kb * BK;
-      if (k < g.K0) tma_load_2d(st, &mapA0, &full[tma_s], k, rbase + r0);
-      else          tma_load_2d(st, &mapA1, &full[tma_s], k - g.K0, rbase + r0);
+      const int k = tma_kb * Cfg::kBlockK;
+#pragma unroll
+      for (int h = 0; h < Cfg::kBlockK / 32; ++h) {                // raw fp32 A: one 128-byte-swizzled box per 32 floats
+        const int ka = k + 32 * h;
+        if (ka < g.K0) tma_load_2d(st + h * 16384, &mapA0, &full[tma_s], ka, rbase + r0);
+        else           tma_load_2d(st + h * 16384, &mapA1, &full[tma_s], ka - g.K0, rbase + r0);
+      }
       tma_load_2d(st + Cfg::kABytes, &mapWhi, &full[tma_s], k, wbase + c0);
       tma_load_2d(st + Cfg::kABytes + Cfg::kWBytes, &mapWlo, &full[tma_s], k, wbase + c0);
       if (++tma_s == Cfg::kStages) { tma_s = 0; tma_ph ^= 1; }
@@ -213,8 +227,8 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
   // address nor the bias) and goes straight on to request the first stages; everybody else waits for it and for the
   // TMEM allocation.  (With a plain __syncthreads the first TMA was issued ~1200 clk into the kernel; issuing it from
   // inside the sync-ing warp before the barrier delayed the barrier for everybody instead.)
-  if (warp == kWarpTma) asm volatile("bar.arrive 1, %0;" ::"n"(kThreadsTc) : "memory");
-  else                  asm volatile("bar.sync 1, %0;" ::"n"(kThreadsTc) : "memory");
+  if (warp == kWarpTma) asm volatile("bar.arrive 1, %0;" ::"n"(tc_threads(PREC)) : "memory");
+  else                  asm volatile("bar.sync 1, %0;" ::"n"(tc_threads(PREC)) : "memory");
   tcgen05_fence_after();
   const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);   // warp-uniform for the compiler
   if (trace && threadIdx.x == 0) trace[1] = clock64();
@@ -222,13 +236,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
   if (warp == kWarpTma) {
     // ===== TMA producer =====
     if (lane == 0) tma_produce(nkb);
-  } else if (warp >= kWarpMma) {
+  } else if (warp == kWarpMma || warp == kWarpMma + 1) {
     // ===== MMA issuers: lane 0 of warp kWarpMma + t handles the k-blocks kb = t, t + kIssuers, ... =====
     // A comes from TMEM (written by the splitters), W from shared memory: with A in shared memory as well the
     // operand reads of three MMAs per k-step saturated the shared-memory port (profiles/r01_gemm_pipeline_trace.txt).
     const int t = __shfl_sync(0xffffffffu, warp - kWarpMma, 0);   // provably warp-uniform: the MMA operands stay in
     if (lane == 0 && t < Cfg::kIssuers) {                        // uniform registers (no ELECT / R2UR.BROADCAST per MMA)
-      constexpr uint32_t idesc = umma_idesc_tf32(BM, BN);
+      constexpr uint32_t idesc = PREC ? umma_idesc_f16(BM, BN, 0) : umma_idesc_tf32(BM, BN);
       // one descriptor per stage, built once: inside the loop an operand advance is a single 64-bit add
       const uint64_t d_stage0 = umma_desc_sw128(smem_u32(stage_ptr(0) + Cfg::kABytes));
       int last = -1;
@@ -247,12 +261,20 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
         const uint32_t main_acc = tmem_base + t * BN;
         const uint32_t corr = Cfg::kFold ? main_acc : tmem_base + (Cfg::kMainAcc + t) * BN;
         const uint32_t fresh = kb >= Cfg::kIssuers ? 1u : 0u;      // 0: first k-block of this issuer
+        // 4 k-steps per k-block either way: 8 tf32 or 16 fp16 values = 32 bytes inside the 128-B swizzle row of W and
+        // 8 TMEM columns of A
 #pragma unroll
-        for (int ks = 0; ks < BK / 8; ++ks) {
-          const uint64_t koff = (ks * 32) >> 4;       // 8 tf32 = 32 bytes inside the 128-B swizzle row
-          umma_tf32_ts(corr, a_lo + ks * 8, w_hi + koff, idesc, ks ? 1u : fresh);
-          umma_tf32_ts(corr, a_hi + ks * 8, w_lo + koff, idesc, 1u);
-          umma_tf32_ts(main_acc, a_hi + ks * 8, w_hi + koff, idesc, (Cfg::kFold || ks) ? 1u : fresh);
+        for (int ks = 0; ks < 4; ++ks) {
+          const uint64_t koff = (ks * 32) >> 4;
+          if (PREC) {
+            umma_f16_ts(corr, a_lo + ks * 8, w_hi + koff, idesc, ks ? 1u : fresh);
+            umma_f16_ts(corr, a_hi + ks * 8, w_lo + koff, idesc, 1u);
+            umma_f16_ts(main_acc, a_hi + ks * 8, w_hi + koff, idesc, (Cfg::kFold || ks) ? 1u : fresh);
+          } else {
+            umma_tf32_ts(corr, a_lo + ks * 8, w_hi + koff, idesc, ks ? 1u : fresh);
+            umma_tf32_ts(corr, a_hi + ks * 8, w_lo + koff, idesc, 1u);
+            umma_tf32_ts(main_acc, a_hi + ks * 8, w_hi + koff, idesc, (Cfg::kFold || ks) ? 1u : fresh);
+          }
         }
         if (trace && kb < 8) trace[32 + kb] = clock64();
         umma_commit(&empty[s]);                        // W slot reusable once these MMAs retire
@@ -261,45 +283,73 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
         if (trace && kb < 8) trace[40 + kb] = clock64();
       }
     }
-  } else if (warp < 4) {
-    // ===== A splitters (warps 0..3; thread = tile row = TMEM lane), then epilogue =====
-    const int t = threadIdx.x;                         // 0..127
-    const int q = warp;                                // TMEM lane quarter this warp may access
+  } else if (warp < 4 || warp >= 7) {
+    // ===== A splitters (warps 0..3 and, at PREC 1, 7..10; thread = tile row = TMEM lane), then epilogue =====
+    const int grp = warp >= 7 ? 1 : 0;                 // PREC 1: group g converts box g of every k-block, and takes every
+    constexpr int kGroups = PREC ? 2 : 1;              // second epilogue chunk
+    const int q = warp & 3;                            // TMEM lane quarter this warp may access (warp id mod 4)
+    const int t = 32 * q + lane;                       // tile row 0..127
+    const bool tr0 = threadIdx.x == 0;                 // the thread that writes the trace
     const uint32_t lane_base = tmem_base + ((uint32_t)(32 * q) << 16);
+    float amax = 0.f;                                  // PREC 1: largest |A| this thread has converted (fp16 range guard)
     {
       int s = 0; uint32_t ph = 0;
       for (int kb = 0; kb < nkb; ++kb) {
         const int slot = kb % Cfg::kRing;
         mbar_wait(&full[s], ph);
-        if (trace && t == 0 && kb < 8) trace[8 + kb] = clock64();
+        if (trace && tr0 && kb < 8) trace[8 + kb] = clock64();
         // row t of the 128-byte-swizzled tile: 16-byte chunk j sits at position j ^ (t & 7)
-        const uint4* rowp = reinterpret_cast<const uint4*>(stage_ptr(s) + t * 128);
         uint32_t x[32], hi[32];
+        if (PREC) {
+          // my 32 floats of this row (box grp) -> 16 packed fp16 hi / lo words: value 2 w in the low half of word w
+          const uint4* rowp = reinterpret_cast<const uint4*>(stage_ptr(s) + grp * 16384 + t * 128);
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          uint4 v = rowp[j ^ (t & 7)];
-          x[4 * j] = v.x; x[4 * j + 1] = v.y; x[4 * j + 2] = v.z; x[4 * j + 3] = v.w;
-        }
+          for (int j = 0; j < 8; ++j) {
+            const uint4 v = rowp[j ^ (t & 7)];
+            const float f0 = __uint_as_float(v.x), f1 = __uint_as_float(v.y), f2 = __uint_as_float(v.z), f3 = __uint_as_float(v.w);
+            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(f0), fabsf(f1)), fmaxf(fabsf(f2), fabsf(f3))));
+            split16x2<0>(f0, f1, hi[2 * j], x[2 * j]);
+            split16x2<0>(f2, f3, hi[2 * j + 1], x[2 * j + 1]);
+          }
+        } else {
+          const uint4* rowp = reinterpret_cast<const uint4*>(stage_ptr(s) + t * 128);
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
-          float h, l;
-          split_tf32(__uint_as_float(x[j]), h, l);
-          hi[j] = __float_as_uint(h); x[j] = __float_as_uint(l);
+          for (int j = 0; j < 8; ++j) {
+            uint4 v = rowp[j ^ (t & 7)];
+            x[4 * j] = v.x; x[4 * j + 1] = v.y; x[4 * j + 2] = v.z; x[4 * j + 3] = v.w;
+          }
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float h, l;
+            split_tf32(__uint_as_float(x[j]), h, l);
+            hi[j] = __float_as_uint(h); x[j] = __float_as_uint(l);
+          }
         }
         mbar_wait(&tfree[slot], ((uint32_t)(kb / Cfg::kRing) & 1u) ^ 1u);   // MMAs of k-block kb - kRing are done
         tcgen05_fence_after();
-        if (trace && t == 0 && kb < 8) trace[48 + kb] = clock64();
-        tmem_st_32x32(lane_base + Cfg::kRingCol + slot * 64, hi);
-        tmem_st_32x32(lane_base + Cfg::kRingCol + slot * 64 + 32, x);
+        if (trace && tr0 && kb < 8) trace[48 + kb] = clock64();
+        if (PREC) {
+          uint32_t h16[16], l16[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) { h16[j] = hi[j]; l16[j] = x[j]; }
+          tmem_st_32x16(lane_base + Cfg::kRingCol + slot * 64 + 16 * grp, h16);
+          tmem_st_32x16(lane_base + Cfg::kRingCol + slot * 64 + 32 + 16 * grp, l16);
+        } else {
+          tmem_st_32x32(lane_base + Cfg::kRingCol + slot * 64, hi);
+          tmem_st_32x32(lane_base + Cfg::kRingCol + slot * 64 + 32, x);
+        }
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
         if (lane == 0) mbar_arrive(&conv[slot]);
-        if (trace && t == 0 && kb < 8) trace[16 + kb] = clock64();
+        if (trace && tr0 && kb < 8) trace[16 + kb] = clock64();
         if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
       }
     }
+    // rows past the live count may hold anything (other segments, stale scratch): only live rows raise the range flag
+    if (PREC && g.status && amax >= 32768.f && r0 + t < rows) atomicOr(g.status, GIMS_STATUS_FP16_RANGE);
     // ---- epilogue ----
+    const float wsc = (PREC && g.wscale_inv) ? *g.wscale_inv : 1.f;
     const int n_main = nkb < Cfg::kMainAcc ? nkb : Cfg::kMainAcc;
     const int n_corr = nkb < Cfg::kCorrAcc ? nkb : Cfg::kCorrAcc;
     // Each warp transposes its 32x32 chunks through a private staging tile in the (now idle) pipeline stages, so that
@@ -308,7 +358,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
     // all shared-memory reads of a chunk are issued before the first store, and MODE is a template parameter, so
     // there is no branch or address arithmetic between the stores.
     constexpr int kStgLd = 36;                         // floats; 16-byte aligned rows, conflict-free both ways
-    const uint32_t stg = smem_u32(smem) + (uint32_t)(q * 32 * kStgLd * 4);
+    const uint32_t stg = smem_u32(smem) + (uint32_t)((q + 4 * grp) * 32 * kStgLd * 4);
     const int rl0 = lane >> 3, cj = (lane & 7) * 4;    // read-back: row i*4 + rl0 of the chunk, columns cj..cj+3
     const int rfirst = r0 + 32 * q + rl0;              // tile row of read-back slot i = 0; slot i is 4*i further
     const int nvalid = rows - rfirst;                  // slot i is a live row iff 4*i < nvalid
@@ -317,13 +367,13 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
     float4 rres[8];                                    // residual of the current chunk, fetched one chunk ahead
 #pragma unroll
     for (int i = 0; i < 8; ++i)
-      rres[i] = (use_r && 4 * i < nvalid && c0 + cj < ncols) ? *reinterpret_cast<const float4*>(rrow + (size_t)(4 * i) * g.ldr)
+      rres[i] = (use_r && 4 * i < nvalid && c0 + 32 * grp + cj < ncols) ? *reinterpret_cast<const float4*>(rrow + (size_t)(4 * i) * g.ldr + 32 * grp)
                                                              : make_float4(0.f, 0.f, 0.f, 0.f);
     mbar_wait(accum_full, 0);                          // the residual's latency hides behind the tail of the k-loop
     tcgen05_fence_after();
-    if (trace && t == 0) trace[3] = clock64();
+    if (trace && tr0) trace[3] = clock64();
 #pragma unroll 1
-    for (int cc = 0; cc < BN / 32; ++cc) {
+    for (int cc = grp; cc < BN / 32; cc += kGroups) {
       uint32_t v[32];
       const uint32_t lane_col = lane_base + (uint32_t)(cc * 32);
       tmem_ld_32x32(lane_col, v);
@@ -336,7 +386,11 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
 #pragma unroll
         for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
       }
-      if (trace && t == 0 && cc < 2) trace[56 + 3 * cc] = clock64();
+      if (PREC) {
+#pragma unroll
+        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * wsc);
+      }
+      if (trace && tr0 && cc < 2) trace[56 + 3 * cc] = clock64();
       const int c = c0 + cc * 32;
       if (c >= ncols) continue;                                // warp-uniform
       if (MODE >= 2 && c >= 2 * kD) {
@@ -385,7 +439,7 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
                      "r"(v[j + 1]), "r"(v[j + 2]), "r"(v[j + 3])
                      : "memory");
       __syncwarp();
-      if (trace && t == 0 && cc < 2) trace[57 + 3 * cc] = clock64();
+      if (trace && tr0 && cc < 2) trace[57 + 3 * cc] = clock64();
       if (MODE == 1) {
         // couplings rows are n1_max + 1 floats long (not 16-byte aligned) and end raggedly: scalar, one row per store
         if (c + lane < ncols) {
@@ -414,10 +468,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
         o[i].x += bias4.x + rres[i].x; o[i].y += bias4.y + rres[i].y;
         o[i].z += bias4.z + rres[i].z; o[i].w += bias4.w + rres[i].w;
       }
-      if (use_r && cc + 1 < BN / 32 && c + 32 < ncols) {       // the next chunk's residual, one chunk ahead
+      if (use_r && cc + kGroups < BN / 32 && c + 32 * kGroups < ncols) {       // my next chunk's residual, one chunk ahead
 #pragma unroll
         for (int i = 0; i < 8; ++i)
-          if (4 * i < nvalid) rres[i] = *reinterpret_cast<const float4*>(rrow + (size_t)(4 * i) * g.ldr + (cc + 1) * 32);
+          if (4 * i < nvalid) rres[i] = *reinterpret_cast<const float4*>(rrow + (size_t)(4 * i) * g.ldr + (cc + kGroups) * 32);
       }
       if (MODE >= 2) {
         if (c < kD) {
@@ -478,10 +532,10 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
           if (4 * i < nvalid) *reinterpret_cast<float4*>(yp + (size_t)(4 * i) * g.ldy) = y;
         }
       }
-      if (trace && t == 0 && cc < 2) trace[58 + 3 * cc] = clock64();
+      if (trace && tr0 && cc < 2) trace[58 + 3 * cc] = clock64();
     }
     tcgen05_fence_before();
-    if (trace && t == 0) trace[4] = clock64();
+    if (trace && tr0) trace[4] = clock64();
   }
   __syncthreads();
   if (warp == kWarpMma) {
@@ -505,20 +559,36 @@ __global__ void k_split_planes(const float* __restrict__ x, float* __restrict__ 
   reinterpret_cast<float4*>(lo)[i] = l;
 }
 
-template <int BN, int MODE>
+// x -> fp16 (hi, lo) planes, hi = fp16(x), lo = fp16(x - hi); the score GEMM's "weight" operand at PREC 1
+__global__ void k_split_planes16(const float* __restrict__ x, uint16_t* __restrict__ hi, uint16_t* __restrict__ lo, size_t n4,
+                                 unsigned* status) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = reinterpret_cast<const float4*>(x)[i];
+  uint2 h, l;
+  tc::split16x2<0>(v.x, v.y, h.x, l.x);
+  tc::split16x2<0>(v.z, v.w, h.y, l.y);
+  reinterpret_cast<uint2*>(hi)[i] = h;
+  reinterpret_cast<uint2*>(lo)[i] = l;
+  // (rows past the live counts hold whatever the projection left there: only finite overflow is flagged)
+  const float m = fmaxf(fmaxf(fabsf(v.x), fabsf(v.y)), fmaxf(fabsf(v.z), fabsf(v.w)));
+  if (status && m >= 32768.f && m < 3e38f) atomicOr(status, GIMS_STATUS_FP16_RANGE);
+}
+
+template <int BN, int MODE, int PREC = 0>
 int launch_tc(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& whi, const CUtensorMap& wlo,
               const TcArgs& g, int col_tiles, int row_tiles, int prof_class, cudaStream_t st) {
-  using Cfg = TcCfg<BN>;
-  GIMS_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc<BN, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
+  using Cfg = TcCfg<BN, PREC>;
+  GIMS_CUDA_OK(cudaFuncSetAttribute(k_gemm_tc<BN, MODE, PREC>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::kSmemBytes));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(col_tiles, row_tiles);
-  cfg.blockDim = dim3(kThreadsTc);
+  cfg.blockDim = dim3(tc_threads(PREC));
   cfg.dynamicSmemBytes = Cfg::kSmemBytes;
   cfg.stream = st;
   cfg.attrs = nullptr;
   cfg.numAttrs = 0;
   ProfScope prof(prof_class, st);
-  GIMS_CUDA_OK(cudaLaunchKernelEx(&cfg, k_gemm_tc<BN, MODE>, a0, a1, whi, wlo, g));
+  GIMS_CUDA_OK(cudaLaunchKernelEx(&cfg, k_gemm_tc<BN, MODE, PREC>, a0, a1, whi, wlo, g));
   count_launch();
   return GIMS_OK;
 }
@@ -535,43 +605,64 @@ int pick_bn(int n) {
 
 }  // namespace
 
-// W_hi / W_lo: [N][K] planes produced at pack time (gims_b200/packing.py) — same layout as the fp32 weight.
-int launch_gemm_tc(const GemmArgs& a, const float* w_hi, const float* w_lo, cudaStream_t st, const QkvPlanes* qkv) {
+// W planes: [N][K] produced at pack time (gims_b200/packing.py) — same layout as the fp32 weight.  prec 0: tf32 hi / lo
+// (fp32 words); prec 1: fp16 hi / lo of W * 2^e with *sinv = 2^-e.
+int launch_gemm_tc(const GemmArgs& a, const WPlanes& w, int prec, cudaStream_t st, const QkvPlanes* qkv) {
   int K = a.K0 + a.K1;
-  if (a.K0 % BK || a.K1 % BK || K == 0 || a.N % 32 || (a.lda0 % 4) || (a.K1 && (a.lda1 % 4))) {
+  if (prec && (a.K0 % 64 || a.K1 % 64 || !w.h16 || !w.l16 || !w.sinv)) prec = 0;     // shapes the fp16 kernel does not take
+  if (a.K0 % BK || a.K1 % BK || K == 0 || a.N % 32 || (a.lda0 % 4) || (a.K1 && (a.lda1 % 4)) || !w.hi32 || !w.lo32) {
     set_error("launch_gemm_tc: unsupported shape K0=%d K1=%d N=%d", a.K0, a.K1, a.N);
     return GIMS_ERR_ARG;
   }
   int total_rows = segs_rows(a.segs);
   int bn = pick_bn(a.N);
   if (qkv && (bn != 64 || qkv->fmt >= 0)) bn = 192;
+  if (prec) bn = (qkv || (a.N >= 256 && bn != 64)) ? 128 : 64;      // (GIMS_GEMM_BN=64 forces the two-CTAs-per-SM shape)
   CUtensorMap mA0, mA1, mWh, mWl;
   GIMS_TRY(tc::make_tmap_f32_k32(&mA0, a.A0, total_rows, a.K0, a.lda0, BM));
   if (a.K1) GIMS_TRY(tc::make_tmap_f32_k32(&mA1, a.A1, total_rows, a.K1, a.lda1, BM));
   else mA1 = mA0;
-  GIMS_TRY(tc::make_tmap_f32_k32(&mWh, w_hi, a.N, K, K, bn));
-  GIMS_TRY(tc::make_tmap_f32_k32(&mWl, w_lo, a.N, K, K, bn));
+  if (prec) {
+    GIMS_TRY(tc::make_tmap_16_k64(&mWh, w.h16, 0, a.N, K, K, bn));
+    GIMS_TRY(tc::make_tmap_16_k64(&mWl, w.l16, 0, a.N, K, K, bn));
+  } else {
+    GIMS_TRY(tc::make_tmap_f32_k32(&mWh, w.hi32, a.N, K, K, bn));
+    GIMS_TRY(tc::make_tmap_f32_k32(&mWl, w.lo32, a.N, K, K, bn));
+  }
   TcArgs g;
   g.K0 = a.K0; g.K1 = a.K1; g.bias = a.bias; g.R = a.R; g.ldr = a.ldr; g.Y = a.Y; g.ldy = a.ldy; g.N = a.N;
   g.relu = a.relu; g.scale = 1.f; g.score = 0; g.segs = a.segs;
-  g.qkv = 0; g.qp = nullptr; g.kp = g.vt = nullptr; g.ldv = 0; g.rows_total = total_rows; g.status = nullptr;
+  g.qkv = 0; g.qp = nullptr; g.kp = g.vt = nullptr; g.ldv = 0; g.rows_total = total_rows; g.status = a.status;
+  g.wscale_inv = prec ? w.sinv : nullptr;
   for (int i = 0; i < kMaxSegs; ++i) g.vbase[i] = 0;
   if (qkv) {
     if (a.N != 3 * kD || !a.bias) { set_error("launch_gemm_tc: qkv mode needs N = 768 and a bias"); return GIMS_ERR_ARG; }
     g.qkv = 1; g.qp = qkv->qp; g.kp = qkv->kp; g.vt = qkv->vt; g.ldv = qkv->ldv;
     for (int i = 0; i < kMaxSegs; ++i) g.vbase[i] = qkv->vbase[i];
-    g.status = qkv->status;
+    if (qkv->status) g.status = qkv->status;
   }
   int tiles = 0;
   for (int i = 0; i < a.segs.nseg; ++i) { tiles += cdiv(a.segs.nmax[i], BM); g.tile_end[i] = tiles; }
   if (tiles == 0) return GIMS_OK;
   int ct = cdiv(a.N, bn);
   if (qkv) {
-    if (qkv->fmt == 0 && qkv->planes == 2) return launch_tc<192, 3>(mA0, mA1, mWh, mWl, g, ct, tiles, GIMS_PROF_GEMM, st);
-    if (qkv->fmt == 1 && qkv->planes == 1) return launch_tc<192, 4>(mA0, mA1, mWh, mWl, g, ct, tiles, GIMS_PROF_GEMM, st);
-    if (qkv->fmt >= 0) { set_error("launch_gemm_tc: unsupported 16-bit plane format"); return GIMS_ERR_ARG; }
+    if (qkv->fmt >= 0 && !((qkv->fmt == 0 && qkv->planes == 2) || (qkv->fmt == 1 && qkv->planes == 1))) {
+      set_error("launch_gemm_tc: unsupported 16-bit plane format");
+      return GIMS_ERR_ARG;
+    }
+    if (prec) {
+      if (qkv->fmt == 0) return launch_tc<128, 3, 1>(mA0, mA1, mWh, mWl, g, ct, tiles, GIMS_PROF_GEMM, st);
+      if (qkv->fmt == 1) return launch_tc<128, 4, 1>(mA0, mA1, mWh, mWl, g, ct, tiles, GIMS_PROF_GEMM, st);
+      return launch_tc<128, 2, 1>(mA0, mA1, mWh, mWl, g, ct, tiles, GIMS_PROF_GEMM, st);
+    }
+    if (qkv->fmt == 0) return launch_tc<192, 3>(mA0, mA1, mWh, mWl, g, ct, tiles, GIMS_PROF_GEMM, st);
+    if (qkv->fmt == 1) return launch_tc<192, 4>(mA0, mA1, mWh, mWl, g, ct, tiles, GIMS_PROF_GEMM, st);
     if (bn == 64) return launch_tc<64, 2>(mA0, mA1, mWh, mWl, g, ct, tiles, GIMS_PROF_GEMM, st);
     return launch_tc<192, 2>(mA0, mA1, mWh, mWl, g, ct, tiles, GIMS_PROF_GEMM, st);
+  }
+  if (prec) {
+    if (bn == 128) return launch_tc<128, 0, 1>(mA0, mA1, mWh, mWl, g, ct, tiles, GIMS_PROF_GEMM, st);
+    return launch_tc<64, 0, 1>(mA0, mA1, mWh, mWl, g, ct, tiles, GIMS_PROF_GEMM, st);
   }
   switch (bn) {
     case 192: return launch_tc<192, 0>(mA0, mA1, mWh, mWl, g, ct, tiles, GIMS_PROF_GEMM, st);
@@ -592,25 +683,37 @@ int launch_split_planes(const float* x, float* hi, float* lo, size_t n, cudaStre
   return GIMS_OK;
 }
 
-// couplings[i][j] = <mdesc0_i, mdesc1_j> / 16 on tensor cores; `planes` = 2 * (n0_max+n1_max) * 256 floats scratch
+// couplings[i][j] = <mdesc0_i, mdesc1_j> / 16 on tensor cores; `planes` = 2 * (n0_max+n1_max) * 256 floats scratch.
+// prec 1: fp16 hi / lo planes of mdesc (|mdesc| >= 32768 raises GIMS_STATUS_FP16_RANGE in *status)
 int launch_score_gemm_tc(const float* mdesc, int n0_max, int n1_max, const int* n_dev, float* planes, float* couplings,
-                         cudaStream_t st) {
+                         int prec, unsigned* status, cudaStream_t st) {
   size_t rows = (size_t)n0_max + n1_max;
-  float* hi = planes;
-  float* lo = planes + rows * kD;
-  GIMS_TRY(launch_split_planes(mdesc, hi, lo, rows * kD, st));
   constexpr int bn = 128;
   CUtensorMap mA, mWh, mWl;
   GIMS_TRY(tc::make_tmap_f32_k32(&mA, mdesc, rows, kD, kD, BM));
-  GIMS_TRY(tc::make_tmap_f32_k32(&mWh, hi, rows, kD, kD, bn));
-  GIMS_TRY(tc::make_tmap_f32_k32(&mWl, lo, rows, kD, kD, bn));
+  if (prec) {
+    uint16_t* hi = reinterpret_cast<uint16_t*>(planes);
+    uint16_t* lo = hi + rows * kD;
+    k_split_planes16<<<(unsigned)((rows * kD / 4 + 255) / 256), 256, 0, st>>>(mdesc, hi, lo, rows * kD / 4, status);
+    GIMS_LAUNCH_OK();
+    GIMS_TRY(tc::make_tmap_16_k64(&mWh, hi, 0, rows, kD, kD, bn));
+    GIMS_TRY(tc::make_tmap_16_k64(&mWl, lo, 0, rows, kD, kD, bn));
+  } else {
+    float* hi = planes;
+    float* lo = planes + rows * kD;
+    GIMS_TRY(launch_split_planes(mdesc, hi, lo, rows * kD, st));
+    GIMS_TRY(tc::make_tmap_f32_k32(&mWh, hi, rows, kD, kD, bn));
+    GIMS_TRY(tc::make_tmap_f32_k32(&mWl, lo, rows, kD, kD, bn));
+  }
   TcArgs g;
   g.K0 = kD; g.K1 = 0; g.bias = nullptr; g.R = nullptr; g.ldr = 0; g.Y = couplings; g.ldy = coup_ld(n1_max); g.N = n1_max;
   g.relu = 0; g.scale = 0.0625f; g.score = 1;
-  g.qkv = 0; g.qp = nullptr; g.kp = g.vt = nullptr; g.ldv = 0; g.rows_total = (int)rows; g.status = nullptr;
+  g.qkv = 0; g.qp = nullptr; g.kp = g.vt = nullptr; g.ldv = 0; g.rows_total = (int)rows; g.status = status;
+  g.wscale_inv = nullptr;
   for (int i = 0; i < kMaxSegs; ++i) { g.vbase[i] = 0; g.tile_end[i] = 0; }
   g.segs = two_segs(n0_max, n1_max, n_dev);
   g.tile_end[0] = cdiv(n0_max, BM);
+  if (prec) return launch_tc<bn, 1, 1>(mA, mA, mWh, mWl, g, cdiv(n1_max, bn), g.tile_end[0], GIMS_PROF_SCORE, st);
   return launch_tc<bn, 1>(mA, mA, mWh, mWl, g, cdiv(n1_max, bn), g.tile_end[0], GIMS_PROF_SCORE, st);
 }
 

@@ -14,7 +14,8 @@ Done once at load time, in float64 then rounded to fp32:
   * every weight matrix W is followed by its tensor-core planes W_hi = tf32(W) (round-to-nearest, ties away,
     like cvt.rna.tf32.f32) and W_lo = W - W_hi (exact in fp32), consumed by the 3xTF32 tcgen05 GEMM
 
-Blob order (== offsets passed to gims_model_create); each matrix W stands for three blobs W, W_hi, W_lo:
+Blob order (== offsets passed to gims_model_create); each matrix W stands for six blobs W, W_hi, W_lo (tf32 planes),
+W_h16, W_l16 (fp16 planes of W * 2^e, raw bits), 2^-e:
   bin_score, (kenc W_i, b_i) for every kenc conv, (sage W_l, b_l) l=0..2,
   per attention layer: Wqkv, bqkv, W1 (merge composed in, BN folded), b1, W2, b2; final_proj W, b.
 """
@@ -47,6 +48,22 @@ def split_tf32(w32):
     return hi, w32 - hi
 
 
+def split_f16(w32):
+    """fp32 matrix -> (hi bits, lo bits, 2^-e): hi = fp16(W * 2^e), lo = fp16(W * 2^e - hi) (round to nearest even, what
+    cvt.rn.f16.f32 computes), the two planes returned as float32 tensors that hold the raw 16-bit patterns (two per
+    word, row-major); e puts max|W| * 2^e into [512, 1024], so that both planes are normal fp16 numbers for every weight
+    within 2^-13 of the largest one."""
+    w32 = w32.contiguous()
+    amax = float(w32.abs().max()) if w32.numel() else 0.0
+    e = int(torch.floor(torch.log2(torch.tensor(1024.0 / amax)))) if amax > 0 else 0
+    e = max(-12, min(24, e))
+    scaled = w32 * float(2.0 ** e)
+    hi = scaled.to(torch.float16)
+    lo = (scaled - hi.float()).to(torch.float16)
+    assert w32.numel() % 2 == 0
+    return hi.view(torch.float32).reshape(-1), lo.view(torch.float32).reshape(-1), torch.tensor([2.0 ** -e], dtype=torch.float32)
+
+
 def pack_state_dict(sd, config=None):
     """Returns (flat fp32 CPU tensor, list of float offsets, list of blob names)."""
     cfg = {**DEFAULT_CONFIG, **(config or {})}
@@ -61,6 +78,10 @@ def pack_state_dict(sd, config=None):
             hi, lo = split_tf32(t.float())
             blobs.append((name + '.hi', hi.double()))
             blobs.append((name + '.lo', lo.double()))
+            h16, l16, sinv = split_f16(t.float())
+            blobs.append((name + '.h16', h16))    # raw 16-bit patterns: float32 words, never converted
+            blobs.append((name + '.l16', l16))
+            blobs.append((name + '.sinv', sinv))
 
     add('bin_score', sd['bin_score'].reshape(1))
     ch = kenc_channels(cfg)
@@ -107,7 +128,7 @@ def pack_state_dict(sd, config=None):
 
     offsets, names, parts, off = [], [], [], 0
     for name, t in blobs:
-        flat = t.reshape(-1).float()
+        flat = t.reshape(-1) if t.dtype == torch.float32 else t.reshape(-1).float()
         pad = (-flat.numel()) % 64              # keep every blob 256-byte aligned
         offsets.append(off)
         names.append(name)

@@ -54,7 +54,7 @@ extern "C" {
  * Error bits (the host side raises on them): */
 #define GIMS_STATUS_EDGE_OVERFLOW     1u   /* edge_cap exceeded: the graph is reported EMPTY (N' = 0), retry larger */
 #define GIMS_STATUS_SINKHORN_TIMEOUT  2u   /* a bounded poll inside k_sinkhorn expired: outputs are poisoned (NaN / -2) */
-#define GIMS_STATUS_FP16_RANGE        4u   /* GIMS_GEMM_TC_F16: an attention operand reached 32768 — rerun with GIMS_GEMM_TC */
+#define GIMS_STATUS_FP16_RANGE        4u   /* GIMS_GEMM_TC_F16: a tensor-core operand reached 32768 — rerun with GIMS_GEMM_TC */
 #define GIMS_STATUS_ERROR_MASK        0xffu
 /* Information bits: which Sinkhorn iteration the launch ran */
 #define GIMS_STATUS_SINKHORN_FAST   0x100u /* exp-free scaled-kernel iteration */
@@ -83,11 +83,11 @@ GIMS_API long long   gims_launch_count(void);
  * (gims_pair_inputs.gemm_mode):
  *   GIMS_GEMM_SIMT    fp32 FMA CUDA-core kernels (bit-for-bit fp32 products; used to validate the others)
  *   GIMS_GEMM_TC      tcgen05/TMEM/TMA tensor-core kernels, 3xTF32 error-compensated fp32 everywhere
- *   GIMS_GEMM_TC_F16  (default) as GIMS_GEMM_TC, attention operands as fp16 hi + lo planes: the same error class
+ *   GIMS_GEMM_TC_F16  (default) every tensor-core operand as fp16 hi + lo planes instead of tf32 hi + lo: the same error class
  *                     (|x - hi - lo| <= max(2^-22 |x|, 2^-25)) at twice the tensor-pipe rate.  fp16 overflows at
  *                     65504: a value >= 32768 raises GIMS_STATUS_FP16_RANGE and the caller reruns with GIMS_GEMM_TC.
- *   GIMS_GEMM_BF16    the "bf16 variant": attention operands and the score GEMM in bf16 (8-bit mantissa), projections
- *                     as GIMS_GEMM_TC.  NOT fp32 parity — reported separately (BASELINE.json north_star). */
+ *   GIMS_GEMM_BF16    the "bf16 variant": attention operands in bf16 (8-bit mantissa, one MMA per product), projections
+ *                     as GIMS_GEMM_TC_F16.  NOT fp32 parity — reported separately (BASELINE.json north_star). */
 #define GIMS_GEMM_SIMT   0
 #define GIMS_GEMM_TC     1
 #define GIMS_GEMM_TC_F16 2
@@ -96,10 +96,12 @@ GIMS_API int gims_set_gemm_mode(int mode);
 GIMS_API int gims_get_gemm_mode(void);
 
 /* Bring-up / test entry points for the GEMM kernels: Y[r][o] = act(sum_k A(r,k) W[o][k] + bias[o] + R[r][o]),
- * A = [A0 | A1] along K (K0 + K1), W [N][K0+K1]; W_hi/W_lo = planes from gims_split_tf32 (TC mode). */
+ * A = [A0 | A1] along K (K0 + K1), W [N][K0+K1]; W_hi/W_lo = tf32 planes (GIMS_GEMM_TC); W_h16/W_l16 = fp16 planes of
+ * W * 2^e and W_sinv -> 2^-e (GIMS_GEMM_TC_F16; K0, K1 multiples of 64, otherwise the tf32 kernel runs). */
 GIMS_API int gims_linear(const float* A0, int lda0, int K0, const float* A1, int lda1, int K1, const float* W,
-                const float* W_hi, const float* W_lo, const float* bias, const float* R, int ldr, float* Y, int ldy,
-                int N, int relu, int rows_max, const int* rows_dev, int mode, void* stream);
+                const float* W_hi, const float* W_lo, const void* W_h16, const void* W_l16, const float* W_sinv,
+                const float* bias, const float* R, int ldr, float* Y, int ldy,
+                int N, int relu, int rows_max, const int* rows_dev, int mode, unsigned* status_dev, void* stream);
 GIMS_API int gims_split_tf32(const float* x, float* hi, float* lo, size_t n, void* stream);
 /* Profiling aid: CTA (0,0,0) of every following attention launch stores clock64() stamps of its pipeline
  * (8 int64 per 64-key tile, see attention_tc.cu) into dev_buf; pass NULL to switch the trace off. */

@@ -37,7 +37,7 @@ def test_host_queries(lib):
     from gims_b200 import GMatcher
     m = GMatcher({})
     c = m.c_config()
-    assert lib.gims_packed_blob_count(C.byref(c)) == 1 + 4 * 5 + 4 * 3 + 12 * 18 + 4
+    assert lib.gims_packed_blob_count(C.byref(c)) == 1 + 7 * 5 + 7 * 3 + 21 * 18 + 7
     assert [c.layer_is_cross[i] for i in range(4)] == [0, 1, 0, 1]
     assert [c.kenc_dims[i] for i in range(6)] == [2, 32, 64, 128, 256, 256]
 
@@ -109,6 +109,23 @@ def test_packing_equals_oracle_layer():
     delta = hid @ blob['l3.w2'][:256 * 512].view(256, 512).t() + blob['l3.b2'][:256]
     want = orc.attn_propagation(sd, l, x.t()[None], src.t()[None])[0].t()
     assert torch.allclose(delta, want, rtol=1e-4, atol=1e-5)
+
+
+def test_fp16_weight_planes():
+    """split_f16: hi + lo reproduce W * 2^e to 2^-22 relative (both planes normal fp16 numbers), raw bits survive packing."""
+    from gims_b200.packing import pack_state_dict, split_f16
+    from gims_b200.synth import make_state_dict
+    w = torch.randn(64, 128) * 0.05
+    h, l, sinv = split_f16(w)
+    hi = h.view(torch.float16).float().view(64, 128)
+    lo = l.view(torch.float16).float().view(64, 128)
+    rec = (hi + lo) * sinv
+    assert ((rec - w).abs() <= w.abs() * 2.0 ** -21 + 1e-12).all()
+    assert float(hi.abs().max()) < 2048 and float(1.0 / sinv) == 2.0 ** round(float(torch.log2(1.0 / sinv)))
+    flat, off, names = pack_state_dict(make_state_dict(0))
+    i = names.index('l3.w2.h16')
+    want = split_f16(flat[off[names.index('l3.w2')]:off[names.index('l3.w2')] + 256 * 512].view(256, 512))[0]
+    assert torch.equal(flat[off[i]:off[i] + want.numel()].view(torch.int32), want.view(torch.int32))
 
 
 def test_packing_equals_oracle_sage_kenc():

@@ -34,12 +34,16 @@ def _run(mode, rows_max, rows, N, K0, K1, bias, resid, relu, seed=0):
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     _lib.check(L.gims_split_tf32(_lib.ptr(W), _lib.ptr(hi), _lib.ptr(lo), W.numel(), st), 'split')
     assert torch.equal(hi + lo, W)
+    from gims_b200.packing import split_f16
+    h16, l16, sinv = [t.to(dev) for t in split_f16(W.cpu())]
     Y = torch.full((rows_max, N), float('nan'), device=dev)
     nd = torch.tensor([rows], dtype=torch.int32, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
     _lib.check(L.gims_linear(_lib.ptr(A0), K0, K0, _lib.ptr(A1), K1, K1, _lib.ptr(W), _lib.ptr(hi), _lib.ptr(lo),
-                             _lib.ptr(b), _lib.ptr(R), N, _lib.ptr(Y), N, N, int(relu), rows_max, _lib.ptr(nd), mode, st),
-               'gims_linear')
+                             _lib.ptr(h16), _lib.ptr(l16), _lib.ptr(sinv), _lib.ptr(b), _lib.ptr(R), N, _lib.ptr(Y), N, N,
+                             int(relu), rows_max, _lib.ptr(nd), mode, _lib.ptr(status), st), 'gims_linear')
     torch.cuda.synchronize()
+    assert int(status.cpu()) == 0
     A = torch.cat([A0, A1], 1) if K1 else A0
     ref = A.double() @ W.double().t()
     if bias:
@@ -60,6 +64,39 @@ def test_simt_gemm(shape):
     e = _run(_lib.GEMM_SIMT, *shape)
     print('\n[simt gemm %s] rel err %.2e' % (shape[:5], e))
     assert e < 2e-6
+
+
+@pytest.mark.parametrize('shape', SHAPES)
+def test_f16_gemm(shape):
+    """fp16 hi + lo operands (k-blocks of 64; shapes with K % 64 != 0 run the tf32 kernel)."""
+    from gims_b200 import _lib
+    e = _run(_lib.GEMM_TC_F16, *shape)
+    print('\n[f16x2 gemm %s] rel err %.2e' % (shape[:5], e))
+    assert e < 4e-6
+
+
+def test_f16_gemm_range_flag():
+    """An activation >= 32768 raises GIMS_STATUS_FP16_RANGE instead of silently overflowing."""
+    from gims_b200 import _lib
+    from gims_b200.packing import split_f16
+    L = _lib.lib()
+    dev = torch.device('cuda')
+    A = torch.randn(256, 128, device=dev)
+    A[77, 5] = 5e4
+    W = torch.randn(64, 128) / 11
+    hi, lo = torch.empty(64, 128, device=dev), torch.empty(64, 128, device=dev)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    Wd = W.to(dev)
+    _lib.check(L.gims_split_tf32(_lib.ptr(Wd), _lib.ptr(hi), _lib.ptr(lo), Wd.numel(), st), 'split')
+    h16, l16, sinv = [t.to(dev) for t in split_f16(W)]
+    Y = torch.empty(256, 64, device=dev)
+    nd = torch.tensor([256], dtype=torch.int32, device=dev)
+    status = torch.zeros(1, dtype=torch.int32, device=dev)
+    _lib.check(L.gims_linear(_lib.ptr(A), 128, 128, None, 0, 0, _lib.ptr(Wd), _lib.ptr(hi), _lib.ptr(lo), _lib.ptr(h16),
+                             _lib.ptr(l16), _lib.ptr(sinv), None, None, 0, _lib.ptr(Y), 64, 64, 0, 256, _lib.ptr(nd),
+                             _lib.GEMM_TC_F16, _lib.ptr(status), st), 'gims_linear')
+    torch.cuda.synchronize()
+    assert int(status.cpu()) & _lib.STATUS_FP16_RANGE
 
 
 @pytest.mark.parametrize('shape', SHAPES)

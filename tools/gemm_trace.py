@@ -9,6 +9,8 @@ L = _lib.lib()
 dev = torch.device('cuda')
 st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
 rows = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+MODE = _lib.GEMM_MODES[sys.argv[2]] if len(sys.argv) > 2 else _lib.GEMM_TC_F16
+from gims_b200.packing import split_f16
 
 
 def run(K0, K1, N, reps=50, dump=True):
@@ -17,13 +19,15 @@ def run(K0, K1, N, reps=50, dump=True):
     W = torch.randn(N, K0 + K1, device=dev) / (K0 + K1) ** 0.5
     hi, lo = torch.empty_like(W), torch.empty_like(W)
     _lib.check(L.gims_split_tf32(_lib.ptr(W), _lib.ptr(hi), _lib.ptr(lo), W.numel(), st), 'split')
+    h16, l16, sinv = [t.to(dev) for t in split_f16(W.cpu())]
     b = torch.randn(N, device=dev)
     Y = torch.empty(rows, N, device=dev)
     nd = torch.tensor([rows], dtype=torch.int32, device=dev)
 
     def call():
         _lib.check(L.gims_linear(_lib.ptr(A0), K0, K0, _lib.ptr(A1), K1, K1, _lib.ptr(W), _lib.ptr(hi), _lib.ptr(lo),
-                                 _lib.ptr(b), None, N, _lib.ptr(Y), N, N, 1, rows, _lib.ptr(nd), _lib.GEMM_TC, st), 'lin')
+                                 _lib.ptr(h16), _lib.ptr(l16), _lib.ptr(sinv), _lib.ptr(b), None, N, _lib.ptr(Y), N, N, 1, rows,
+                                 _lib.ptr(nd), MODE, None, st), 'lin')
     for _ in range(5):
         call()
     torch.cuda.synchronize()
