@@ -460,8 +460,8 @@ def main():
     L = _lib.lib()
     if args.gemm_mode:
         L.gims_set_gemm_mode(_lib.GEMM_MODES[args.gemm_mode])
-    gemm_mode_name = {0: 'simt (fp32 CUDA cores)', 1: 'tf32x3', 2: 'f16x2 attention operands + tf32x3 projections',
-                      3: 'bf16 attention operands + tf32x3 projections (bf16 variant, not fp32 parity)'}[L.gims_get_gemm_mode()]
+    gemm_mode_name = {0: 'simt (fp32 CUDA cores)', 1: 'tf32x3', 2: 'fp16 hi+lo operands (3 MMAs per fp32 product) in attention and projections',
+                      3: 'bf16 attention operands + fp16 hi+lo projections (bf16 variant, not fp32 parity)'}[L.gims_get_gemm_mode()]
 
     cfg = {'sinkhorn_iterations': 100, 'match_threshold': 0.2}
     matching = Matching(cfg)

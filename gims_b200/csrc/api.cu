@@ -49,30 +49,42 @@ ProfScope::~ProfScope() {
 
 // ---- cooperative-kernel chain -------------------------------------------------------------------
 static std::mutex g_coop_mu;
-static cudaEvent_t g_coop_ev[64];
-static bool g_coop_has[64];
+static cudaEvent_t g_coop_ev[64][2];
+static bool g_coop_has[64][2];
+static unsigned g_coop_next[64];
 
 static std::mutex g_coop_launch_mu;
 void coop_chain_lock() { g_coop_launch_mu.lock(); }
 void coop_chain_unlock() { g_coop_launch_mu.unlock(); }
 
-int coop_chain_wait(cudaStream_t st) {
+int coop_chain_pick_lane() {
   int dev = 0;
-  GIMS_CUDA_OK(cudaGetDevice(&dev));
+  if (cudaGetDevice(&dev) != cudaSuccess || dev >= 64) return 0;
   std::lock_guard<std::mutex> lk(g_coop_mu);
-  if (dev < 64 && g_coop_has[dev]) GIMS_CUDA_OK(cudaStreamWaitEvent(st, g_coop_ev[dev], 0));
-  return GIMS_OK;
+  return (int)(g_coop_next[dev]++ & 1u);
 }
-int coop_chain_record(cudaStream_t st) {
+int coop_chain_wait(cudaStream_t st, int lane) {
   int dev = 0;
   GIMS_CUDA_OK(cudaGetDevice(&dev));
   if (dev >= 64) return GIMS_OK;
   std::lock_guard<std::mutex> lk(g_coop_mu);
-  if (!g_coop_has[dev]) {
-    GIMS_CUDA_OK(cudaEventCreateWithFlags(&g_coop_ev[dev], cudaEventDisableTiming));
-    g_coop_has[dev] = true;
+  for (int l = 0; l < 2; ++l)
+    if ((lane < 0 || lane == l) && g_coop_has[dev][l]) GIMS_CUDA_OK(cudaStreamWaitEvent(st, g_coop_ev[dev][l], 0));
+  return GIMS_OK;
+}
+int coop_chain_record(cudaStream_t st, int lane) {
+  int dev = 0;
+  GIMS_CUDA_OK(cudaGetDevice(&dev));
+  if (dev >= 64) return GIMS_OK;
+  std::lock_guard<std::mutex> lk(g_coop_mu);
+  for (int l = 0; l < 2; ++l) {
+    if (lane >= 0 && lane != l) continue;
+    if (!g_coop_has[dev][l]) {
+      GIMS_CUDA_OK(cudaEventCreateWithFlags(&g_coop_ev[dev][l], cudaEventDisableTiming));
+      g_coop_has[dev][l] = true;
+    }
+    GIMS_CUDA_OK(cudaEventRecord(g_coop_ev[dev][l], st));
   }
-  GIMS_CUDA_OK(cudaEventRecord(g_coop_ev[dev], st));
   return GIMS_OK;
 }
 

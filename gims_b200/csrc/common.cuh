@@ -46,18 +46,27 @@ struct ProfScope {
   ~ProfScope();
 };
 
-// Cooperative (grid-synchronising) kernels of different streams must never be partially co-resident:
-// they are chained through one per-device event.  The scope holds a process-wide lock from the wait to the
-// record, so concurrent host threads (one stream each) cannot both chain onto the same predecessor.
-int coop_chain_wait(cudaStream_t st);
-int coop_chain_record(cudaStream_t st);
+// Cooperative (grid-synchronising) kernels of different streams must never be partially co-resident with more CTAs in
+// total than the GPU has SMs: they are chained through per-device events.  There are two chains ("lanes"): a kernel that
+// occupies at most half the SMs joins one lane (alternating), so two such kernels of different streams may run side by
+// side; a kernel that needs every SM waits for both lanes and both lanes wait for it.  The scope holds a process-wide
+// lock from the wait to the record, so concurrent host threads (one stream each) cannot both chain onto the same
+// predecessor.
+int coop_chain_wait(cudaStream_t st, int lane);      // lane 0 / 1, or -1 = both
+int coop_chain_record(cudaStream_t st, int lane);
+int coop_chain_pick_lane();
 void coop_chain_lock();
 void coop_chain_unlock();
 struct CoopChainScope {
   cudaStream_t st;
+  int lane;
   int rc;
-  explicit CoopChainScope(cudaStream_t s) : st(s) { coop_chain_lock(); rc = coop_chain_wait(st); }
-  ~CoopChainScope() { if (rc == 0) coop_chain_record(st); coop_chain_unlock(); }
+  CoopChainScope(cudaStream_t s, bool half_gpu) : st(s) {
+    coop_chain_lock();
+    lane = half_gpu ? coop_chain_pick_lane() : -1;
+    rc = coop_chain_wait(st, lane);
+  }
+  ~CoopChainScope() { if (rc == 0) coop_chain_record(st, lane); coop_chain_unlock(); }
 };
 
 constexpr int kD = GIMS_DESC_DIM;     // 256

@@ -328,20 +328,28 @@ struct ColUpdate {
 };
 
 // =====================================================================================================================
-// Scaled-kernel iteration, slab in registers: thread t owns the float4 column group t of every slab row (<= 16 rows x 4
-// floats) together with the group's weights, so neither pass reads the slab from shared memory: the row pass is 64 FMAs
-// + a block reduction of <= 16 row sums, the column pass 64 FMAs whose result is already this CTA's complete partial for
-// those columns.  The (<= 3) columns past the last full group, among them the dustbin column, come from the shared-memory
-// copy of the slab.  Per iteration (profiles/): row pass 1.55 k, column pass 1.15 k, hop 2.7 k, gather 3.4 k clk.
+// Scaled-kernel iteration, slab on chip: thread t owns the float4 column group t of every slab row together with the
+// group's weights.  The first kRMax (16) rows live in REGISTERS, up to kRSmem (16) more in shared memory, so neither pass
+// touches global memory: the row pass is 4 FMAs per row + a block reduction of the row sums, the column pass 4 FMAs per
+// row whose result is already this CTA's complete partial for those columns.  The (<= 3) columns past the last full
+// group, among them the dustbin column, sit in a small shared array.
+//
+// Why up to 32 rows per CTA: the iteration is bound by the exchange (148 CTAs x 513 red.v4 into L2, then every CTA reading
+// every column sum back), whose cost grows with the number of CTAs, not by the arithmetic.  With twice the rows on HALF
+// the SMs an iteration takes about as long (profiles/), and the other half of the GPU runs other pairs' kernels
+// meanwhile — this kernel allocates a whole SM's register file, nothing shares an SM with it.
 // =====================================================================================================================
+constexpr int kRSmem = 16;
 __global__ void __launch_bounds__(kThreads, 1) k_sinkhorn_reg(SinkArgs a) {
   extern __shared__ __align__(16) float smem[];
   __shared__ float red_m[32][17], red_s[32][17];
+  __shared__ float left[kRMax + kRSmem][4];
   const SinkGeom g = sink_geom(a);
   const int n0 = g.n0, C = g.C, G = g.G, b = g.b, nrows = g.nrows, r_begin = g.r_begin, Ga = g.Ga;
   const int c_begin = g.c_begin, c_end = g.c_end;
   const float norm = g.norm, log_mu_last = g.log_mu_last;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int nreg = min(nrows, kRMax), nsm = nrows - nreg;      // rows in registers / in shared memory
 
   const int vlen = (a.n1_max + 1 + 3) & ~3;
   const int rlen = (a.rpc_max + 3) & ~3;
@@ -350,34 +358,50 @@ __global__ void __launch_bounds__(kThreads, 1) k_sinkhorn_reg(SinkArgs a) {
   float* u_s = w_s + vlen;                          // [rlen]  u_r
   float* rmax_s = u_s + rlen;                       // [rlen]  row maxima of my slab
   float* e_s = rmax_s + rlen;                       // [rlen]  column-pass weight of row r
-  float* slab = e_s + rlen;                         // [nrows][slab_ld]
+  float* slab = e_s + rlen;                         // [min(rpc, 16)][slab_ld]: staging of the register rows, then rows 16..
   const int C4 = (C + 3) & ~3;                      // slab rows are padded up to a multiple of 4
   const int n4 = C4 >> 2;
   const int Gf = C >> 2;                            // full groups: one per thread (host guarantees Gf <= kThreads)
   const size_t cs_ld = ((size_t)a.ldp + 3) & ~(size_t)3;
   unsigned* counter = a.err + kErrCounter;
   unsigned target = 0;
+  const bool own = tid < Gf;
+  float4 ereg[kRMax];
 
-  // ---- load the slab, row maxima ------------------------------------------------------------------------------
-  for (int r = warp; r < nrows; r += kWarps) {
-    const float* src = a.Z + (size_t)(r_begin + r) * a.ld;
-    float* dst = slab + (size_t)r * a.slab_ld;
-    float mx = -CUDART_INF_F;
-    for (int j = lane; j < C4; j += 32) {
-      float z = (j < C) ? src[j] : -CUDART_INF_F;
-      dst[j] = z;
-      mx = fmaxf(mx, z);
+  // ---- load the slab (raw scores), row maxima, column maxima of z - rowmax over ALL rows (one grid-wide exchange) ----
+  // two rounds through the same staging area: rows [0, nreg) end up in registers, rows [nreg, nrows) stay
+  for (int round = 0; round < 2; ++round) {
+    const int r0 = round ? nreg : 0, cnt = round ? nsm : nreg;
+    if (round) __syncthreads();                     // round 0's readers are done with the staging area
+    for (int r = warp; r < cnt; r += kWarps) {
+      const float* src = a.Z + (size_t)(r_begin + r0 + r) * a.ld;
+      float* dst = slab + (size_t)r * a.slab_ld;
+      float mx = -CUDART_INF_F;
+      for (int j = lane; j < C4; j += 32) {
+        float z = (j < C) ? src[j] : -CUDART_INF_F;
+        dst[j] = z;
+        mx = fmaxf(mx, z);
+      }
+      mx = warp_max(mx);
+      if (lane == 0) rmax_s[r0 + r] = mx;
     }
-    mx = warp_max(mx);
-    if (lane == 0) rmax_s[r] = mx;
-  }
-  __syncthreads();
-  // ---- column maxima of z - rowmax over ALL rows (one grid-wide exchange) ----------------------------------------
-  if (b < Ga) {
-    for (int j = tid; j < C; j += kThreads) {
-      float m = -CUDART_INF_F;
-      for (int r = 0; r < nrows; ++r) m = fmaxf(m, slab[(size_t)r * a.slab_ld + j] - rmax_s[r]);
-      atomicMax(&a.cmkey[j], cm_key(m));
+    __syncthreads();
+    if (b < Ga && cnt > 0) {
+      for (int j = tid; j < C; j += kThreads) {
+        float m = -CUDART_INF_F;
+        for (int r = 0; r < cnt; ++r) m = fmaxf(m, slab[(size_t)r * a.slab_ld + j] - rmax_s[r0 + r]);
+        atomicMax(&a.cmkey[j], cm_key(m));
+      }
+    }
+    if (tid < 4 * cnt) {
+      const int r = tid >> 2, q = tid & 3, j = 4 * Gf + q;
+      left[r0 + r][q] = (j < C) ? slab[(size_t)r * a.slab_ld + j] : -CUDART_INF_F;
+    }
+    if (round == 0) {
+#pragma unroll
+      for (int r = 0; r < kRMax; ++r)
+        ereg[r] = (own && r < nreg) ? *reinterpret_cast<const float4*>(slab + (size_t)r * a.slab_ld + 4 * tid)
+                                    : make_float4(0.f, 0.f, 0.f, 0.f);
     }
   }
   target += (unsigned)G;
@@ -389,10 +413,26 @@ __global__ void __launch_bounds__(kThreads, 1) k_sinkhorn_reg(SinkArgs a) {
     w_s[j] = (j < C) ? ex2(cm * kLog2e) : 0.f;
   }
   __syncthreads();
-  for (int r = warp; r < nrows; r += kWarps) {      // slab <- E = exp(z - rowmax - cmax), pads 0
+  // slab <- E = exp(z - rowmax - cmax), pads 0: in the registers, in shared memory, in the left-over array
+  {
+    const float4 cm4 = own ? *reinterpret_cast<const float4*>(v_s + 4 * tid) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int r = 0; r < kRMax; ++r) {
+      if (own && r < nreg) {
+        const float rm = rmax_s[r];
+        ereg[r].x = ex2(((ereg[r].x - rm) - cm4.x) * kLog2e); ereg[r].y = ex2(((ereg[r].y - rm) - cm4.y) * kLog2e);
+        ereg[r].z = ex2(((ereg[r].z - rm) - cm4.z) * kLog2e); ereg[r].w = ex2(((ereg[r].w - rm) - cm4.w) * kLog2e);
+      }
+    }
+  }
+  for (int r = warp; r < nsm; r += kWarps) {
     float* row = slab + (size_t)r * a.slab_ld;
-    const float rm = rmax_s[r];
+    const float rm = rmax_s[kRMax + r];
     for (int j = lane; j < C4; j += 32) row[j] = (j < C) ? ex2(((row[j] - rm) - v_s[j]) * kLog2e) : 0.f;
+  }
+  if (tid < 4 * (kRMax + kRSmem)) {
+    const int r = tid >> 2, q = tid & 3, j = 4 * Gf + q;
+    left[r][q] = (r < nrows && j < C) ? ex2(((left[r][q] - rmax_s[r]) - v_s[j]) * kLog2e) : 0.f;
   }
   if (b == 0 && tid == 0) a.err[kErrPath] = GIMS_STATUS_SINKHORN_FAST;
   __syncthreads();
@@ -401,12 +441,8 @@ __global__ void __launch_bounds__(kThreads, 1) k_sinkhorn_reg(SinkArgs a) {
   long long* const gtrace = (tid == 0) ? g_sink_trace : nullptr;
   long long* trace = (b == 0) ? gtrace : nullptr;
 
-  const bool own = tid < Gf;
-  float4 ereg[kRMax];
-#pragma unroll
-  for (int r = 0; r < kRMax; ++r)
-    ereg[r] = (own && r < nrows) ? *reinterpret_cast<const float4*>(slab + (size_t)r * a.slab_ld + 4 * tid)
-                                 : make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4* slab4 = reinterpret_cast<const float4*>(slab) + tid;     // my column group of shared-memory row r: [r * ld4]
+  const int ld4 = a.slab_ld >> 2;
   float4 wreg = own ? *reinterpret_cast<const float4*>(w_s + 4 * tid) : make_float4(0.f, 0.f, 0.f, 0.f);
   float vref = 0.f;                               // reference the current w_s was scaled with
   float v0_prev = v_s[0];                         // v~_0 after the previous iteration
@@ -416,32 +452,45 @@ __global__ void __launch_bounds__(kThreads, 1) k_sinkhorn_reg(SinkArgs a) {
     float* cs = a.colsum + (size_t)(it % 3) * kWays * cs_ld;   // [kWays][cs_ld]
     float* my = cs + (size_t)(b % kWays) * cs_ld;
     const float Rref = norm - vref;
-    float part[kRMax];
-#pragma unroll
-    for (int r = 0; r < kRMax; ++r)
-      part[r] = fmaf(ereg[r].x, wreg.x, ereg[r].y * wreg.y) + fmaf(ereg[r].z, wreg.z, ereg[r].w * wreg.w);
     // 16 sums over 32 lanes with 16 shuffles (a butterfly that halves the number of live values per step) instead
     // of 16 x 5: shuffles issue at one warp instruction per clock per SM and were the longest part of this pass
-    static_assert(kRMax == 16, "the butterfly below is written for 16 row sums");
+    static_assert(kRMax == 16 && kRSmem == 16, "the butterfly below is written for 16 row sums");
 #pragma unroll
-    for (int h = 8, bit = 16; h >= 1; h >>= 1, bit >>= 1) {
-      const bool up = (lane & bit) != 0;
+    for (int half = 0; half < 2; ++half) {
+      if (half == 1 && nsm == 0) break;
+      float part[kRMax];
+      if (half == 0) {
 #pragma unroll
-      for (int i = 0; i < h; ++i) {
-        const float send = up ? part[i] : part[i + h];
-        const float keep = up ? part[i + h] : part[i];
-        part[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+        for (int r = 0; r < kRMax; ++r)
+          part[r] = fmaf(ereg[r].x, wreg.x, ereg[r].y * wreg.y) + fmaf(ereg[r].z, wreg.z, ereg[r].w * wreg.w);
+      } else {
+#pragma unroll
+        for (int r = 0; r < kRSmem; ++r) {
+          const float4 e = (own && r < nsm) ? slab4[(size_t)r * ld4] : make_float4(0.f, 0.f, 0.f, 0.f);
+          part[r] = fmaf(e.x, wreg.x, e.y * wreg.y) + fmaf(e.z, wreg.z, e.w * wreg.w);
+        }
       }
+#pragma unroll
+      for (int h = 8, bit = 16; h >= 1; h >>= 1, bit >>= 1) {
+        const bool up = (lane & bit) != 0;
+#pragma unroll
+        for (int i = 0; i < h; ++i) {
+          const float send = up ? part[i] : part[i + h];
+          const float keep = up ? part[i + h] : part[i];
+          part[i] = keep + __shfl_xor_sync(0xffffffffu, send, bit);
+        }
+      }
+      part[0] += __shfl_xor_sync(0xffffffffu, part[0], 1);
+      if ((lane & 1) == 0) red_m[half * kWarps + warp][lane >> 1] = part[0];      // lane 2r holds the warp's sum of row r
     }
-    part[0] += __shfl_xor_sync(0xffffffffu, part[0], 1);
-    if ((lane & 1) == 0) red_m[warp][lane >> 1] = part[0];      // lane 2r holds the warp's sum of row r
     __syncthreads();
     SINK_TRACE(7);
     if (tid < nrows) {                              // thread r finishes row r
       float sr = 0.f;
+      const int hb = (tid >> 4) * kWarps, rr = tid & 15;
 #pragma unroll
-      for (int w = 0; w < kWarps; ++w) sr += red_m[w][tid];
-      for (int j = 4 * Gf; j < C; ++j) sr = fmaf(slab[(size_t)tid * a.slab_ld + j], w_s[j], sr);
+      for (int w = 0; w < kWarps; ++w) sr += red_m[hb + w][rr];
+      for (int j = 4 * Gf; j < C; ++j) sr = fmaf(left[tid][j - 4 * Gf], w_s[j], sr);
       bad = bad || !sum_ok(sr);
       const float lmu = (r_begin + tid == n0) ? log_mu_last : norm;
       const float lse_rel = vref + logf(sr);               // LSE_j(z + v) - rowmax
@@ -455,9 +504,20 @@ __global__ void __launch_bounds__(kThreads, 1) k_sinkhorn_reg(SinkArgs a) {
         float4 sm = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
         for (int r = 0; r < kRMax; ++r) {
-          const float er = (r < nrows) ? e_s[r] : 0.f;
+          const float er = (r < nreg) ? e_s[r] : 0.f;
           sm.x = fmaf(ereg[r].x, er, sm.x); sm.y = fmaf(ereg[r].y, er, sm.y);
           sm.z = fmaf(ereg[r].z, er, sm.z); sm.w = fmaf(ereg[r].w, er, sm.w);
+        }
+        if (nsm > 0) {
+#pragma unroll
+          for (int r = 0; r < kRSmem; ++r) {
+            if (r < nsm) {
+              const float er = e_s[kRMax + r];
+              const float4 e = slab4[(size_t)r * ld4];
+              sm.x = fmaf(e.x, er, sm.x); sm.y = fmaf(e.y, er, sm.y);
+              sm.z = fmaf(e.z, er, sm.z); sm.w = fmaf(e.w, er, sm.w);
+            }
+          }
         }
         // (packed FFMA2 for these passes and a 16-lanes-per-row finish were tried: both slower on B200)
         SINK_TRACE(6);
@@ -465,9 +525,9 @@ __global__ void __launch_bounds__(kThreads, 1) k_sinkhorn_reg(SinkArgs a) {
                      "f"(sm.z), "f"(sm.w)
                      : "memory");
       }
-      const int jl = 4 * Gf + warp;                 // the (at most 3) left-over columns
+      const int jl = 4 * Gf + warp;                 // the (at most 3) left-over columns: lane = row
       if (jl < C) {
-        const float xx = (lane < nrows) ? slab[(size_t)lane * a.slab_ld + jl] * e_s[lane] : 0.f;
+        const float xx = (lane < nrows) ? left[lane][warp] * e_s[lane] : 0.f;
         const float ss = warp_sum(xx);
         if (lane == 0) atomicAdd(my + jl, ss);
       }
@@ -981,10 +1041,11 @@ bool plan(SinkPlan& p, int n0_max, int n1_max, int G, int smem_optin, bool vec_o
   if (p.dyn_exact > budget) return false;
   p.kind = kSinkExact; p.kg = 0; p.rc = 0; p.slab_rows = 0; p.dyn_smem = 0;
   if (iters <= 0) return true;
-  // register kernel: v, w | u, rmax, e | slab
+  // on-chip kernel: v, w | u, rmax, e | staging / shared-memory rows (16 rows in registers + up to 16 in shared memory)
   const size_t fixed_reg = (2 * vlen + 3 * rlen) * sizeof(float);
-  if (p.rpc <= kRMax && (C >> 2) <= kThreads && fixed_reg + slab_bytes <= budget) {
-    p.kind = kSinkReg; p.slab_rows = p.rpc; p.dyn_smem = fixed_reg + slab_bytes;
+  const size_t stage_bytes = (size_t)(p.rpc < kRMax ? p.rpc : kRMax) * p.slab_ld * sizeof(float);
+  if (p.rpc <= kRMax + kRSmem && (C >> 2) <= kThreads && fixed_reg + stage_bytes <= budget) {
+    p.kind = kSinkReg; p.slab_rows = p.rpc; p.dyn_smem = fixed_reg + stage_bytes;
     return true;
   }
   if (!vec_ok) return true;
@@ -1035,7 +1096,22 @@ size_t carve(SinkWs& w, void* base, size_t cap, int n0_max, int n1_max, int grid
 // Capacities above which the scaled matrix may need the scratch buffer (the register kernel needs none).  The grid of
 // the launch is not known to the workspace query, so it assumes the streaming kernel whenever the register kernel
 // cannot be guaranteed on a part with >= 128 SMs.
-bool may_stream(int n0_max, int n1_max) { return n0_max + 1 > kRMax * 128 || ((n1_max + 1) >> 2) > kThreads; }
+bool may_stream(int n0_max, int n1_max) { return n0_max + 1 > (kRMax + kRSmem) * 64 || ((n1_max + 1) >> 2) > kThreads; }
+
+// Grid of a problem.  The on-chip kernel runs on HALF the SMs whenever its slab then still fits (<= 32 rows per CTA):
+// an iteration is bound by the grid-wide exchange, which gets cheaper with fewer CTAs about as fast as the arithmetic
+// gets longer, and the other half of the GPU stays free for other streams (GIMS_SINKHORN_GRID=full: all SMs, for A/B
+// measurements).  Everything else uses every SM.
+struct SinkGrid { int G; bool half; };
+SinkGrid choose_grid(int n0_max, int n1_max, int sms, int smem_optin, int iters) {
+  static const bool force_full = [] { const char* e = getenv("GIMS_SINKHORN_GRID"); return e && e[0] == 'f'; }();
+  const int full = sms < kMaxGrid ? sms : kMaxGrid;
+  const int half = full / 2;
+  SinkPlan p;
+  if (!force_full && half >= 32 && plan(p, n0_max, n1_max, half, smem_optin, false, iters) && p.kind == kSinkReg)
+    return {half, true};
+  return {full, false};
+}
 
 template <int KG, int RC>
 int launch_stream(SinkArgs& a, int G, size_t dyn, int budget, cudaStream_t st) {
@@ -1093,7 +1169,8 @@ extern "C" int gims_sinkhorn_match(const float* couplings, int ld, int n0_max, i
   GIMS_CUDA_OK(cudaGetDevice(&dev));
   GIMS_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
   GIMS_CUDA_OK(cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev));
-  int G = sms < kMaxGrid ? sms : kMaxGrid;
+  const SinkGrid grid = choose_grid(n0_max, n1_max, sms, smem_optin, iters);
+  const int G = grid.G;
   const bool with_e = may_stream(n0_max, n1_max);
   SinkWs w;
   size_t need = carve(w, workspace, workspace_bytes, n0_max, n1_max, G, with_e);
@@ -1122,7 +1199,7 @@ extern "C" int gims_sinkhorn_match(const float* couplings, int ld, int n0_max, i
   GIMS_CUDA_OK(cudaMemsetAsync(w.err, 0, w.zero_bytes, st));    // clears err and every flag / tag word (contiguous)
   void* params[] = {&a};
   {
-    CoopChainScope chain(st);
+    CoopChainScope chain(st, grid.half);
     GIMS_TRY(chain.rc);
     ProfScope prof(GIMS_PROF_SINKHORN, st);
     if (p.kind == kSinkReg) {

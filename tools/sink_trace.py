@@ -42,6 +42,8 @@ for it in range(1, 12):
 
 import numpy as np
 pc = pc.numpy().astype(np.int64)
+pc = pc[pc[:, 0] > 0]          # CTAs of this launch (the on-chip kernel uses half the SMs)
+print('CTAs traced: %d' % len(pc))
 base = pc[:, 0].min()
 print('per-CTA globaltimer (ns) at iteration 5, relative to the earliest start:')
 print('cta   start  row_done  col_done  hop_done  gather_done')
