@@ -140,6 +140,202 @@ struct TcArgs {
 // Optional pipeline trace (bring-up / profiling): CTA (0,0) stores clock64() stamps, see tools/gemm_trace.py.
 __device__ long long* g_gemm_trace = nullptr;
 
+// Where a tile sits: row segment, live rows / columns, first row / column of the tile, first row of the segment.
+struct TileCoord { int seg, rows, ncols, r0, c0, rbase; };
+
+// The epilogue of one 128 x BN tile for the warp (lane quarter q, column-chunk group grp of kGroups): tcgen05.ld of the
+// accumulator chunks at `lane_base` (n_main / n_corr accumulators BN columns apart), bias / residual / ReLU or the QKV
+// planes or the couplings, stores.  `ready()` is called once the residual prefetch has been issued and must return
+// when the accumulators may be read.  `stg`: this warp's private 32 x 36-float staging tile in shared memory.
+template <int BN, int MODE, int PREC, typename Ready>
+__device__ __forceinline__ void epilogue_tile(const TcArgs& g, const TileCoord& tcd, uint32_t lane_base, int n_main, int n_corr,
+                                              int grp, int kGroups, int q, int lane, uint32_t stg, const float* bias_s,
+                                              Ready&& ready, long long* trace, bool tr0) {
+  using Cfg = TcCfg<BN, PREC>;
+  const int seg = tcd.seg, rows = tcd.rows, ncols = tcd.ncols, r0 = tcd.r0, c0 = tcd.c0, rbase = tcd.rbase;
+  const float wsc = (PREC && g.wscale_inv) ? *g.wscale_inv : 1.f;
+  // Each warp transposes its 32x32 chunks through a private staging tile in the (now idle) pipeline stages, so that
+  // one store instruction covers four complete 128-byte lines of Y and the residual is read the same way.  An SM
+  // takes ~30 bytes of stores per clock (tools/micro/store_rate.cu), which is what this loop should be bound by:
+  // all shared-memory reads of a chunk are issued before the first store, and MODE is a template parameter, so
+  // there is no branch or address arithmetic between the stores.
+  constexpr int kStgLd = 36;                         // floats; 16-byte aligned rows, conflict-free both ways
+  const int rl0 = lane >> 3, cj = (lane & 7) * 4;    // read-back: row i*4 + rl0 of the chunk, columns cj..cj+3
+  const int rfirst = r0 + 32 * q + rl0;              // tile row of read-back slot i = 0; slot i is 4*i further
+  const int nvalid = rows - rfirst;                  // slot i is a live row iff 4*i < nvalid
+  const bool use_r = MODE == 0 && g.R != nullptr;
+  const float* rrow = use_r ? g.R + (size_t)(rbase + rfirst) * g.ldr + c0 + cj : nullptr;
+  float4 rres[8];                                    // residual of the current chunk, fetched one chunk ahead
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+    rres[i] = (use_r && 4 * i < nvalid && c0 + 32 * grp + cj < ncols) ? *reinterpret_cast<const float4*>(rrow + (size_t)(4 * i) * g.ldr + 32 * grp)
+                                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+  ready();                                           // the residual's latency hides behind the tail of the k-loop
+  if (trace && tr0) trace[3] = clock64();
+#pragma unroll 1
+  for (int cc = grp; cc < BN / 32; cc += kGroups) {
+    uint32_t v[32];
+    const uint32_t lane_col = lane_base + (uint32_t)(cc * 32);
+    tmem_ld_32x32(lane_col, v);
+    tmem_ld_wait();
+    for (int a = 1; a < Cfg::kMainAcc + Cfg::kCorrAcc; ++a) {
+      if (a < Cfg::kMainAcc ? a >= n_main : a - Cfg::kMainAcc >= n_corr) continue;   // never written (short K)
+      uint32_t w[32];
+      tmem_ld_32x32(lane_col + (uint32_t)(a * BN), w);       // a >= kMainAcc: the correction accumulators
+      tmem_ld_wait();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
+    }
+    if (PREC) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * wsc);
+    }
+    if (trace && tr0 && cc < 2) trace[56 + 3 * cc] = clock64();
+    const int c = c0 + cc * 32;
+    if (c >= ncols) continue;                                // warp-uniform
+    if (MODE >= 2 && c >= 2 * kD) {
+      // V: key column of this row in Vt; image 1 starts at a 64-aligned column (TMA box starts must be 16-byte
+      // aligned in global memory).  Lanes = consecutive rows = consecutive addresses: coalesced as it is.
+      // Rows between the live count and the next multiple of 64 are ZERO-FILLED: the attention kernel multiplies them
+      // by P = 0, which must not meet a NaN / Inf left over from whatever used this workspace before.
+      const int r = r0 + 32 * q + lane;
+      if (r < ((g.segs.nmax[seg] + 63) & ~63)) {             // never touch the other image's columns
+        const bool row_ok = r < rows;
+        const int cc256 = c & 255;
+        const size_t kcol = (size_t)g.vbase[seg] + r;
+        if (MODE == 2) {
+          float* hi = static_cast<float*>(g.vt) + (size_t)cc256 * g.ldv + kcol;
+          float* lo = hi + (size_t)kD * g.ldv;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float h, l;
+            split_tf32(row_ok ? __uint_as_float(v[j]) + bias_s[cc * 32 + j] : 0.f, h, l);
+            hi[(size_t)j * g.ldv] = h;
+            lo[(size_t)j * g.ldv] = l;
+          }
+        } else {
+          constexpr int FMT = MODE == 4 ? 1 : 0;
+          uint16_t* hi = static_cast<uint16_t*>(g.vt) + (size_t)cc256 * g.ldv + kcol;
+          uint16_t* lo = hi + (size_t)kD * g.ldv;
+          bool ovf = false;
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const float x = row_ok ? __uint_as_float(v[j]) + bias_s[cc * 32 + j] : 0.f;
+            if (FMT == 0) ovf = ovf || fabsf(x) >= 32768.f;
+            uint32_t wh, wl;
+            if (MODE == 3) split16x2<FMT>(x, 0.f, wh, wl); else wh = pack16<FMT>(x, 0.f);
+            hi[(size_t)j * g.ldv] = (uint16_t)wh;
+            if (MODE == 3) lo[(size_t)j * g.ldv] = (uint16_t)wl;
+          }
+          if (ovf && g.status) atomicOr(g.status, GIMS_STATUS_FP16_RANGE);
+        }
+      }
+      continue;
+    }
+    __syncwarp();                                            // the previous chunk has been read back
+#pragma unroll
+    for (int j = 0; j < 32; j += 4)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (uint32_t)((lane * kStgLd + j) * 4)), "r"(v[j]),
+                   "r"(v[j + 1]), "r"(v[j + 2]), "r"(v[j + 3])
+                   : "memory");
+    __syncwarp();
+    if (trace && tr0 && cc < 2) trace[57 + 3 * cc] = clock64();
+    if (MODE == 1) {
+      // couplings rows are n1_max + 1 floats long (not 16-byte aligned) and end raggedly: scalar, one row per store
+      if (c + lane < ncols) {
+        float* yp = g.Y + (size_t)(r0 + 32 * q) * g.ldy + c + lane;
+        const int nrow = min(32, rows - (r0 + 32 * q));
+#pragma unroll 8
+        for (int i = 0; i < 32; ++i) {
+          float x;
+          asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(stg + (uint32_t)((i * kStgLd + lane) * 4)) : "memory");
+          if (i < nrow) yp[(size_t)i * g.ldy] = x * g.scale;
+        }
+      }
+      continue;
+    }
+    const float4 bias4 = *reinterpret_cast<const float4*>(bias_s + cc * 32 + cj);
+    float4 o[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(o[i].x), "=f"(o[i].y), "=f"(o[i].z), "=f"(o[i].w)
+                   : "r"(stg + (uint32_t)(((i * 4 + rl0) * kStgLd + cj) * 4))
+                   : "memory");
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      o[i].x += bias4.x + rres[i].x; o[i].y += bias4.y + rres[i].y;
+      o[i].z += bias4.z + rres[i].z; o[i].w += bias4.w + rres[i].w;
+    }
+    if (use_r && cc + kGroups < BN / 32 && c + 32 * kGroups < ncols) {       // my next chunk's residual, one chunk ahead
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (4 * i < nvalid) rres[i] = *reinterpret_cast<const float4*>(rrow + (size_t)(4 * i) * g.ldr + (cc + kGroups) * 32);
+    }
+    if (MODE >= 2) {
+      if (c < kD) {
+        // Q: one fp32 plane, scaled by log2(e)/sqrt(64) (scores in the log2 domain); the attention kernel splits
+        // its own query rows when it loads them into TMEM
+        float* qd = g.qp + (size_t)(rbase + rfirst) * kD + c + cj;
+        const float sc = 0.18033688011112042f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i)
+          if (4 * i < nvalid)
+            *reinterpret_cast<float4*>(qd + (size_t)(4 * i) * kD) =
+                make_float4(o[i].x * sc, o[i].y * sc, o[i].z * sc, o[i].w * sc);
+      } else if (MODE == 2) {
+        float* hi = static_cast<float*>(g.kp) + (size_t)(rbase + rfirst) * kD + (c & 255) + cj;
+        const size_t plane = (size_t)g.rows_total * kD;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          float4 h, l;
+          split_tf32(o[i].x, h.x, l.x); split_tf32(o[i].y, h.y, l.y);
+          split_tf32(o[i].z, h.z, l.z); split_tf32(o[i].w, h.w, l.w);
+          if (4 * i < nvalid) {
+            *reinterpret_cast<float4*>(hi + (size_t)(4 * i) * kD) = h;
+            *reinterpret_cast<float4*>(hi + (size_t)(4 * i) * kD + plane) = l;
+          }
+        }
+      } else {
+        // K: 16-bit planes, four channels = one 8-byte store per plane
+        constexpr int FMT = MODE == 4 ? 1 : 0;
+        uint16_t* hi = static_cast<uint16_t*>(g.kp) + (size_t)(rbase + rfirst) * kD + (c & 255) + cj;
+        const size_t plane = (size_t)g.rows_total * kD;
+        bool ovf = false;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          uint2 h, l;
+          if (FMT == 0 && 4 * i < nvalid)
+            ovf = ovf || fmaxf(fmaxf(fabsf(o[i].x), fabsf(o[i].y)), fmaxf(fabsf(o[i].z), fabsf(o[i].w))) >= 32768.f;
+          if (MODE == 3) {
+            split16x2<FMT>(o[i].x, o[i].y, h.x, l.x);
+            split16x2<FMT>(o[i].z, o[i].w, h.y, l.y);
+          } else {
+            h.x = pack16<FMT>(o[i].x, o[i].y);
+            h.y = pack16<FMT>(o[i].z, o[i].w);
+          }
+          if (4 * i < nvalid) {
+            *reinterpret_cast<uint2*>(hi + (size_t)(4 * i) * kD) = h;
+            if (MODE == 3) *reinterpret_cast<uint2*>(hi + (size_t)(4 * i) * kD + plane) = l;
+          }
+        }
+        if (ovf && g.status) atomicOr(g.status, GIMS_STATUS_FP16_RANGE);
+      }
+    } else {
+      float* yp = g.Y + (size_t)(rbase + rfirst) * g.ldy + c + cj;
+      const bool relu = g.relu != 0;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float4 y = o[i];
+        if (relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
+        if (4 * i < nvalid) *reinterpret_cast<float4*>(yp + (size_t)(4 * i) * g.ldy) = y;
+      }
+    }
+    if (trace && tr0 && cc < 2) trace[58 + 3 * cc] = clock64();
+  }
+}
+
 // MODE 0: Y = act(acc + bias + R);  1: couplings (score GEMM);  QKV projection: 2: Q / K / Vt tf32 planes,
 // 3: fp16 hi + lo planes, 4: one bf16 plane (K / Vt; Q stays fp32)
 template <int BN, int MODE, int PREC>
@@ -349,190 +545,14 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
     // rows past the live count may hold anything (other segments, stale scratch): only live rows raise the range flag
     if (PREC && g.status && amax >= 32768.f && r0 + t < rows) atomicOr(g.status, GIMS_STATUS_FP16_RANGE);
     // ---- epilogue ----
-    const float wsc = (PREC && g.wscale_inv) ? *g.wscale_inv : 1.f;
-    const int n_main = nkb < Cfg::kMainAcc ? nkb : Cfg::kMainAcc;
-    const int n_corr = nkb < Cfg::kCorrAcc ? nkb : Cfg::kCorrAcc;
-    // Each warp transposes its 32x32 chunks through a private staging tile in the (now idle) pipeline stages, so that
-    // one store instruction covers four complete 128-byte lines of Y and the residual is read the same way.  An SM
-    // takes ~30 bytes of stores per clock (tools/micro/store_rate.cu), which is what this loop should be bound by:
-    // all shared-memory reads of a chunk are issued before the first store, and MODE is a template parameter, so
-    // there is no branch or address arithmetic between the stores.
-    constexpr int kStgLd = 36;                         // floats; 16-byte aligned rows, conflict-free both ways
-    const uint32_t stg = smem_u32(smem) + (uint32_t)((q + 4 * grp) * 32 * kStgLd * 4);
-    const int rl0 = lane >> 3, cj = (lane & 7) * 4;    // read-back: row i*4 + rl0 of the chunk, columns cj..cj+3
-    const int rfirst = r0 + 32 * q + rl0;              // tile row of read-back slot i = 0; slot i is 4*i further
-    const int nvalid = rows - rfirst;                  // slot i is a live row iff 4*i < nvalid
-    const bool use_r = MODE == 0 && g.R != nullptr;
-    const float* rrow = use_r ? g.R + (size_t)(rbase + rfirst) * g.ldr + c0 + cj : nullptr;
-    float4 rres[8];                                    // residual of the current chunk, fetched one chunk ahead
-#pragma unroll
-    for (int i = 0; i < 8; ++i)
-      rres[i] = (use_r && 4 * i < nvalid && c0 + 32 * grp + cj < ncols) ? *reinterpret_cast<const float4*>(rrow + (size_t)(4 * i) * g.ldr + 32 * grp)
-                                                             : make_float4(0.f, 0.f, 0.f, 0.f);
-    mbar_wait(accum_full, 0);                          // the residual's latency hides behind the tail of the k-loop
-    tcgen05_fence_after();
-    if (trace && tr0) trace[3] = clock64();
-#pragma unroll 1
-    for (int cc = grp; cc < BN / 32; cc += kGroups) {
-      uint32_t v[32];
-      const uint32_t lane_col = lane_base + (uint32_t)(cc * 32);
-      tmem_ld_32x32(lane_col, v);
-      tmem_ld_wait();
-      for (int a = 1; a < Cfg::kMainAcc + Cfg::kCorrAcc; ++a) {
-        if (a < Cfg::kMainAcc ? a >= n_main : a - Cfg::kMainAcc >= n_corr) continue;   // never written (short K)
-        uint32_t w[32];
-        tmem_ld_32x32(lane_col + (uint32_t)(a * BN), w);       // a >= kMainAcc: the correction accumulators
-        tmem_ld_wait();
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(w[j]));
-      }
-      if (PREC) {
-#pragma unroll
-        for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) * wsc);
-      }
-      if (trace && tr0 && cc < 2) trace[56 + 3 * cc] = clock64();
-      const int c = c0 + cc * 32;
-      if (c >= ncols) continue;                                // warp-uniform
-      if (MODE >= 2 && c >= 2 * kD) {
-        // V: key column of this row in Vt; image 1 starts at a 64-aligned column (TMA box starts must be 16-byte
-        // aligned in global memory).  Lanes = consecutive rows = consecutive addresses: coalesced as it is.
-        // Rows between the live count and the next multiple of 64 are ZERO-FILLED: the attention kernel multiplies them
-        // by P = 0, which must not meet a NaN / Inf left over from whatever used this workspace before.
-        const int r = r0 + 32 * q + lane;
-        if (r < ((g.segs.nmax[seg] + 63) & ~63)) {             // never touch the other image's columns
-          const bool row_ok = r < rows;
-          const int cc256 = c & 255;
-          const size_t kcol = (size_t)g.vbase[seg] + r;
-          if (MODE == 2) {
-            float* hi = static_cast<float*>(g.vt) + (size_t)cc256 * g.ldv + kcol;
-            float* lo = hi + (size_t)kD * g.ldv;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float h, l;
-              split_tf32(row_ok ? __uint_as_float(v[j]) + bias_s[cc * 32 + j] : 0.f, h, l);
-              hi[(size_t)j * g.ldv] = h;
-              lo[(size_t)j * g.ldv] = l;
-            }
-          } else {
-            constexpr int FMT = MODE == 4 ? 1 : 0;
-            uint16_t* hi = static_cast<uint16_t*>(g.vt) + (size_t)cc256 * g.ldv + kcol;
-            uint16_t* lo = hi + (size_t)kD * g.ldv;
-            bool ovf = false;
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const float x = row_ok ? __uint_as_float(v[j]) + bias_s[cc * 32 + j] : 0.f;
-              if (FMT == 0) ovf = ovf || fabsf(x) >= 32768.f;
-              uint32_t wh, wl;
-              if (MODE == 3) split16x2<FMT>(x, 0.f, wh, wl); else wh = pack16<FMT>(x, 0.f);
-              hi[(size_t)j * g.ldv] = (uint16_t)wh;
-              if (MODE == 3) lo[(size_t)j * g.ldv] = (uint16_t)wl;
-            }
-            if (ovf && g.status) atomicOr(g.status, GIMS_STATUS_FP16_RANGE);
-          }
-        }
-        continue;
-      }
-      __syncwarp();                                            // the previous chunk has been read back
-#pragma unroll
-      for (int j = 0; j < 32; j += 4)
-        asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(stg + (uint32_t)((lane * kStgLd + j) * 4)), "r"(v[j]),
-                     "r"(v[j + 1]), "r"(v[j + 2]), "r"(v[j + 3])
-                     : "memory");
-      __syncwarp();
-      if (trace && tr0 && cc < 2) trace[57 + 3 * cc] = clock64();
-      if (MODE == 1) {
-        // couplings rows are n1_max + 1 floats long (not 16-byte aligned) and end raggedly: scalar, one row per store
-        if (c + lane < ncols) {
-          float* yp = g.Y + (size_t)(r0 + 32 * q) * g.ldy + c + lane;
-          const int nrow = min(32, rows - (r0 + 32 * q));
-#pragma unroll 8
-          for (int i = 0; i < 32; ++i) {
-            float x;
-            asm volatile("ld.shared.f32 %0, [%1];" : "=f"(x) : "r"(stg + (uint32_t)((i * kStgLd + lane) * 4)) : "memory");
-            if (i < nrow) yp[(size_t)i * g.ldy] = x * g.scale;
-          }
-        }
-        continue;
-      }
-      const float4 bias4 = *reinterpret_cast<const float4*>(bias_s + cc * 32 + cj);
-      float4 o[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
-                     : "=f"(o[i].x), "=f"(o[i].y), "=f"(o[i].z), "=f"(o[i].w)
-                     : "r"(stg + (uint32_t)(((i * 4 + rl0) * kStgLd + cj) * 4))
-                     : "memory");
-      }
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        o[i].x += bias4.x + rres[i].x; o[i].y += bias4.y + rres[i].y;
-        o[i].z += bias4.z + rres[i].z; o[i].w += bias4.w + rres[i].w;
-      }
-      if (use_r && cc + kGroups < BN / 32 && c + 32 * kGroups < ncols) {       // my next chunk's residual, one chunk ahead
-#pragma unroll
-        for (int i = 0; i < 8; ++i)
-          if (4 * i < nvalid) rres[i] = *reinterpret_cast<const float4*>(rrow + (size_t)(4 * i) * g.ldr + (cc + kGroups) * 32);
-      }
-      if (MODE >= 2) {
-        if (c < kD) {
-          // Q: one fp32 plane, scaled by log2(e)/sqrt(64) (scores in the log2 domain); the attention kernel splits
-          // its own query rows when it loads them into TMEM
-          float* qd = g.qp + (size_t)(rbase + rfirst) * kD + c + cj;
-          const float sc = 0.18033688011112042f;
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (4 * i < nvalid)
-              *reinterpret_cast<float4*>(qd + (size_t)(4 * i) * kD) =
-                  make_float4(o[i].x * sc, o[i].y * sc, o[i].z * sc, o[i].w * sc);
-        } else if (MODE == 2) {
-          float* hi = static_cast<float*>(g.kp) + (size_t)(rbase + rfirst) * kD + (c & 255) + cj;
-          const size_t plane = (size_t)g.rows_total * kD;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            float4 h, l;
-            split_tf32(o[i].x, h.x, l.x); split_tf32(o[i].y, h.y, l.y);
-            split_tf32(o[i].z, h.z, l.z); split_tf32(o[i].w, h.w, l.w);
-            if (4 * i < nvalid) {
-              *reinterpret_cast<float4*>(hi + (size_t)(4 * i) * kD) = h;
-              *reinterpret_cast<float4*>(hi + (size_t)(4 * i) * kD + plane) = l;
-            }
-          }
-        } else {
-          // K: 16-bit planes, four channels = one 8-byte store per plane
-          constexpr int FMT = MODE == 4 ? 1 : 0;
-          uint16_t* hi = static_cast<uint16_t*>(g.kp) + (size_t)(rbase + rfirst) * kD + (c & 255) + cj;
-          const size_t plane = (size_t)g.rows_total * kD;
-          bool ovf = false;
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            uint2 h, l;
-            if (FMT == 0 && 4 * i < nvalid)
-              ovf = ovf || fmaxf(fmaxf(fabsf(o[i].x), fabsf(o[i].y)), fmaxf(fabsf(o[i].z), fabsf(o[i].w))) >= 32768.f;
-            if (MODE == 3) {
-              split16x2<FMT>(o[i].x, o[i].y, h.x, l.x);
-              split16x2<FMT>(o[i].z, o[i].w, h.y, l.y);
-            } else {
-              h.x = pack16<FMT>(o[i].x, o[i].y);
-              h.y = pack16<FMT>(o[i].z, o[i].w);
-            }
-            if (4 * i < nvalid) {
-              *reinterpret_cast<uint2*>(hi + (size_t)(4 * i) * kD) = h;
-              if (MODE == 3) *reinterpret_cast<uint2*>(hi + (size_t)(4 * i) * kD + plane) = l;
-            }
-          }
-          if (ovf && g.status) atomicOr(g.status, GIMS_STATUS_FP16_RANGE);
-        }
-      } else {
-        float* yp = g.Y + (size_t)(rbase + rfirst) * g.ldy + c + cj;
-        const bool relu = g.relu != 0;
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          float4 y = o[i];
-          if (relu) { y.x = fmaxf(y.x, 0.f); y.y = fmaxf(y.y, 0.f); y.z = fmaxf(y.z, 0.f); y.w = fmaxf(y.w, 0.f); }
-          if (4 * i < nvalid) *reinterpret_cast<float4*>(yp + (size_t)(4 * i) * g.ldy) = y;
-        }
-      }
-      if (trace && tr0 && cc < 2) trace[58 + 3 * cc] = clock64();
+    {
+      const int n_main = nkb < Cfg::kMainAcc ? nkb : Cfg::kMainAcc;
+      const int n_corr = nkb < Cfg::kCorrAcc ? nkb : Cfg::kCorrAcc;
+      const TileCoord tcd = {seg, rows, ncols, r0, c0, rbase};
+      // each warp transposes through a private staging tile in the (now idle) pipeline stages
+      const uint32_t stg = smem_u32(smem) + (uint32_t)((q + 4 * grp) * 32 * 36 * 4);
+      epilogue_tile<BN, MODE, PREC>(g, tcd, lane_base, n_main, n_corr, grp, kGroups, q, lane, stg, bias_s,
+                                    [&] { mbar_wait(accum_full, 0); tcgen05_fence_after(); }, trace, tr0);
     }
     tcgen05_fence_before();
     if (trace && tr0) trace[4] = clock64();
@@ -547,6 +567,281 @@ k_gemm_tc(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUt
     unsigned long long gt; asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
     trace[7] = (long long)gt;
   }
+}
+
+// =====================================================================================================================
+// Persistent variant of the fp16 hi+lo kernel (BN = 128): a CTA walks over several output tiles, and the store-bound
+// epilogue of tile i runs on its own warps while the k-loop of tile i+1 is already feeding the tensor pipe.  One tile
+// per CTA spends more than half of its life outside the k-loop (prologue 1.4 k clk, first TMA round trip 1.4 k, epilogue
+// 3.3 k of 11.8 k clk: profiles/r01_gemm_pipeline_trace.txt, tools/gemm_trace.py); here that is paid once per CTA.
+//
+// TMEM (512 columns): accumulators 0 / 1 of the tile in flight (2 x 128, even / odd k-blocks as in k_gemm_tc — the chains
+// stay short, the arithmetic is identical) | PARK 128 | A ring 2 x 64.  When a tile's MMAs have retired the splitter
+// warps fold accumulator 0 + 1 into PARK (tcgen05.ld, add, tcgen05.st: ~400 clk) and hand the accumulators back to the
+// issuers; the four epilogue warps drain PARK with the code of the one-tile kernel (epilogue_tile).
+//   warps 0-3, 7-10  A splitters (as k_gemm_tc at PREC 1) + the fold      warp 4  TMA producer
+//   warps 5, 6       MMA issuers                                          warps 11-14  epilogue (lane quarter = warp & 3)
+// Barriers per tile: accum_full (issuers -> splitters), acc_free + park_full (fold -> issuers / epilogue),
+// park_free (epilogue -> next fold).  The TMA / conversion rings count k-blocks across tiles.
+// =====================================================================================================================
+constexpr int kThreadsP = 480;
+struct TcpCfg {
+  static constexpr int BN = 128;
+  static constexpr int kBlockK = 64;
+  static constexpr int kABytes = BM * kBlockK * 4;          // 32 KB raw fp32 A (two 32-float boxes)
+  static constexpr int kWBytes = BN * 64 * 2;               // 16 KB per 16-bit W plane
+  static constexpr int kStageBytes = kABytes + 2 * kWBytes; // 64 KB
+  static constexpr int kStages = 3;
+  static constexpr int kRing = 2;
+  static constexpr int kParkCol = 2 * BN;
+  static constexpr int kRingCol = 3 * BN;
+  static constexpr int kStgBytes = 4 * 32 * 36 * 4;         // one staging tile per epilogue warp
+  static constexpr int kBarriers = 2 * kStages + 2 * kRing + 4;
+  static constexpr int kBiasOff = (kBarriers * 8 + 16 + 15) & ~15;
+  static constexpr int kSmemBytes = kStages * kStageBytes + kStgBytes + 1024 /*align*/ + kBiasOff + 2 * BN * 4;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kThreadsP, 1)
+k_gemm_tcp(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
+           const __grid_constant__ CUtensorMap mapWhi, const __grid_constant__ CUtensorMap mapWlo, TcArgs g, int col_tiles,
+           int total_work) {
+  using Cfg = TcpCfg;
+  constexpr int BN = Cfg::BN;
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* stg_base = smem + Cfg::kStages * Cfg::kStageBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(stg_base + Cfg::kStgBytes);
+  uint64_t* full = bars;                                // [kStages] TMA bytes landed (A raw, W_hi, W_lo)
+  uint64_t* empty = bars + Cfg::kStages;                // [kStages] the MMAs that read the W tiles have retired
+  uint64_t* conv = bars + 2 * Cfg::kStages;             // [kRing]   A_hi / A_lo of a k-block are in TMEM
+  uint64_t* tfree = conv + Cfg::kRing;                  // [kRing]   the MMAs that read that TMEM slot have retired
+  uint64_t* accum_full = tfree + Cfg::kRing;            // the tile's MMAs have retired
+  uint64_t* acc_free = accum_full + 1;                  // accumulators folded into PARK: the next tile may overwrite them
+  uint64_t* park_full = acc_free + 1;                   // PARK holds a finished tile
+  uint64_t* park_free = park_full + 1;                  // the epilogue has read PARK
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(park_free + 1);
+  float* bias_s = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(bars) + Cfg::kBiasOff);   // [2][BN]
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  constexpr int kWarpTma = 4, kWarpMma = 5, kWarpEpi = 11;
+  // optional timeline of CTA 0 (tools/gemm_trace.py): 8 stamps per tile for the first 4 tiles, after the entry stamp
+  long long* trace = (blockIdx.x == 0 && lane == 0) ? g_gemm_trace : nullptr;
+  if (trace && threadIdx.x == 0) trace[0] = clock64();
+#define TCP_TRACE(k) do { if (trace && lt < 4) trace[8 + lt * 8 + (k)] = clock64(); } while (0)
+  const int nkb = (g.K0 + g.K1) / Cfg::kBlockK;
+  const int n_issuers = nkb >= 2 ? 2 : 1;
+
+  // the live row counts are device scalars: read once (a global load per tile per role cost ~800 clk at every tile
+  // boundary), before the start-up barrier below
+  __shared__ int cnt_s[kMaxSegs];
+  if (threadIdx.x < kMaxSegs) cnt_s[threadIdx.x] = (int)threadIdx.x < g.segs.nseg ? seg_count(g.segs, threadIdx.x) : 0;
+  // work item -> tile; identical in every role.  Tiles outside the live rows / columns are skipped by everybody.
+  auto decode = [&](int w, TileCoord& t, bool from_global = false) -> bool {
+    const int rt = w / col_tiles, ct = w - rt * col_tiles;
+    int seg = 0, tile = rt;
+    if (MODE != 1) {
+      while (seg + 1 < g.segs.nseg && rt >= g.tile_end[seg]) ++seg;
+      tile = rt - (seg ? g.tile_end[seg - 1] : 0);
+    }
+    t.seg = seg;
+    // (the TMA warp does not wait at the start-up barrier and reads the counts itself; it runs ahead anyway)
+    t.rows = from_global ? seg_count(g.segs, seg) : cnt_s[seg];
+    t.ncols = MODE == 1 ? (from_global ? seg_count(g.segs, 1) : cnt_s[1]) : g.N;
+    t.r0 = tile * BM; t.c0 = ct * BN;
+    t.rbase = g.segs.base[seg];
+    return t.r0 < t.rows && t.c0 < t.ncols;
+  };
+  const int wbase = MODE == 1 ? g.segs.base[1] : 0;
+
+  if (warp == kWarpTma && lane == 0) {
+    tma_prefetch_desc(&mapA0);
+    if (g.K1) tma_prefetch_desc(&mapA1);
+    tma_prefetch_desc(&mapWhi);
+    tma_prefetch_desc(&mapWlo);
+    for (int s = 0; s < Cfg::kStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    for (int s = 0; s < Cfg::kRing; ++s) { mbar_init(&conv[s], 8); mbar_init(&tfree[s], 1); }
+    mbar_init(accum_full, n_issuers);
+    mbar_init(acc_free, 8);
+    mbar_init(park_full, 8);
+    mbar_init(park_free, 4);
+    fence_barrier_init();
+  }
+  if (warp == kWarpMma) tmem_alloc<512>(tmem_slot);
+  tcgen05_fence_before();
+  if (warp == kWarpTma) asm volatile("bar.arrive 1, %0;" ::"n"(kThreadsP) : "memory");
+  else                  asm volatile("bar.sync 1, %0;" ::"n"(kThreadsP) : "memory");
+  tcgen05_fence_after();
+  const uint32_t tmem_base = __shfl_sync(0xffffffffu, *tmem_slot, 0);
+  auto stage_ptr = [&](int s) { return smem + (size_t)s * Cfg::kStageBytes; };
+
+  if (warp == kWarpTma) {
+    // ===== TMA producer: runs ahead across tile boundaries as far as the stage ring allows =====
+    if (lane == 0) {
+      int s = 0; uint32_t ph = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        TileCoord t;
+        if (!decode(w, t, true)) continue;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&empty[s], ph ^ 1);
+          uint8_t* st = stage_ptr(s);
+          mbar_arrive_expect_tx(&full[s], Cfg::kABytes + 2 * Cfg::kWBytes);
+          const int k = kb * Cfg::kBlockK;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int ka = k + 32 * h;
+            if (ka < g.K0) tma_load_2d(st + h * 16384, &mapA0, &full[s], ka, t.rbase + t.r0);
+            else           tma_load_2d(st + h * 16384, &mapA1, &full[s], ka - g.K0, t.rbase + t.r0);
+          }
+          tma_load_2d(st + Cfg::kABytes, &mapWhi, &full[s], k, wbase + t.c0);
+          tma_load_2d(st + Cfg::kABytes + Cfg::kWBytes, &mapWlo, &full[s], k, wbase + t.c0);
+          if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
+        }
+      }
+    }
+  } else if (warp == kWarpMma || warp == kWarpMma + 1) {
+    // ===== MMA issuers: lane 0 of warp kWarpMma + t handles the k-blocks kb = t, t + 2, ... of every tile =====
+    const int t = __shfl_sync(0xffffffffu, warp - kWarpMma, 0);
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_f16(BM, BN, 0);
+      const uint64_t d_stage0 = umma_desc_sw128(smem_u32(stage_ptr(0) + Cfg::kABytes));
+      const uint32_t acc = tmem_base + t * BN;
+      int last = -1;
+      for (int kb = t; kb < nkb; kb += 2) last = kb;
+      int lt = 0;                                          // live tiles so far
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        TileCoord tcd;
+        if (!decode(w, tcd)) continue;
+        if (lt > 0 && last >= 0) { mbar_wait(acc_free, (uint32_t)(lt - 1) & 1u); tcgen05_fence_after(); }
+        for (int kb = t; kb < nkb; kb += 2) {
+          const int gk = lt * nkb + kb;
+          const int s = gk % Cfg::kStages, slot = gk % Cfg::kRing;
+          mbar_wait(&conv[slot], (uint32_t)(gk / Cfg::kRing) & 1u);
+          tcgen05_fence_after();
+          const uint64_t w_hi = d_stage0 + (uint64_t)((s * Cfg::kStageBytes) >> 4);
+          const uint64_t w_lo = w_hi + (Cfg::kWBytes >> 4);
+          const uint32_t a_hi = tmem_base + Cfg::kRingCol + slot * 64;
+          const uint32_t a_lo = a_hi + 32;
+          const uint32_t fresh = kb >= 2 ? 1u : 0u;        // 0: first k-block of this issuer in this tile
+          if (t == 0 && kb == 0) TCP_TRACE(7);
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            const uint64_t koff = (ks * 32) >> 4;
+            umma_f16_ts(acc, a_lo + ks * 8, w_hi + koff, idesc, ks ? 1u : fresh);
+            umma_f16_ts(acc, a_hi + ks * 8, w_lo + koff, idesc, 1u);
+            umma_f16_ts(acc, a_hi + ks * 8, w_hi + koff, idesc, 1u);
+          }
+          umma_commit(&empty[s]);
+          umma_commit(&tfree[slot]);
+          if (kb == last) umma_commit(accum_full);
+        }
+        ++lt;
+      }
+    }
+  } else if (warp < 4 || (warp >= 7 && warp < kWarpEpi)) {
+    // ===== A splitters (thread = tile row = TMEM lane; group grp converts box grp of every k-block), then the fold =====
+    const int grp = warp >= 7 ? 1 : 0;
+    const int q = warp & 3;
+    const int t = 32 * q + lane;
+    const uint32_t lane_base = tmem_base + ((uint32_t)(32 * q) << 16);
+    const int n_main = nkb < 2 ? nkb : 2;
+    // PARK = accumulator 0 + accumulator 1 of tile f (fp32, RN — what the one-tile epilogue computes), then the
+    // accumulators go back to the issuers
+    auto fold = [&](int f) {
+      int lt = f;                                          // (for the trace macro)
+      mbar_wait(accum_full, (uint32_t)f & 1u);
+      tcgen05_fence_after();
+      if (warp == 0) TCP_TRACE(2);
+      if (f > 0) { mbar_wait(park_free, (uint32_t)(f - 1) & 1u); tcgen05_fence_after(); }
+      if (warp == 0) TCP_TRACE(3);
+#pragma unroll
+      for (int cc = grp; cc < BN / 32; cc += 2) {
+        uint32_t v[32];
+        tmem_ld_32x32(lane_base + (uint32_t)(cc * 32), v);
+        if (n_main > 1) {
+          uint32_t x[32];
+          tmem_ld_32x32(lane_base + (uint32_t)(BN + cc * 32), x);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __float_as_uint(__uint_as_float(v[j]) + __uint_as_float(x[j]));
+        } else {
+          tmem_ld_wait();
+        }
+        tmem_st_32x32(lane_base + (uint32_t)(Cfg::kParkCol + cc * 32), v);
+      }
+      tmem_st_wait();
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) { mbar_arrive(acc_free); mbar_arrive(park_full); }
+      if (warp == 0) TCP_TRACE(4);
+    };
+    // (Converting the first k-blocks of the next tile BEFORE the fold was tried: the fold then starts later by as much
+    // as the issuers gain afterwards — the stage ring, not the conversion, decides when the next tile's operands land.)
+    int lt = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      TileCoord tcd;
+      if (!decode(w, tcd)) continue;
+      float amax = 0.f;
+      for (int kb = 0; kb < nkb; ++kb) {
+        const int gk = lt * nkb + kb;
+        const int s = gk % Cfg::kStages, slot = gk % Cfg::kRing;
+        mbar_wait(&full[s], (uint32_t)(gk / Cfg::kStages) & 1u);
+        if (warp == 0 && kb == 0) TCP_TRACE(0);
+        uint32_t hi[16], lo[16];
+        const uint4* rowp = reinterpret_cast<const uint4*>(stage_ptr(s) + grp * 16384 + t * 128);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const uint4 v = rowp[j ^ (t & 7)];
+          const float f0 = __uint_as_float(v.x), f1 = __uint_as_float(v.y), f2 = __uint_as_float(v.z), f3 = __uint_as_float(v.w);
+          amax = fmaxf(amax, fmaxf(fmaxf(fabsf(f0), fabsf(f1)), fmaxf(fabsf(f2), fabsf(f3))));
+          split16x2<0>(f0, f1, hi[2 * j], lo[2 * j]);
+          split16x2<0>(f2, f3, hi[2 * j + 1], lo[2 * j + 1]);
+        }
+        mbar_wait(&tfree[slot], ((uint32_t)(gk / Cfg::kRing) & 1u) ^ 1u);   // MMAs of k-block gk - kRing are done
+        tcgen05_fence_after();
+        tmem_st_32x16(lane_base + Cfg::kRingCol + slot * 64 + 16 * grp, hi);
+        tmem_st_32x16(lane_base + Cfg::kRingCol + slot * 64 + 32 + 16 * grp, lo);
+        tmem_st_wait();
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&conv[slot]);
+      }
+      if (warp == 0) TCP_TRACE(1);
+      // rows past the live count may hold anything (other segments, stale scratch): only live rows raise the range flag
+      if (g.status && amax >= 32768.f && tcd.r0 + t < tcd.rows) atomicOr(g.status, GIMS_STATUS_FP16_RANGE);
+      fold(lt);
+      ++lt;
+    }
+  } else {
+    // ===== epilogue warps: drain PARK while the next tile's k-loop runs =====
+    const int q = warp & 3;
+    const int et = threadIdx.x - kWarpEpi * 32;            // 0..127
+    const uint32_t lane_base = tmem_base + ((uint32_t)(32 * q) << 16) + Cfg::kParkCol;
+    const uint32_t stg = smem_u32(stg_base) + (uint32_t)((warp - kWarpEpi) * 32 * 36 * 4);
+    int lt = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+      TileCoord tcd;
+      if (!decode(w, tcd)) continue;
+      float* bias_t = bias_s + (lt & 1) * BN;             // the other half may still be read by a slower epilogue warp
+      bias_t[et] = (g.bias && tcd.c0 + et < g.N) ? g.bias[tcd.c0 + et] : 0.f;
+      asm volatile("bar.sync 2, 128;" ::: "memory");
+      epilogue_tile<BN, MODE, 1>(g, tcd, lane_base, 1, 0, 0, 1, q, lane, stg, bias_t,
+                                 [&] { mbar_wait(park_full, (uint32_t)lt & 1u); tcgen05_fence_after();
+                                       if (warp == kWarpEpi) TCP_TRACE(5); }, nullptr, false);
+      tcgen05_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(park_free);
+      if (warp == kWarpEpi) TCP_TRACE(6);
+      ++lt;
+    }
+  }
+#undef TCP_TRACE
+  __syncthreads();
+  if (warp == kWarpMma) {
+    tcgen05_fence_after();
+    tmem_dealloc<512>(tmem_base);
+  }
+  if (trace && threadIdx.x == 0) trace[1] = clock64();
 }
 
 // x -> (hi, lo) planes, hi = tf32(x); used for activations that act as the "weight" operand (score GEMM)
@@ -589,6 +884,40 @@ int launch_tc(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w
   cfg.numAttrs = 0;
   ProfScope prof(prof_class, st);
   GIMS_CUDA_OK(cudaLaunchKernelEx(&cfg, k_gemm_tc<BN, MODE, PREC>, a0, a1, whi, wlo, g));
+  count_launch();
+  return GIMS_OK;
+}
+
+// Persistent launch: `total` = col_tiles * row_tiles work items, row-tile major (the column tiles of one row tile run on
+// neighbouring CTAs at the same time and share the A tile in L2).  Grid: enough CTAs that each gets about
+// GIMS_GEMM_TPC (default 2) tiles — what matters when several streams keep the GPU full is SM-time per tile, and a CTA's
+// fixed cost (prologue, first TMA round trip, last epilogue) is then paid once per two tiles; small problems (fewer
+// work items than half the SMs) keep one tile per CTA for latency.
+bool persist_enabled() {
+  static const bool on = [] { const char* e = getenv("GIMS_GEMM_PERSIST"); return !(e && e[0] == '0'); }();
+  return on;
+}
+template <int MODE>
+int launch_tcp(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& whi, const CUtensorMap& wlo,
+               const TcArgs& g, int col_tiles, int row_tiles, int prof_class, cudaStream_t st) {
+  static const int tpc_env = [] { const char* e = getenv("GIMS_GEMM_TPC"); int v = e ? atoi(e) : 2; return v < 1 ? 1 : v; }();
+  int dev = 0, sms = 0;
+  GIMS_CUDA_OK(cudaGetDevice(&dev));
+  GIMS_CUDA_OK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+  const int total = col_tiles * row_tiles;
+  const int tpc = (2 * total <= sms) ? 1 : tpc_env;
+  int grid = (total + tpc - 1) / tpc;
+  if (grid > sms) grid = sms;
+  GIMS_CUDA_OK(cudaFuncSetAttribute(k_gemm_tcp<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcpCfg::kSmemBytes));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid);
+  cfg.blockDim = dim3(kThreadsP);
+  cfg.dynamicSmemBytes = TcpCfg::kSmemBytes;
+  cfg.stream = st;
+  cfg.attrs = nullptr;
+  cfg.numAttrs = 0;
+  ProfScope prof(prof_class, st);
+  GIMS_CUDA_OK(cudaLaunchKernelEx(&cfg, k_gemm_tcp<MODE>, a0, a1, whi, wlo, g, col_tiles, total));
   count_launch();
   return GIMS_OK;
 }
@@ -650,6 +979,11 @@ int launch_gemm_tc(const GemmArgs& a, const WPlanes& w, int prec, cudaStream_t s
       set_error("launch_gemm_tc: unsupported 16-bit plane format");
       return GIMS_ERR_ARG;
     }
+    if (prec && persist_enabled()) {
+      if (qkv->fmt == 0) return launch_tcp<3>(mA0, mA1, mWh, mWl, g, ct, tiles, GIMS_PROF_GEMM, st);
+      if (qkv->fmt == 1) return launch_tcp<4>(mA0, mA1, mWh, mWl, g, ct, tiles, GIMS_PROF_GEMM, st);
+      return launch_tcp<2>(mA0, mA1, mWh, mWl, g, ct, tiles, GIMS_PROF_GEMM, st);
+    }
     if (prec) {
       if (qkv->fmt == 0) return launch_tc<128, 3, 1>(mA0, mA1, mWh, mWl, g, ct, tiles, GIMS_PROF_GEMM, st);
       if (qkv->fmt == 1) return launch_tc<128, 4, 1>(mA0, mA1, mWh, mWl, g, ct, tiles, GIMS_PROF_GEMM, st);
@@ -661,6 +995,7 @@ int launch_gemm_tc(const GemmArgs& a, const WPlanes& w, int prec, cudaStream_t s
     return launch_tc<192, 2>(mA0, mA1, mWh, mWl, g, ct, tiles, GIMS_PROF_GEMM, st);
   }
   if (prec) {
+    if (bn == 128 && persist_enabled()) return launch_tcp<0>(mA0, mA1, mWh, mWl, g, ct, tiles, GIMS_PROF_GEMM, st);
     if (bn == 128) return launch_tc<128, 0, 1>(mA0, mA1, mWh, mWl, g, ct, tiles, GIMS_PROF_GEMM, st);
     return launch_tc<64, 0, 1>(mA0, mA1, mWh, mWl, g, ct, tiles, GIMS_PROF_GEMM, st);
   }
@@ -713,6 +1048,7 @@ int launch_score_gemm_tc(const float* mdesc, int n0_max, int n1_max, const int* 
   for (int i = 0; i < kMaxSegs; ++i) { g.vbase[i] = 0; g.tile_end[i] = 0; }
   g.segs = two_segs(n0_max, n1_max, n_dev);
   g.tile_end[0] = cdiv(n0_max, BM);
+  if (prec && persist_enabled()) return launch_tcp<1>(mA, mA, mWh, mWl, g, cdiv(n1_max, bn), g.tile_end[0], GIMS_PROF_SCORE, st);
   if (prec) return launch_tc<bn, 1, 1>(mA, mA, mWh, mWl, g, cdiv(n1_max, bn), g.tile_end[0], GIMS_PROF_SCORE, st);
   return launch_tc<bn, 1>(mA, mA, mWh, mWl, g, cdiv(n1_max, bn), g.tile_end[0], GIMS_PROF_SCORE, st);
 }

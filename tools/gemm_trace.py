@@ -49,6 +49,15 @@ def run(K0, K1, N, reps=50, dump=True):
     if not dump:
         return
     z = t[0]
+    if os.environ.get('GIMS_GEMM_PERSIST', '1') != '0' and MODE == _lib.GEMM_TC_F16 and N >= 256:
+        # persistent kernel: 8 stamps per tile of CTA 0
+        print('  CTA 0 exit %d clk.  tile: first operands | last A block split | MMAs retired | PARK free | fold done | first MMA || epilogue: PARK full  done' % (t[1] - z))
+        for lt in range(4):
+            r = t[8 + 8 * lt: 16 + 8 * lt]
+            if r[0] == 0:
+                break
+            print('  %d %14d %14d %14d %10d %10d %10d || %10d %10d' % (lt, r[0] - z, r[1] - z, r[2] - z, r[3] - z, r[4] - z, r[7] - z, r[5] - z, r[6] - z))
+        return
     nkb = (K0 + K1) // 32
     print('  entry 0 | prologue done %d | accum_full seen %d | epilogue done %d | exit %d | globaltimer span %d ns' %
           (t[1] - z, t[3] - z, t[4] - z, t[5] - z, t[7] - t[6]))
