@@ -324,7 +324,9 @@ static int final_proj(const gims_model* m, const float* desc, const Segs& s, flo
 static int score_matrix(const gims_model* m, const float* mdesc, int n0_max, int n1_max, const int* n_dev, float* couplings,
                         float* scratch, int mode, cudaStream_t st, unsigned* status = nullptr) {
   if (mode != GIMS_GEMM_SIMT && scratch) {
-    GIMS_TRY(launch_score_gemm_tc(mdesc, n0_max, n1_max, n_dev, scratch, couplings, gemm_prec(mode), status, st));
+    // the bf16 variant (BASELINE configs[4]: "bf16 score GEMM") runs the score matrix on ONE bf16 plane per operand
+    const int prec = mode == GIMS_GEMM_BF16 ? 2 : gemm_prec(mode);
+    GIMS_TRY(launch_score_gemm_tc(mdesc, n0_max, n1_max, n_dev, scratch, couplings, prec, status, st));
     GIMS_TRY(launch_score_border(n0_max, n1_max, n_dev, m->bin_score, couplings, st));
   } else {
     GIMS_TRY(launch_score_gemm(mdesc, n0_max, n1_max, n_dev, m->bin_score, couplings, st));

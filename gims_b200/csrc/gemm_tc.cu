@@ -601,7 +601,9 @@ struct TcpCfg {
   static constexpr int kSmemBytes = kStages * kStageBytes + kStgBytes + 1024 /*align*/ + kBiasOff + 2 * BN * 4;
 };
 
-template <int MODE>
+// PLANES 2: fp16 hi + lo operands, three MMAs per k-step (fp32 parity).  PLANES 1: ONE bf16 plane per operand, one MMA per
+// k-step — the bf16 variant of the score GEMM (BASELINE configs[4]), reported separately, never the fp32 line.
+template <int MODE, int PLANES>
 __global__ void __launch_bounds__(kThreadsP, 1)
 k_gemm_tcp(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CUtensorMap mapA1,
            const __grid_constant__ CUtensorMap mapWhi, const __grid_constant__ CUtensorMap mapWlo, TcArgs g, int col_tiles,
@@ -685,7 +687,7 @@ k_gemm_tcp(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
         for (int kb = 0; kb < nkb; ++kb) {
           mbar_wait(&empty[s], ph ^ 1);
           uint8_t* st = stage_ptr(s);
-          mbar_arrive_expect_tx(&full[s], Cfg::kABytes + 2 * Cfg::kWBytes);
+          mbar_arrive_expect_tx(&full[s], Cfg::kABytes + PLANES * Cfg::kWBytes);
           const int k = kb * Cfg::kBlockK;
 #pragma unroll
           for (int h = 0; h < 2; ++h) {
@@ -694,7 +696,7 @@ k_gemm_tcp(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
             else           tma_load_2d(st + h * 16384, &mapA1, &full[s], ka - g.K0, t.rbase + t.r0);
           }
           tma_load_2d(st + Cfg::kABytes, &mapWhi, &full[s], k, wbase + t.c0);
-          tma_load_2d(st + Cfg::kABytes + Cfg::kWBytes, &mapWlo, &full[s], k, wbase + t.c0);
+          if (PLANES == 2) tma_load_2d(st + Cfg::kABytes + Cfg::kWBytes, &mapWlo, &full[s], k, wbase + t.c0);
           if (++s == Cfg::kStages) { s = 0; ph ^= 1; }
         }
       }
@@ -703,7 +705,7 @@ k_gemm_tcp(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
     // ===== MMA issuers: lane 0 of warp kWarpMma + t handles the k-blocks kb = t, t + 2, ... of every tile =====
     const int t = __shfl_sync(0xffffffffu, warp - kWarpMma, 0);
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_f16(BM, BN, 0);
+      constexpr uint32_t idesc = umma_idesc_f16(BM, BN, PLANES == 2 ? 0 : 1);
       const uint64_t d_stage0 = umma_desc_sw128(smem_u32(stage_ptr(0) + Cfg::kABytes));
       const uint32_t acc = tmem_base + t * BN;
       int last = -1;
@@ -727,9 +729,13 @@ k_gemm_tcp(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
             const uint64_t koff = (ks * 32) >> 4;
-            umma_f16_ts(acc, a_lo + ks * 8, w_hi + koff, idesc, ks ? 1u : fresh);
-            umma_f16_ts(acc, a_hi + ks * 8, w_lo + koff, idesc, 1u);
-            umma_f16_ts(acc, a_hi + ks * 8, w_hi + koff, idesc, 1u);
+            if (PLANES == 2) {
+              umma_f16_ts(acc, a_lo + ks * 8, w_hi + koff, idesc, ks ? 1u : fresh);
+              umma_f16_ts(acc, a_hi + ks * 8, w_lo + koff, idesc, 1u);
+              umma_f16_ts(acc, a_hi + ks * 8, w_hi + koff, idesc, 1u);
+            } else {
+              umma_f16_ts(acc, a_hi + ks * 8, w_hi + koff, idesc, ks ? 1u : fresh);
+            }
           }
           umma_commit(&empty[s]);
           umma_commit(&tfree[slot]);
@@ -793,14 +799,19 @@ k_gemm_tcp(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
         for (int j = 0; j < 8; ++j) {
           const uint4 v = rowp[j ^ (t & 7)];
           const float f0 = __uint_as_float(v.x), f1 = __uint_as_float(v.y), f2 = __uint_as_float(v.z), f3 = __uint_as_float(v.w);
-          amax = fmaxf(amax, fmaxf(fmaxf(fabsf(f0), fabsf(f1)), fmaxf(fabsf(f2), fabsf(f3))));
-          split16x2<0>(f0, f1, hi[2 * j], lo[2 * j]);
-          split16x2<0>(f2, f3, hi[2 * j + 1], lo[2 * j + 1]);
+          if (PLANES == 2) {
+            amax = fmaxf(amax, fmaxf(fmaxf(fabsf(f0), fabsf(f1)), fmaxf(fabsf(f2), fabsf(f3))));
+            split16x2<0>(f0, f1, hi[2 * j], lo[2 * j]);
+            split16x2<0>(f2, f3, hi[2 * j + 1], lo[2 * j + 1]);
+          } else {
+            hi[2 * j] = pack16<1>(f0, f1);
+            hi[2 * j + 1] = pack16<1>(f2, f3);
+          }
         }
         mbar_wait(&tfree[slot], ((uint32_t)(gk / Cfg::kRing) & 1u) ^ 1u);   // MMAs of k-block gk - kRing are done
         tcgen05_fence_after();
         tmem_st_32x16(lane_base + Cfg::kRingCol + slot * 64 + 16 * grp, hi);
-        tmem_st_32x16(lane_base + Cfg::kRingCol + slot * 64 + 32 + 16 * grp, lo);
+        if (PLANES == 2) tmem_st_32x16(lane_base + Cfg::kRingCol + slot * 64 + 32 + 16 * grp, lo);
         tmem_st_wait();
         tcgen05_fence_before();
         __syncwarp();
@@ -808,7 +819,7 @@ k_gemm_tcp(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
       }
       if (warp == 0) TCP_TRACE(1);
       // rows past the live count may hold anything (other segments, stale scratch): only live rows raise the range flag
-      if (g.status && amax >= 32768.f && tcd.r0 + t < tcd.rows) atomicOr(g.status, GIMS_STATUS_FP16_RANGE);
+      if (PLANES == 2 && g.status && amax >= 32768.f && tcd.r0 + t < tcd.rows) atomicOr(g.status, GIMS_STATUS_FP16_RANGE);
       fold(lt);
       ++lt;
     }
@@ -870,6 +881,17 @@ __global__ void k_split_planes16(const float* __restrict__ x, uint16_t* __restri
   if (status && m >= 32768.f && m < 3e38f) atomicOr(status, GIMS_STATUS_FP16_RANGE);
 }
 
+// x -> one bf16 plane (the bf16 variant of the score GEMM)
+__global__ void k_plane_bf16(const float* __restrict__ x, uint16_t* __restrict__ hi, size_t n4) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const float4 v = reinterpret_cast<const float4*>(x)[i];
+  uint2 h;
+  h.x = tc::pack16<1>(v.x, v.y);
+  h.y = tc::pack16<1>(v.z, v.w);
+  reinterpret_cast<uint2*>(hi)[i] = h;
+}
+
 template <int BN, int MODE, int PREC = 0>
 int launch_tc(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& whi, const CUtensorMap& wlo,
               const TcArgs& g, int col_tiles, int row_tiles, int prof_class, cudaStream_t st) {
@@ -897,7 +919,7 @@ bool persist_enabled() {
   static const bool on = [] { const char* e = getenv("GIMS_GEMM_PERSIST"); return !(e && e[0] == '0'); }();
   return on;
 }
-template <int MODE>
+template <int MODE, int PLANES = 2>
 int launch_tcp(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& whi, const CUtensorMap& wlo,
                const TcArgs& g, int col_tiles, int row_tiles, int prof_class, cudaStream_t st) {
   static const int tpc_env = [] { const char* e = getenv("GIMS_GEMM_TPC"); int v = e ? atoi(e) : 2; return v < 1 ? 1 : v; }();
@@ -908,7 +930,7 @@ int launch_tcp(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& 
   const int tpc = (2 * total <= sms) ? 1 : tpc_env;
   int grid = (total + tpc - 1) / tpc;
   if (grid > sms) grid = sms;
-  GIMS_CUDA_OK(cudaFuncSetAttribute(k_gemm_tcp<MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcpCfg::kSmemBytes));
+  GIMS_CUDA_OK(cudaFuncSetAttribute(k_gemm_tcp<MODE, PLANES>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcpCfg::kSmemBytes));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3(grid);
   cfg.blockDim = dim3(kThreadsP);
@@ -917,7 +939,7 @@ int launch_tcp(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& 
   cfg.attrs = nullptr;
   cfg.numAttrs = 0;
   ProfScope prof(prof_class, st);
-  GIMS_CUDA_OK(cudaLaunchKernelEx(&cfg, k_gemm_tcp<MODE>, a0, a1, whi, wlo, g, col_tiles, total));
+  GIMS_CUDA_OK(cudaLaunchKernelEx(&cfg, k_gemm_tcp<MODE, PLANES>, a0, a1, whi, wlo, g, col_tiles, total));
   count_launch();
   return GIMS_OK;
 }
@@ -1026,7 +1048,14 @@ int launch_score_gemm_tc(const float* mdesc, int n0_max, int n1_max, const int* 
   constexpr int bn = 128;
   CUtensorMap mA, mWh, mWl;
   GIMS_TRY(tc::make_tmap_f32_k32(&mA, mdesc, rows, kD, kD, BM));
-  if (prec) {
+  if (prec == 2) {
+    // bf16 variant: one plane per operand, one MMA per k-step (no range concern: bf16 has the fp32 exponent)
+    uint16_t* hi = reinterpret_cast<uint16_t*>(planes);
+    k_plane_bf16<<<(unsigned)((rows * kD / 4 + 255) / 256), 256, 0, st>>>(mdesc, hi, rows * kD / 4);
+    GIMS_LAUNCH_OK();
+    GIMS_TRY(tc::make_tmap_16_k64(&mWh, hi, 1, rows, kD, kD, bn));
+    mWl = mWh;
+  } else if (prec) {
     uint16_t* hi = reinterpret_cast<uint16_t*>(planes);
     uint16_t* lo = hi + rows * kD;
     k_split_planes16<<<(unsigned)((rows * kD / 4 + 255) / 256), 256, 0, st>>>(mdesc, hi, lo, rows * kD / 4, status);
@@ -1048,6 +1077,7 @@ int launch_score_gemm_tc(const float* mdesc, int n0_max, int n1_max, const int* 
   for (int i = 0; i < kMaxSegs; ++i) { g.vbase[i] = 0; g.tile_end[i] = 0; }
   g.segs = two_segs(n0_max, n1_max, n_dev);
   g.tile_end[0] = cdiv(n0_max, BM);
+  if (prec == 2) return launch_tcp<1, 1>(mA, mA, mWh, mWl, g, cdiv(n1_max, bn), g.tile_end[0], GIMS_PROF_SCORE, st);
   if (prec && persist_enabled()) return launch_tcp<1>(mA, mA, mWh, mWl, g, cdiv(n1_max, bn), g.tile_end[0], GIMS_PROF_SCORE, st);
   if (prec) return launch_tc<bn, 1, 1>(mA, mA, mWh, mWl, g, cdiv(n1_max, bn), g.tile_end[0], GIMS_PROF_SCORE, st);
   return launch_tc<bn, 1>(mA, mA, mWh, mWl, g, cdiv(n1_max, bn), g.tile_end[0], GIMS_PROF_SCORE, st);

