@@ -80,6 +80,11 @@ class PairOutputs(C.Structure):
     ]
 
 
+class NamedTensor(C.Structure):
+    """gims_named_tensor (include/gims_b200.h)."""
+    _fields_ = [('name', C.c_char_p), ('data', C.c_void_p), ('numel', C.c_int64)]
+
+
 # name -> (restype, argtypes); every symbol include/gims_b200.h declares
 SIGNATURES = {
     'gims_version': (C.c_int, []),
@@ -91,6 +96,9 @@ SIGNATURES = {
                                     C.POINTER(C.c_void_p)]),
     'gims_model_destroy': (None, [C.c_void_p]),
     'gims_packed_blob_count': (C.c_int, [C.POINTER(Config)]),
+    'gims_pack_weights_floats': (C.c_size_t, [C.POINTER(Config)]),
+    'gims_pack_weights': (C.c_int, [C.POINTER(Config), C.POINTER(NamedTensor), C.c_int, C.c_void_p, C.c_size_t,
+                                    C.POINTER(C.c_int64), C.c_int]),
     'gims_agc_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int]),
     'gims_agc_build': (C.c_int, [C.c_void_p, C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_double, C.c_longlong,
                                  C.c_int, C.c_void_p, C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,

@@ -134,6 +134,22 @@ GIMS_API int  gims_model_create(const gims_config* cfg_host, const float* packed
 GIMS_API void gims_model_destroy(gims_model* m);
 GIMS_API int  gims_packed_blob_count(const gims_config* cfg_host);
 
+/* Weight packing for integrators that do not run Python (the Python host uses gims_b200/packing.py, the specification of
+ * the layout; both produce the same buffer).  HOST function, no GPU involved: `tensors` is the reference
+ * GMatcher.state_dict() (models/gmatcher.py:177-217) as fp32 host arrays under the reference's own key names
+ * ("kenc.encoder.0.weight", "gnn.layers.3.attn.proj.1.bias", "gnn_encoder.layers.0.fc_neigh.weight", "bin_score", ...;
+ * Conv1d weights as (out, in[, 1]) row-major; num_batches_tracked and input_proj.* are ignored).  Writes the packed
+ * buffer (gims_pack_weights_floats(cfg) floats) and the blob offsets (gims_packed_blob_count(cfg) entries); copy the
+ * buffer to the device and hand both to gims_model_create. */
+typedef struct gims_named_tensor {
+  const char*  name;
+  const float* data;
+  int64_t      numel;
+} gims_named_tensor;
+GIMS_API size_t gims_pack_weights_floats(const gims_config* cfg_host);
+GIMS_API int    gims_pack_weights(const gims_config* cfg_host, const gims_named_tensor* tensors, int n_tensors,
+                         float* packed_host, size_t capacity_floats, int64_t* offsets_host, int n_offsets);
+
 /* ---- a-1..a-7: adaptive graph construction for ONE image ----------------------------------
  * replaces models/agc.py:682-709 build_optimize_graph_with_cosine_similarity (+ 367-391, 413-449,
  * 476-565, 660-678) and the repack of gmatcher.py:244-252.

@@ -130,6 +130,49 @@ def test_fp16_weight_planes():
     assert torch.equal(flat[off[i]:off[i] + want.numel()].view(torch.int32), want.view(torch.int32))
 
 
+def test_c_packer_equals_python_packer(lib):
+    """gims_pack_weights (csrc/pack.cu, for integrators without Python) against gims_b200/packing.py on a random state_dict
+    with non-trivial BatchNorm statistics: same blob offsets; every blob bit-identical except W1 / b1, whose merge composition
+    is a 256-term fp64 product summed in a different order (<= 1 fp32 ulp), and the planes derived from W1."""
+    from gims_b200 import GMatcher, _lib
+    from gims_b200.packing import pack_state_dict
+    from gims_b200.synth import make_state_dict
+    sd = make_state_dict(3)
+    flat, offsets, names = pack_state_dict(sd)
+    gm = GMatcher({})
+    cfg = gm.c_config()
+    items = [(k, v.detach().float().contiguous()) for k, v in sd.items() if v.dtype.is_floating_point]
+    arr = (_lib.NamedTensor * len(items))()
+    for a, (k, v) in zip(arr, items):
+        a.name, a.data, a.numel = k.encode(), v.data_ptr(), v.numel()
+    n_floats = lib.gims_pack_weights_floats(C.byref(cfg))
+    assert n_floats == flat.numel()
+    out = torch.full((n_floats,), float('nan'))
+    offs = (C.c_int64 * len(offsets))()
+    rc = lib.gims_pack_weights(C.byref(cfg), arr, len(items), C.c_void_p(out.data_ptr()), n_floats, offs, len(offsets))
+    assert rc == 0, lib.gims_last_error()
+    assert list(offs) == offsets
+    bounds = offsets + [flat.numel()]
+    for i, name in enumerate(names):
+        a, b = flat[bounds[i]:bounds[i + 1]], out[bounds[i]:bounds[i + 1]]
+        if '.w1' in name or '.b1' in name:
+            if name.endswith('.w1') or name.endswith('.b1') or name.endswith('.hi'):
+                assert torch.allclose(a, b, rtol=3e-7, atol=1e-9), name
+            elif name.endswith('.lo'):
+                assert (a - b).abs().max() <= 1e-6 * flat[bounds[i - 2]:bounds[i - 1]].abs().max(), name
+            elif name.endswith('.sinv'):
+                assert torch.equal(a, b), name
+            else:                                   # fp16 planes: raw bit patterns, compare the values they encode
+                ha, hb = a.view(torch.float16).float(), b.view(torch.float16).float()
+                if name.endswith('.h16'):
+                    assert (ha - hb).abs().max() <= 2.0 ** -10 * ha.abs().max(), name
+        else:
+            assert torch.equal(a.view(torch.int32), b.view(torch.int32)), name
+    # a missing entry is an error that names the key
+    rc = lib.gims_pack_weights(C.byref(cfg), arr, len(items) - 1, C.c_void_p(out.data_ptr()), n_floats, offs, len(offsets))
+    assert rc != 0 and items[-1][0].encode() in lib.gims_last_error()
+
+
 def test_packing_equals_oracle_sage_kenc():
     from gims_b200.packing import pack_state_dict
     from gims_b200.synth import make_state_dict
