@@ -224,6 +224,21 @@ GIMS_API int gims_sinkhorn_match(const float* couplings, int ld, int n0_max, int
                         int64_t* matches0, int64_t* matches1, float* mscores0, float* mscores1,
                         unsigned* status_dev, void* stream);
 
+/* ---- caller-side result consumption on the device --------------------
+ * gims_gt_matches replaces utils/preprocess_utils.py:98-132 torch_find_matches (called at eval_homography.py:205):
+ *   kpts0 [n0][2], kpts1 [n1][2] pixel xy (fp32, device); homography_dev: 9 fp32, row-major, maps image 0 -> image 1.
+ *   n_iters rounds of mutual nearest neighbours among the still unmatched points, accepted below dist_thresh pixels.
+ *   gt0 [n0] = index in image 1 of the ground-truth partner or -1; gt1 [n1] likewise; round0 [n0] = the round (0-based) in
+ *   which point i was matched, -1 if never (the reference returns the pairs ordered by round, then by image-1 index).
+ * gims_match_counts replaces eval_homography.py:224-228: counts_dev[3] = { true positives, predicted matches, missed
+ *   ground-truth matches } over the first *n_dev (or n0_max) rows; precision = c0 / c1, recall = c0 / (c0 + c2). */
+GIMS_API size_t gims_gt_workspace_bytes(int n0, int n1);
+GIMS_API int gims_gt_matches(const float* kpts0, int n0, const float* kpts1, int n1, const float* homography_dev,
+                    float dist_thresh, int n_iters, void* workspace, size_t workspace_bytes, int* gt0, int* gt1,
+                    int* round0, void* stream);
+GIMS_API int gims_match_counts(const int64_t* matches0, const int* gt0, int n0_max, const int* n_dev /* may be NULL */,
+                      int* counts_dev, void* stream);
+
 /* ---- whole pair: replaces GMatcher.forward (gmatcher.py:219-307), test mode ----------------- */
 typedef struct {
   const float* kpts[2];          /* [n][2] */

@@ -390,3 +390,53 @@ def gmatcher_forward(sd, data, config=None, stages=False, timings=None):
             'mutual0': m['mutual0'], 'mutual1': m['mutual1'],
         }
     return out
+
+
+# --------------------------------------------------------------------------------------------
+# f-3  caller-side result consumption (test infrastructure like everything in this file)
+# --------------------------------------------------------------------------------------------
+def warp_keypoints(keypoints, homography_mat):
+    """utils/preprocess_utils.py:82-96."""
+    source = torch.cat([keypoints, torch.ones(len(keypoints), 1)], dim=-1)
+    dest = (homography_mat @ source.T).T
+    dest = dest / dest[:, 2:3]
+    return dest[:, :2]
+
+
+def find_gt_matches(kpts0, kpts1, homography, dist_thresh=3, n_iters=1):
+    """utils/preprocess_utils.py:98-132 `torch_find_matches` (with torch_cdist :74-78 and torch_setdiff1d :80-84)."""
+    match1 = torch.empty(0, dtype=torch.int64)
+    match2 = torch.empty(0, dtype=torch.int64)
+    miss1 = torch.arange(len(kpts0), dtype=torch.long)
+    miss2 = torch.arange(len(kpts1), dtype=torch.long)
+    proj = warp_keypoints(kpts0, homography)
+    for _ in range(n_iters):
+        a, b = proj[miss1, :], kpts1[miss2, :]
+        distance = torch.sqrt(((a[:, None, :] - b[None, :, :]) ** 2).sum(-1))
+        min1 = torch.argmin(distance, 1)
+        min2 = torch.argmin(distance, 0)
+        inter2 = torch.where(min1[min2] == torch.arange(len(min2)))[0]
+        inter1 = min2[inter2]
+        ok = distance[inter1, inter2] < dist_thresh
+        inter1, inter2 = inter1[ok], inter2[ok]
+        m1, m2 = miss1[inter1], miss2[inter2]
+
+        def setdiff(x, y):
+            unq, count = torch.cat((x, y)).unique(return_counts=True)
+            return unq[count == 1]
+        miss1, miss2 = setdiff(miss1, m1), setdiff(miss2, m2)
+        match1, match2 = torch.cat((match1, m1)), torch.cat((match2, m2))
+    return match1, match2, miss1, miss2
+
+
+def precision_recall(matches, ma_0, ma_1):
+    """eval_homography.py:209-211, 224-228 (numpy): matches = matches0 of the pair."""
+    matches = np.asarray(matches)
+    gt = np.ones((len(matches),), dtype=np.int64) * -1
+    gt[np.asarray(ma_0)] = np.asarray(ma_1)
+    valid = matches > -1
+    match_flag = (matches[np.asarray(ma_0)] == np.asarray(ma_1))
+    precision = match_flag.sum() / valid.sum()
+    fn_flag = np.logical_and((matches != gt), (matches == -1))
+    recall = match_flag.sum() / (match_flag.sum() + fn_flag.sum())
+    return precision, recall

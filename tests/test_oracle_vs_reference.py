@@ -51,3 +51,25 @@ def test_forward_equals_live_reference():
     assert torch.allclose(ref['matching_scores0'], got['matching_scores0'], atol=1e-5)
     assert torch.allclose(ref['mdesc0'], got['mdesc0'], rtol=1e-4, atol=1e-4 * float(ref['mdesc0'].abs().max()))
     assert int((ref['matches0'] >= 0).sum()) > 10          # the case is not degenerate
+
+
+def test_gt_matches_equal_live_reference():
+    """utils/preprocess_utils.py:98-132 run unchanged vs oracle.find_gt_matches (row f-3)."""
+    import importlib
+    import sys
+    load_reference()
+    sys.path.insert(0, '/root/reference')
+    try:
+        with contextlib.redirect_stdout(io.StringIO()):
+            pu = importlib.import_module('utils.preprocess_utils')
+    except Exception as e:                         # albumentations / pycocotools are not in this image
+        pytest.skip('utils.preprocess_utils cannot be imported here: %s' % e)
+    g = torch.Generator().manual_seed(77)
+    k0 = torch.rand(300, 2, generator=g) * 400
+    H = torch.tensor([[1.02, 0.03, 5.0], [-0.02, 0.98, -3.0], [1e-5, -2e-5, 1.0]])
+    k1 = orc.warp_keypoints(k0, H)[torch.randperm(300, generator=g)[:260]] + torch.randn(260, 2, generator=g) * 1.5
+    ref = pu.torch_find_matches(k0, k1, H, dist_thresh=3, n_iters=3)
+    got = orc.find_gt_matches(k0, k1, H, dist_thresh=3, n_iters=3)
+    for a, b in zip(ref, got):
+        assert torch.equal(a, b)
+    assert len(got[0]) > 100
