@@ -391,7 +391,7 @@ int launch_or_status(const unsigned* src, unsigned* dst, unsigned mask, cudaStre
 // kernel run per pair on the same stream and share one scratch area each.
 namespace {
 struct BatchWs {
-  void* agc;        size_t agc_bytes;
+  void* agc[2];     size_t agc_bytes;          // one per image: the two graph chains of a pair run on two streams
   float* sage_out;  // [rows][256]
   float* desc;      // [rows][256]
   float* mdesc;     // [rows][256]
@@ -412,7 +412,8 @@ size_t carve_batch(BatchWs& w, void* base, size_t cap, int n_pairs, const int* n
     sink = sb > sink ? sb : sink;
   }
   w.agc_bytes = gims_agc_workspace_bytes(nmax, edge_cap);
-  w.agc = a.take<char>(w.agc_bytes);
+  w.agc[0] = a.take<char>(w.agc_bytes);
+  w.agc[1] = a.take<char>(w.agc_bytes);
   w.sage_out = a.take<float>(rows * kD);
   w.desc = a.take<float>(rows * kD);
   w.mdesc = a.take<float>(rows * kD);
@@ -422,6 +423,32 @@ size_t carve_batch(BatchWs& w, void* base, size_t cap, int n_pairs, const int* n
   w.sink = a.take<char>(sink);
   return align_up(a.off, 256);
 }
+// Image 0 and image 1 of a pair are independent until the first attention layer: graph construction, GraphSAGE and the
+// keypoint encoder of image 1 run on a side stream forked from the caller's stream and joined before the layers (about
+// 60 small, strictly serial launches per image — alone on one stream they are a third of a single caller's latency).
+// One side stream + two events per caller stream, created on first use (GIMS_FORK_IMAGES=0: everything on one stream).
+struct SideStream { cudaStream_t s; cudaEvent_t fork, join; };
+static std::mutex g_side_mu;
+static std::vector<std::pair<std::pair<int, cudaStream_t>, SideStream>> g_side;
+bool fork_images() {
+  static const bool on = [] { const char* e = getenv("GIMS_FORK_IMAGES"); return !(e && e[0] == '0'); }();
+  return on;
+}
+int side_stream_for(cudaStream_t main, SideStream& out) {
+  int dev = 0;
+  GIMS_CUDA_OK(cudaGetDevice(&dev));
+  std::lock_guard<std::mutex> lk(g_side_mu);
+  for (auto& e : g_side)
+    if (e.first.first == dev && e.first.second == main) { out = e.second; return GIMS_OK; }
+  SideStream n;
+  GIMS_CUDA_OK(cudaStreamCreateWithFlags(&n.s, cudaStreamNonBlocking));
+  GIMS_CUDA_OK(cudaEventCreateWithFlags(&n.fork, cudaEventDisableTiming));
+  GIMS_CUDA_OK(cudaEventCreateWithFlags(&n.join, cudaEventDisableTiming));
+  g_side.push_back({{dev, main}, n});
+  out = n;
+  return GIMS_OK;
+}
+
 __global__ void k_copy_rows(const float* __restrict__ src, float* __restrict__ dst, size_t n4) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n4) reinterpret_cast<float4*>(dst)[i] = reinterpret_cast<const float4*>(src)[i];
@@ -506,25 +533,41 @@ extern "C" int gims_forward_pairs(const gims_model* m, int n_pairs, const gims_p
   const size_t rows = (size_t)row;
   // a-1 .. a-7: graphs + pruning (gmatcher.py:233-252), then a-9, a-8, a-10: desc = SAGE(feat) + kenc(normalize(kpts))
   // (gmatcher.py:265-271), image by image into the stacked buffer
+  for (int p = 0; p < n_pairs; ++p) GIMS_CUDA_OK(cudaMemsetAsync(out[p].status_dev, 0, sizeof(unsigned), st));
+  SideStream side = {st, nullptr, nullptr};
+  const bool forked = fork_images();
+  if (forked) {
+    GIMS_TRY(side_stream_for(st, side));
+    GIMS_CUDA_OK(cudaEventRecord(side.fork, st));
+    GIMS_CUDA_OK(cudaStreamWaitEvent(side.s, side.fork, 0));
+  }
+  // each image's chain has its own graph workspace and its own half of the scratch area (2.5 n x 256 floats are needed,
+  // half the attention scratch is 5 (n0 + n1) x 256)
+  float* scratch_img[2] = {w.scratch, w.scratch + (attn_scratch_floats(rows, 2 * n_pairs) / 2 / 64) * 64};
   for (int p = 0; p < n_pairs; ++p) {
     const gims_pair_inputs* ip = in + p;
     const gims_pair_outputs* o = out + p;
-    GIMS_CUDA_OK(cudaMemsetAsync(o->status_dev, 0, sizeof(unsigned), st));
     for (int s = 0; s < 2; ++s) {
+      cudaStream_t ss = s ? side.s : st;
       GIMS_TRY(gims_agc_build(ip->kpts[s], ip->desc[s], ip->desc_channel_major, ip->scores[s], ip->n[s], ip->radius,
-                              ip->k_rank[s], ip->min_size, w.agc, w.agc_bytes, o->kept_idx[s], o->n_kept_dev + s,
+                              ip->k_rank[s], ip->min_size, w.agc[s], w.agc_bytes, o->kept_idx[s], o->n_kept_dev + s,
                               o->csr_indptr[s], o->csr_indices[s], ip->edge_cap, o->n_edges_dev + s, o->kpts[s], o->feat[s],
-                              o->scores[s], o->thr_dev + s, o->n_comp_dev + s, o->status_dev, stream));
+                              o->scores[s], o->thr_dev + s, o->n_comp_dev + s, o->status_dev, ss));
       const size_t base = (size_t)segs.base[2 * p + s];
       GIMS_TRY(sage_fwd(m, o->feat[s], o->csr_indptr[s], o->csr_indices[s], ip->n[s], o->n_kept_dev + s,
-                        w.sage_out + base * kD, w.scratch, mode, st));
+                        w.sage_out + base * kD, scratch_img[s], mode, ss));
       GIMS_TRY(kenc_fwd(m, o->kpts[s], ip->n[s], o->n_kept_dev + s, ip->img_w[s], ip->img_h[s],
-                        w.sage_out + base * kD, w.desc + base * kD, w.scratch, mode, st));
+                        w.sage_out + base * kD, w.desc + base * kD, scratch_img[s], mode, ss));
     }
-    if (o->desc_in) {
-      const size_t base = (size_t)segs.base[2 * p], cnt = (size_t)ip->n[0] + ip->n[1];
-      GIMS_TRY(copy_rows(w.desc + base * kD, o->desc_in, cnt * kD, st));
-    }
+  }
+  if (forked) {
+    GIMS_CUDA_OK(cudaEventRecord(side.join, side.s));
+    GIMS_CUDA_OK(cudaStreamWaitEvent(st, side.join, 0));
+  }
+  for (int p = 0; p < n_pairs; ++p) {
+    if (!out[p].desc_in) continue;
+    const size_t base = (size_t)segs.base[2 * p], cnt = (size_t)in[p].n[0] + in[p].n[1];
+    GIMS_TRY(copy_rows(w.desc + base * kD, out[p].desc_in, cnt * kD, st));
   }
   // a-11, a-12: attention stack (gmatcher.py:272) — one launch per stage and layer for the whole batch.  The fp16-range
   // flag of the batch is raised in pair 0's status word and copied to the others below.
