@@ -493,12 +493,15 @@ __global__ void k_cc_init(int* parent, int n) {
   if (i < n) parent[i] = i;
 }
 
+// warp per node, lanes over its edges: a thread per node walked its edges one after the other, every find a chain of
+// dependent L2 round trips (40 .. 86 us for 15 k edges); the result does not depend on the order (smaller root wins)
 __global__ void k_cc_union_base(int* parent, int n, const int* __restrict__ indptr, const int* __restrict__ idx, int edge_cap) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
   if (i >= n) return;
-  int e0 = indptr[i], e1 = min(indptr[i + 1], edge_cap);
-  for (int e = e0; e < e1; ++e) {
-    int j = idx[e];
+  const int e0 = indptr[i], e1 = min(indptr[i + 1], edge_cap);
+  for (int e = e0 + lane; e < e1; e += 32) {
+    const int j = idx[e];
     if (j > i) uf_union(parent, i, j);
   }
 }
@@ -863,7 +866,7 @@ extern "C" int gims_agc_build(const float* kpts, const float* desc, int desc_cha
   // a-4
   k_cc_init<<<cdiv(n, 256), 256, 0, st>>>(w.parent, n);
   GIMS_LAUNCH_OK();
-  k_cc_union_base<<<cdiv(n, 256), 256, 0, st>>>(w.parent, n, w.indptr_base, w.idx_base, edge_cap);
+  k_cc_union_base<<<cdiv(n, 8), 256, 0, st>>>(w.parent, n, w.indptr_base, w.idx_base, edge_cap);
   GIMS_LAUNCH_OK();
   k_cc_union_iso<<<cdiv(n, 256), 256, 0, st>>>(w.parent, w.iso_u, w.iso_v, w.iso_count);
   GIMS_LAUNCH_OK();
