@@ -488,13 +488,20 @@ __device__ __forceinline__ void uf_union(int* parent, int a, int b) {
   }
 }
 
-__global__ void k_cc_init(int* parent, int n) {
+// Start from a forest instead of singletons: every node points at its smallest neighbour if that is smaller than itself
+// (CSR rows are ascending, so it is the first entry).  Pointers only ever go to strictly smaller ids — no cycles — and
+// only along real edges, so components are unchanged; most unions afterwards find both ends under one root already
+// and return without a CAS (with singletons, every edge of the giant component fought for the same root word).
+__global__ void k_cc_init(int* parent, int n, const int* __restrict__ indptr, const int* __restrict__ idx, int edge_cap) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) parent[i] = i;
+  if (i >= n) return;
+  int p = i;
+  const int e0 = indptr[i];
+  if (e0 < indptr[i + 1] && e0 < edge_cap) p = min(i, idx[e0]);
+  parent[i] = p;
 }
 
-// warp per node, lanes over its edges: a thread per node walked its edges one after the other, every find a chain of
-// dependent L2 round trips (40 .. 86 us for 15 k edges); the result does not depend on the order (smaller root wins)
+// warp per node, lanes over its edges; the result does not depend on the order (smaller root wins)
 __global__ void k_cc_union_base(int* parent, int n, const int* __restrict__ indptr, const int* __restrict__ idx, int edge_cap) {
   const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   const int lane = threadIdx.x & 31;
@@ -864,7 +871,7 @@ extern "C" int gims_agc_build(const float* kpts, const float* desc, int desc_cha
   k_iso_resolve<<<1, 1024, 0, st>>>(n, w.deg_base, n_base_edges, w.nn_iso, w.iso_u, w.iso_v, w.iso_count, w.extra_cnt);
   GIMS_LAUNCH_OK();
   // a-4
-  k_cc_init<<<cdiv(n, 256), 256, 0, st>>>(w.parent, n);
+  k_cc_init<<<cdiv(n, 256), 256, 0, st>>>(w.parent, n, w.indptr_base, w.idx_base, edge_cap);
   GIMS_LAUNCH_OK();
   k_cc_union_base<<<cdiv(n, 8), 256, 0, st>>>(w.parent, n, w.indptr_base, w.idx_base, edge_cap);
   GIMS_LAUNCH_OK();
