@@ -130,24 +130,39 @@ __global__ void k_normalize_rows(const float* __restrict__ feat, int n, float* _
 // ---------------------------------------------------------------------------------------------
 // a-1  C2: S = fl32(Xhat Xhat^T accumulated in fp64), upper-triangular 64x64 tiles mirrored
 // ---------------------------------------------------------------------------------------------
-constexpr int kCT = 128;  // tile edge: 8 x 8 fp64 accumulators per thread — 64 DFMA per 16 shared-memory loads, which keeps
-constexpr int kCK = 16;   // the kernel on the fp64 pipe (at 4 x 4 it was bound by shared-memory bandwidth); k-slab of 16
+constexpr int kCT = 128;  // tile edge
+constexpr int kCK = 16;   // k-slab
+constexpr int kCLd = kCT + 4;   // row pitch of the k-major slabs in doubles: 132 = 4 (mod 16) makes the fragment loads
+                                // (4 k values x 8 rows per half-warp) conflict-free
 
+// D (8x8) += A (8x4, row) * B (4x8, col) in fp64 on the tensor core (DMMA).  Lane l holds A[l>>2][l&3], B[l&3][l>>2] and
+// D[l>>2][2*(l&3) .. +1].
+__device__ __forceinline__ void dmma_8x8x4(double& d0, double& d1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(d0), "+d"(d1)
+               : "d"(a), "d"(b));
+}
+
+// One CTA = one 128 x 128 tile of the upper triangle, 8 warps, warp w owns rows 32 (w & 3) .. +32 and columns
+// 64 (w >> 2) .. +64 as 4 x 8 DMMA tiles (64 fp64 accumulators per thread).  Per k-step of 4: 12 fragment loads for 32 DMMAs
+// — the scalar version (8 x 8 DFMA per thread, 16 loads per 64 DFMA) issued 8 x as many instructions for the same FMAs and
+// ran at 47 % of the fp64 pipe with its two warps per scheduler (ncu: no eligible warp 60 % of the cycles).
 __global__ void __launch_bounds__(256) k_cosine_fp64(const float* __restrict__ xhat, int n, float* __restrict__ S) {
   int bi = blockIdx.y, bj = blockIdx.x;
   if (bj < bi) return;
-  __shared__ double As[kCK][kCT + 2];
-  __shared__ double Bs[kCK][kCT + 2];
-  int tid = threadIdx.x;
-  int tx = tid & 15, ty = tid >> 4;
-  double acc[8][8];
+  __shared__ double As[kCK][kCLd];
+  __shared__ double Bs[kCK][kCLd];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int wr = 32 * (warp & 3), wc = 64 * (warp >> 2);      // this warp's corner inside the tile
+  const int fr = lane >> 2, fk = lane & 3;                    // fragment row / column index, k index
+  double acc[4][8][2];
 #pragma unroll
-  for (int a = 0; a < 8; ++a)
+  for (int a = 0; a < 4; ++a)
 #pragma unroll
-    for (int b = 0; b < 8; ++b) acc[a][b] = 0.0;
-  int i0 = bi * kCT, j0 = bj * kCT;
+    for (int b = 0; b < 8; ++b) acc[a][b][0] = acc[a][b][1] = 0.0;
+  const int i0 = bi * kCT, j0 = bj * kCT;
   // loader mapping: 256 threads load 128 rows x 16 k per operand: two float4 each (rows tid/4 and tid/4 + 64, k4 = tid%4)
-  int lr = tid >> 2, lk = (tid & 3) * 4;
+  const int lr = tid >> 2, lk = (tid & 3) * 4;
   float4 va[2], vb[2];
   auto fetch = [&](int k0) {
 #pragma unroll
@@ -168,28 +183,30 @@ __global__ void __launch_bounds__(256) k_cosine_fp64(const float* __restrict__ x
       Bs[lk + 0][r] = vb[h].x; Bs[lk + 1][r] = vb[h].y; Bs[lk + 2][r] = vb[h].z; Bs[lk + 3][r] = vb[h].w;
     }
     __syncthreads();
-    if (k0 + kCK < kD) fetch(k0 + kCK);      // the next slab's global loads fly during this slab's FMAs
-#pragma unroll 4
-    for (int k = 0; k < kCK; ++k) {          // k ascending, one fma per k: the accumulation order of contract C2
-      double a[8], b[8];
+    if (k0 + kCK < kD) fetch(k0 + kCK);      // the next slab's global loads fly during this slab's MMAs
 #pragma unroll
-      for (int q = 0; q < 8; ++q) { a[q] = As[k][ty + 16 * q]; b[q] = Bs[k][tx + 16 * q]; }
+    for (int kk = 0; kk < kCK; kk += 4) {    // k ascending
+      double a[4], b[8];
 #pragma unroll
-      for (int q = 0; q < 8; ++q)
+      for (int q = 0; q < 4; ++q) a[q] = As[kk + fk][wr + 8 * q + fr];
 #pragma unroll
-        for (int r = 0; r < 8; ++r) acc[q][r] = fma(a[q], b[r], acc[q][r]);
+      for (int q = 0; q < 8; ++q) b[q] = Bs[kk + fk][wc + 8 * q + fr];
+#pragma unroll
+      for (int q = 0; q < 4; ++q)
+#pragma unroll
+        for (int r = 0; r < 8; ++r) dmma_8x8x4(acc[q][r][0], acc[q][r][1], a[q], b[r]);
     }
   }
+  // lane l holds rows fr, column pairs 2 fk, 2 fk + 1 of every 8 x 8 tile: 8-byte stores, the mirror image as scalars
 #pragma unroll
-  for (int q = 0; q < 8; ++q)
+  for (int q = 0; q < 4; ++q)
 #pragma unroll
     for (int r = 0; r < 8; ++r) {
-      int i = i0 + ty + 16 * q, j = j0 + tx + 16 * r;
-      if (i < n && j < n) {
-        float v = (float)acc[q][r];
-        S[(size_t)i * n + j] = v;
-        if (bi != bj) S[(size_t)j * n + i] = v;
-      }
+      const int i = i0 + wr + 8 * q + fr, j = j0 + wc + 8 * r + 2 * fk;
+      if (i >= n) continue;
+      const float v0 = (float)acc[q][r][0], v1 = (float)acc[q][r][1];
+      if (j < n) { S[(size_t)i * n + j] = v0; if (bi != bj) S[(size_t)j * n + i] = v0; }
+      if (j + 1 < n) { S[(size_t)i * n + j + 1] = v1; if (bi != bj) S[(size_t)(j + 1) * n + i] = v1; }
     }
 }
 
