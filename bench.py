@@ -617,13 +617,14 @@ def main():
     # --- e2e: the reference-facing call with pinned host tensors ------------------------------------------
     e2e = None
     if not args.no_e2e:
-        n_e2e = max(8, min(2 * P * args.steps, 128))
-        host = []
-        for i in range(n_e2e):
-            d = pool_host[i % len(pool_host)]
+        # long enough that the ramp and the tail (one pair latency under load, ~20 ms) are a few per cent of the region
+        n_e2e = max(8, min(4 * P * args.steps, 512))
+        pinned = []
+        for d in pool_host:
             h = {k: (v.pin_memory() if torch.is_tensor(v) and k != 'image0' and k != 'image1' else v) for k, v in d.items()}
             h['device'] = dev
-            host.append(h)
+            pinned.append(h)
+        host = [pinned[i % len(pinned)] for i in range(n_e2e)]     # every call copies its inputs from pinned host memory
         # T host threads (one CUDA stream each) issue sequential Matching(data) calls — the reference-facing call,
         # as a server handling concurrent requests would make it; ctypes / torch release the GIL while they wait
         T = max(1, min(args.e2e_threads, n_e2e))

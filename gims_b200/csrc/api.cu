@@ -58,6 +58,8 @@ void coop_chain_lock() { g_coop_launch_mu.lock(); }
 void coop_chain_unlock() { g_coop_launch_mu.unlock(); }
 
 int coop_chain_pick_lane() {
+  static const int lanes = [] { const char* e = getenv("GIMS_COOP_LANES"); int v = e ? atoi(e) : 2; return v == 1 ? 1 : 2; }();
+  if (lanes == 1) return 0;          // (tuning knob: at most one half-GPU cooperative kernel at a time)
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev >= 64) return 0;
   std::lock_guard<std::mutex> lk(g_coop_mu);

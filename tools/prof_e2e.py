@@ -1,0 +1,49 @@
+"""Where the end-to-end path (host threads calling Matching(data) with pinned host tensors) loses against the device-timed
+throughput: per-thread host time inside forward vs time blocked in the result read-back, for 1 .. 16 caller threads."""
+import os, sys, threading, time
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from gims_b200 import Matching
+from gims_b200.synth import make_pair, make_state_dict
+n = 2048
+dev = torch.device('cuda:0')
+m = Matching({})
+m.gmodel.load_state_dict(make_state_dict(0))
+m = m.eval().to(dev)
+pool = []
+for s in range(16):
+    d = make_pair(n, n, seed=100 + s)
+    d = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in d.items()}
+    d['device'] = dev
+    pool.append(d)
+
+def run(T, per_thread, read_back=True):
+    streams = [torch.cuda.Stream(device=dev) for _ in range(T)]
+    t_fwd = [0.0] * T
+    t_read = [0.0] * T
+    def worker(t):
+        torch.cuda.set_device(dev)
+        with torch.no_grad(), torch.cuda.stream(streams[t]):
+            for i in range(per_thread):
+                a = time.perf_counter()
+                pred = m(dict(pool[(t + i) % 16]))
+                b = time.perf_counter()
+                if read_back:
+                    pred['matches0'].cpu(); pred['matching_scores0'].cpu()
+                c = time.perf_counter()
+                t_fwd[t] += b - a; t_read[t] += c - b
+    ths = [threading.Thread(target=worker, args=(t,)) for t in range(T)]
+    t0 = time.perf_counter()
+    for th in ths: th.start()
+    for th in ths: th.join()
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    k = T * per_thread
+    print('T=%2d read_back=%d: %.1f pairs/s | per pair and thread: forward() %.2f ms, read-back %.2f ms' %
+          (T, read_back, k / dt, 1e3 * sum(t_fwd) / k, 1e3 * sum(t_read) / k))
+
+run(8, 4)
+for T in (1, 2, 4, 8, 16):
+    run(T, 256 // T if T > 1 else 64)
+run(8, 32, read_back=False)
+os.environ['X'] = '1'

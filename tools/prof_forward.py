@@ -10,7 +10,7 @@ m.gmodel.load_state_dict(make_state_dict(0))
 m = m.eval().to('cuda')
 pairs = []
 for s in range(8):
-    d = make_pair(n, n, seed=100 + s, width=1600, height=1200)
+    d = make_pair(n, n, seed=100 + s)
     d = {k: (v.pin_memory() if torch.is_tensor(v) else v) for k, v in d.items()}
     d['device'] = 'cuda'
     pairs.append(d)
