@@ -128,6 +128,9 @@ SIGNATURES = {
                                       C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     'gims_sinkhorn_max_columns': (C.c_int, []),
+    'gims_extract_patches': (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p,
+                                       C.c_void_p, C.c_int, C.c_void_p, C.c_void_p]),
+    'gims_debug_bicubic_table': (C.c_int, [C.c_void_p]),
     'gims_gt_workspace_bytes': (C.c_size_t, [C.c_int, C.c_int]),
     'gims_gt_matches': (C.c_int, [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_void_p, C.c_float, C.c_int, C.c_void_p,
                                   C.c_size_t, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),

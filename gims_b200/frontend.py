@@ -8,7 +8,9 @@ Mirrors `sift_forward` (utils/common.py:837-893): OpenCV SIFT detection, OpenCV-
 128-d descriptor duplicated to 256-d (utils/common.py:891).
 
 What is different from the reference, and why:
-  * detection and patch extraction stay on the host (OpenCV; they are the reference's own CPU stages, next row §8f-2);
+  * detection and the Gaussian pyramid stay on the host (OpenCV); the per-keypoint patch loop (§8f row 2: cv2.warpAffine
+    + resize per keypoint, 200-500 ms per image) runs as ONE kernel on the device that reproduces OpenCV's fixed-point
+    cubic warp bit for bit (`extract_patches_device`, csrc/patches.cu; GIMS_HOST_PATCHES=1 keeps the host loop);
   * the descriptor network runs on the device the matcher lives on and its output NEVER leaves it: the reference
     round-trips every batch through `.cpu().detach().numpy()` (carhynet/models.py:656-665) and uploads again at
     utils/common.py:890-892.  The 128 -> 256 duplication and the (N, D) -> (D, N) layout of `descriptors{0,1}` are
@@ -17,6 +19,7 @@ The caller's `carhynet` object is used as it is: anything with a `.model` (the t
 that only offers the reference's `compute_sift(patches, kps, color)` is called through that method.
 """
 import math
+import os
 
 import numpy as np
 import torch
@@ -115,26 +118,111 @@ def extract_patches(kps, levels, support=PATCH_SUPPORT, out_size=PATCH_SIZE):
     return np.array(out) / 255.0
 
 
+def patch_maps(kps):
+    """Per keypoint: the pyramid level index and the 2 x 3 matrix `extract_patches` hands to cv2.warpAffine
+    (utils/library.py:84-110), vectorised over the keypoints with the reference's dtypes (float32 rotation / step, float64
+    shift), then inverted the way cv::warpAffine inverts its argument (imgwarp.cpp).  Returns (level int32 [N],
+    inverse map float64 [N, 6])."""
+    n = len(kps)
+    r = (PATCH_SUPPORT - 1) / 2
+    octv = np.array([k.octave for k in kps], dtype=np.int64).reshape(n)
+    octave = octv & 0xFF
+    layer = (octv >> 8) & 0xFF
+    octave = np.where(octave >= 128, octave - 256, octave)
+    scale = np.where(octave >= 0, 1.0 / (1 << np.maximum(octave, 0)), (1 << np.maximum(-octave, 0)).astype(np.float64))
+    size = np.array([k.size for k in kps], dtype=np.float64).reshape(n)
+    pt = np.array([k.pt for k in kps], dtype=np.float64).reshape(n, 2)
+    ang = np.array([k.angle for k in kps], dtype=np.float64).reshape(n)
+    step = size * scale * 0.5
+    centre = pt * scale[:, None]
+    angle = 360.0 - ang
+    angle = np.where(np.abs(angle - 360.0) < 1.19209e-07, 0.0, angle)
+    phi = np.deg2rad(angle)
+    s, c = np.sin(phi), np.cos(phi)
+    step32 = step.astype(np.float32)
+    r00 = (c.astype(np.float32) / step32).astype(np.float64)
+    r01 = ((-s).astype(np.float32) / step32).astype(np.float64)
+    r10 = (s.astype(np.float32) / step32).astype(np.float64)
+    r11 = r00
+    m2 = r - (r00 * centre[:, 0] + r01 * centre[:, 1])
+    m5 = r - (r10 * centre[:, 0] + r11 * centre[:, 1])
+    # cv::warpAffine without WARP_INVERSE_MAP
+    det = r00 * r11 - r01 * r10
+    with np.errstate(divide='ignore'):
+        d = np.where(det != 0, 1.0 / det, 0.0)
+    a11, a22 = r11 * d, r00 * d
+    i0, i1, i3, i4 = a11, r01 * (-d), r10 * (-d), a22
+    b1 = -i0 * m2 - i1 * m5
+    b2 = -i3 * m2 - i4 * m5
+    inv = np.stack([i0, i1, b1, i3, i4, b2], axis=1)
+    level = ((octave - FIRST_OCTAVE) * (LAYERS + 3) + layer).astype(np.int32)
+    return level, np.ascontiguousarray(inv, dtype=np.float64)
+
+
+def extract_patches_device(kps, levels, device):
+    """`extract_patches` on the GPU: (N, 32, 32[, C]) float32 ON `device`, bit-identical to the host path (the kernel follows
+    OpenCV's 8-bit fixed-point cubic warp, csrc/patches.cu).  The pyramid levels are uploaded once per image."""
+    import ctypes as C
+    from . import _lib
+    dev = torch.device(device)
+    if dev.type != 'cuda':
+        raise _lib.GimsError('extract_patches_device needs a CUDA device')
+    n = len(kps)
+    cn = levels[0].shape[2] if levels[0].ndim == 3 else 1
+    shape = (n, PATCH_SIZE, PATCH_SIZE, cn) if levels[0].ndim == 3 else (n, PATCH_SIZE, PATCH_SIZE)
+    out = torch.empty(shape, dtype=torch.float32, device=dev)
+    if n == 0:
+        return out
+    sizes = [int(l.size) for l in levels]
+    offs = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.int64)
+    flat = torch.empty(int(sum(sizes)), dtype=torch.uint8).pin_memory()
+    fl = flat.numpy()
+    for l, o in zip(levels, offs):
+        if l.dtype != np.uint8:
+            raise _lib.GimsError('extract_patches_device: pyramid levels must be uint8 (got %s)' % l.dtype)
+        fl[o:o + l.size] = np.ascontiguousarray(l).reshape(-1)
+    level, inv = patch_maps(kps)
+    st = torch.cuda.current_stream(dev)
+    with torch.cuda.device(dev):
+        d_lv = flat.to(dev, non_blocking=True)
+        d_off = torch.from_numpy(offs).to(dev)
+        d_h = torch.tensor([l.shape[0] for l in levels], dtype=torch.int32, device=dev)
+        d_w = torch.tensor([l.shape[1] for l in levels], dtype=torch.int32, device=dev)
+        d_level = torch.from_numpy(level).to(dev)
+        d_inv = torch.from_numpy(inv).to(dev)
+        _lib.check(_lib.lib().gims_extract_patches(_lib.ptr(d_lv), _lib.ptr(d_off), _lib.ptr(d_h), _lib.ptr(d_w), len(levels), cn,
+                                                   _lib.ptr(d_level), _lib.ptr(d_inv), n, _lib.ptr(out),
+                                                   C.c_void_p(st.cuda_stream)), 'gims_extract_patches')
+        # the staging buffers may be freed once the stream has passed this point
+        for t in (d_lv, d_off, d_h, d_w, d_level, d_inv):
+            t.record_stream(st)
+    return out
+
+
 def describe(patches, carhynet, device, batch_size=512):
-    """(N, 128) descriptors ON `device`.  `patches`: (N, 32, 32, 3) colour or (N, 32, 32) grey, float in [0, 1]."""
+    """(N, 128) descriptors ON `device`.  `patches`: (N, 32, 32, 3) colour or (N, 32, 32) grey, float in [0, 1]; a numpy
+    array (host path) or a tensor that is already on the device (extract_patches_device)."""
     n = len(patches)
     model = getattr(carhynet, 'model', None)
     if not isinstance(model, torch.nn.Module) and isinstance(carhynet, torch.nn.Module):
         model = carhynet
     if model is None:
         # only the reference's host interface is available (carhynet/models.py:667-670): use it, upload once
+        if torch.is_tensor(patches):
+            patches = patches.cpu().numpy()
         _, d = carhynet.compute_sift(patches, list(range(n)), patches.ndim == 4)
         return torch.as_tensor(np.asarray(d, dtype=np.float32).reshape(n, -1), device=device)
     batch_size = int(getattr(carhynet, 'batch_size', batch_size))
     p = next(model.parameters(), None)
     mdev = p.device if p is not None else torch.device(device)
-    x = torch.from_numpy(np.ascontiguousarray(patches, dtype=np.float32))
+    x = patches if torch.is_tensor(patches) else torch.from_numpy(np.ascontiguousarray(patches, dtype=np.float32))
     x = x.permute(0, 3, 1, 2) if x.dim() == 4 else x.unsqueeze(1)
     outs = []
     with torch.no_grad():
         for i in range(0, n, batch_size):
             chunk = x[i:i + batch_size]
-            chunk = chunk.pin_memory().to(mdev, non_blocking=True) if mdev.type == 'cuda' else chunk.to(mdev)
+            if chunk.device != mdev:
+                chunk = chunk.pin_memory().to(mdev, non_blocking=True) if (mdev.type == 'cuda' and not chunk.is_cuda) else chunk.to(mdev)
             outs.append(model(chunk).reshape(chunk.shape[0], -1))
     d = torch.cat(outs) if outs else torch.zeros(0, 128, device=mdev)
     return d.to(device)
@@ -150,7 +238,8 @@ def sift_forward(data, device):
         img = np.asarray(img)
         kps = detect(img, max_kp)
         levels = gaussian_pyramid(img)
-        patches = extract_patches(kps, levels)
+        on_gpu = torch.device(device).type == 'cuda' and levels[0].dtype == np.uint8 and os.environ.get('GIMS_HOST_PATCHES') != '1'
+        patches = extract_patches_device(kps, levels, device) if on_gpu else extract_patches(kps, levels)
         d = describe(patches, data['carhynet'], device)                        # (N, 128), on the device
         pts = np.array([k.pt for k in kps], dtype=np.float32).reshape(-1, 2)
         resp = np.array([k.response for k in kps], dtype=np.float32)

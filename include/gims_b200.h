@@ -224,6 +224,23 @@ GIMS_API int gims_sinkhorn_match(const float* couplings, int ld, int n0_max, int
                         int64_t* matches0, int64_t* matches1, float* mscores0, float* mscores1,
                         unsigned* status_dev, void* stream);
 
+/* ---- front end: oriented keypoint patches on the device ------------------
+ * replaces the per-keypoint loop of ComputePatches (utils/library.py:84-110: cv2.warpAffine INTER_CUBIC / BORDER_CONSTANT
+ * into 64 x 64) and the INTER_AREA resize to 32 x 32 + /255 of utils/common.py:882-884; bit-identical to OpenCV's 8-bit
+ * fixed-point warp.  The Gaussian pyramid (utils/library.py:234-293) is built by the caller (OpenCV) and uploaded:
+ *   levels           uint8, every level H x W x channels (channels 1 or 3), concatenated; level l starts at byte
+ *                    level_offset_dev[l] and is level_height_dev[l] x level_width_dev[l]
+ *   kp_level_dev     [n_kp] pyramid level of each keypoint ((octave - firstOctave) * (nOctaveLayers + 3) + layer)
+ *   kp_inverse_map_dev [n_kp][6] double: the dst -> src affine map, i.e. the 2 x 3 matrix the reference passes to
+ *                    cv2.warpAffine, inverted as cv::warpAffine inverts it
+ *   patches_out      [n_kp][32][32][channels] fp32 in [0, 1] */
+GIMS_API int gims_extract_patches(const unsigned char* levels, const long long* level_offset_dev, const int* level_height_dev,
+                         const int* level_width_dev, int n_levels, int channels, const int* kp_level_dev,
+                         const double* kp_inverse_map_dev, int n_kp, float* patches_out, void* stream);
+
+/* test hook: the 32 x 32 x 16 int16 bicubic weight table of gims_extract_patches, as built on the host */
+GIMS_API int gims_debug_bicubic_table(short* out_host);
+
 /* ---- caller-side result consumption on the device --------------------
  * gims_gt_matches replaces utils/preprocess_utils.py:98-132 torch_find_matches (called at eval_homography.py:205):
  *   kpts0 [n0][2], kpts1 [n1][2] pixel xy (fp32, device); homography_dev: 9 fp32, row-major, maps image 0 -> image 1.
