@@ -159,6 +159,21 @@ def patch_maps(kps):
     return level, np.ascontiguousarray(inv, dtype=np.float64)
 
 
+_STAGING = __import__('threading').local()
+
+
+def _pinned_staging(nbytes):
+    """Grow-only pinned host buffer of the calling thread (pinning 40 MB per call cost more than the copy itself)."""
+    ev = getattr(_STAGING, 'event', None)
+    if ev is not None:
+        ev.synchronize()                          # the previous upload from this buffer has left the host
+    buf = getattr(_STAGING, 'buf', None)
+    if buf is None or buf.numel() < nbytes:
+        buf = torch.empty(max(nbytes, 1 << 20), dtype=torch.uint8).pin_memory()
+        _STAGING.buf = buf
+    return buf
+
+
 def extract_patches_device(kps, levels, device):
     """`extract_patches` on the GPU: (N, 32, 32[, C]) float32 ON `device`, bit-identical to the host path (the kernel follows
     OpenCV's 8-bit fixed-point cubic warp, csrc/patches.cu).  The pyramid levels are uploaded once per image."""
@@ -173,18 +188,26 @@ def extract_patches_device(kps, levels, device):
     out = torch.empty(shape, dtype=torch.float32, device=dev)
     if n == 0:
         return out
-    sizes = [int(l.size) for l in levels]
+    level, inv = patch_maps(kps)
+    # only the levels that carry keypoints travel (the coarse octaves are small, the unused fine ones are not)
+    used = np.zeros(len(levels), dtype=bool)
+    used[level] = True
+    sizes = [int(l.size) if u else 0 for l, u in zip(levels, used)]
     offs = np.concatenate([[0], np.cumsum(sizes)[:-1]]).astype(np.int64)
-    flat = torch.empty(int(sum(sizes)), dtype=torch.uint8).pin_memory()
+    total = int(sum(sizes))
+    flat = _pinned_staging(total)
     fl = flat.numpy()
-    for l, o in zip(levels, offs):
+    for l, o, u in zip(levels, offs, used):
+        if not u:
+            continue
         if l.dtype != np.uint8:
             raise _lib.GimsError('extract_patches_device: pyramid levels must be uint8 (got %s)' % l.dtype)
-        fl[o:o + l.size] = np.ascontiguousarray(l).reshape(-1)
-    level, inv = patch_maps(kps)
+        np.copyto(fl[o:o + l.size].reshape(l.shape), l)
     st = torch.cuda.current_stream(dev)
     with torch.cuda.device(dev):
-        d_lv = flat.to(dev, non_blocking=True)
+        d_lv = flat[:total].to(dev, non_blocking=True)
+        _STAGING.event = torch.cuda.Event()
+        _STAGING.event.record(st)                 # the staging buffer is reused by this thread's next call
         d_off = torch.from_numpy(offs).to(dev)
         d_h = torch.tensor([l.shape[0] for l in levels], dtype=torch.int32, device=dev)
         d_w = torch.tensor([l.shape[1] for l in levels], dtype=torch.int32, device=dev)
@@ -228,16 +251,39 @@ def describe(patches, carhynet, device, batch_size=512):
     return d.to(device)
 
 
-def sift_forward(data, device):
+def host_stages(image_sets, max_kp=-1):
+    """The OpenCV stages (SIFT detection + Gaussian pyramid) of several images side by side — OpenCV releases the GIL, and
+    the reference runs image 0 and image 1 one after the other (matching.py:18-24).  `image_sets`: a list of iterables of
+    images (each what `data['image']` is); returns, per set, a list of (keypoints, pyramid levels)."""
+    flat = [np.asarray(img) for imgs in image_sets for img in imgs]
+    counts = [len(imgs) for imgs in image_sets]
+
+    def stage(img):
+        return detect(img, max_kp), gaussian_pyramid(img)
+    if len(flat) > 1:
+        from concurrent.futures import ThreadPoolExecutor
+        with ThreadPoolExecutor(max_workers=min(len(flat), 8)) as pool:
+            done = list(pool.map(stage, flat))
+    else:
+        done = [stage(img) for img in flat]
+    out, i = [], 0
+    for c in counts:
+        out.append(done[i:i + c])
+        i += c
+    return out
+
+
+def sift_forward(data, device, staged=None):
     """Same dict in / dict out as utils/common.py:837-893: `data['image']` iterates over images, `data['carhynet']` is the
     caller's descriptor object; returns lists (one entry per image) of device tensors
-    `keypoints` (N, 2) fp32 pixel xy, `scores` (N,) fp32 SIFT responses, `descriptors` (256, N) fp32."""
+    `keypoints` (N, 2) fp32 pixel xy, `scores` (N,) fp32 SIFT responses, `descriptors` (256, N) fp32.
+    `staged`: the (keypoints, pyramid) pairs of the images if `host_stages` has already produced them."""
     max_kp = data.get('max_keypoints', -1)
     kpts, scores, descs = [], [], []
-    for img in data['image']:
-        img = np.asarray(img)
-        kps = detect(img, max_kp)
-        levels = gaussian_pyramid(img)
+    images = [np.asarray(img) for img in data['image']]
+    if staged is None:
+        staged = host_stages([images], max_kp)[0]
+    for img, (kps, levels) in zip(images, staged):
         on_gpu = torch.device(device).type == 'cuda' and levels[0].dtype == np.uint8 and os.environ.get('GIMS_HOST_PATCHES') != '1'
         patches = extract_patches_device(kps, levels, device) if on_gpu else extract_patches(kps, levels)
         d = describe(patches, data['carhynet'], device)                        # (N, 128), on the device

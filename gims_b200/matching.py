@@ -1,7 +1,7 @@
 """Host-side mirror of the reference's `Matching` front-end (models/matching.py:8-30)."""
 import torch
 
-from .frontend import sift_forward
+from .frontend import host_stages, sift_forward
 from .gmatcher import GMatcher
 
 
@@ -20,12 +20,14 @@ class Matching(torch.nn.Module):
 
     def forward(self, data):
         pred = {}
-        for s in ('0', '1'):
-            if 'keypoints' + s not in data:
-                dev = data.get('device', self.gmodel.bin_score.device)
-                out = sift_forward({'image': data['image' + s], 'max_keypoints': self.max_keypoints,
-                                    'carhynet': data['carhynet']}, device=dev)
-                pred = {**pred, **{k + s: v for k, v in out.items()}}
+        need = [s for s in ('0', '1') if 'keypoints' + s not in data]
+        # the OpenCV stages of both images run side by side (the reference does image 0, then image 1)
+        staged = dict(zip(need, host_stages([data['image' + s] for s in need], self.max_keypoints))) if need else {}
+        for s in need:
+            dev = data.get('device', self.gmodel.bin_score.device)
+            out = sift_forward({'image': data['image' + s], 'max_keypoints': self.max_keypoints,
+                                'carhynet': data['carhynet']}, device=dev, staged=staged[s])
+            pred = {**pred, **{k + s: v for k, v in out.items()}}
         data = {**data, **pred}
         for k in data:
             if isinstance(data[k], (list, tuple)):
