@@ -442,6 +442,7 @@ int side_stream_for(cudaStream_t main, SideStream& out) {
   std::lock_guard<std::mutex> lk(g_side_mu);
   for (auto& e : g_side)
     if (e.first.first == dev && e.first.second == main) { out = e.second; return GIMS_OK; }
+  if (g_side.size() >= 64) { out = {main, nullptr, nullptr}; return GIMS_OK; }   // a caller that keeps making streams: no fork
   SideStream n;
   GIMS_CUDA_OK(cudaStreamCreateWithFlags(&n.s, cudaStreamNonBlocking));
   GIMS_CUDA_OK(cudaEventCreateWithFlags(&n.fork, cudaEventDisableTiming));
@@ -537,9 +538,12 @@ extern "C" int gims_forward_pairs(const gims_model* m, int n_pairs, const gims_p
   // (gmatcher.py:265-271), image by image into the stacked buffer
   for (int p = 0; p < n_pairs; ++p) GIMS_CUDA_OK(cudaMemsetAsync(out[p].status_dev, 0, sizeof(unsigned), st));
   SideStream side = {st, nullptr, nullptr};
-  const bool forked = fork_images();
+  bool forked = fork_images();
   if (forked) {
     GIMS_TRY(side_stream_for(st, side));
+    forked = side.fork != nullptr;
+  }
+  if (forked) {
     GIMS_CUDA_OK(cudaEventRecord(side.fork, st));
     GIMS_CUDA_OK(cudaStreamWaitEvent(side.s, side.fork, 0));
   }

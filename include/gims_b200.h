@@ -12,8 +12,13 @@
  *   - every pointer is a DEVICE pointer unless its name ends in `_host`;
  *   - `stream` is a `cudaStream_t` passed as `void*`; all work is enqueued on it, nothing
  *     synchronises unless stated;
- *   - no hidden allocation: scratch memory comes from caller-provided workspaces sized by the
- *     matching `*_workspace_bytes()` query; a `gims_model` only stores pointers/config (host heap);
+ *   - scratch memory comes from caller-provided workspaces sized by the matching `*_workspace_bytes()`
+ *     query; a `gims_model` only stores pointers/config (host heap).  The library itself owns, per
+ *     process and device, only: the 32 KB cubic-weight table of gims_extract_patches (one cudaMalloc on
+ *     first use), one side stream + two events per caller stream (gims_forward_pairs forks the two
+ *     images' graph chains; at most 64 caller streams, further ones run unforked), the two events
+ *     that order cooperative kernels of different streams, the default arithmetic mode
+ *     (gims_set_gemm_mode) and the optional profiler / trace hooks.  All of it is mutex-protected;
  *   - functions return 0 on success, a negative `GIMS_ERR_*` otherwise; `gims_last_error()` gives the
  *     thread-local message;
  *   - features are node-major fp32 rows `[n][256]`; graphs are int32 CSR; counts that depend on the

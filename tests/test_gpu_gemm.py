@@ -17,6 +17,11 @@ SHAPES = [
     (200, 200, 64, 32, 0, True, False, True),
     (129, 129, 32, 64, 0, True, False, False),
     (1, 1, 256, 128, 0, True, True, False),
+    # the persistent kernel's corners: one k-block per tile (a single issuer / accumulator), K concatenated from two
+    # 64-wide buffers, and many tiles per CTA (628 work items on 148 CTAs) with ragged last rows
+    (1000, 977, 256, 64, 0, True, True, True),
+    (700, 700, 384, 64, 64, True, False, False),
+    (20000, 19999, 512, 256, 0, True, True, True),
 ]
 
 
