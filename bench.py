@@ -694,6 +694,7 @@ def main():
             'dtype': 'f32', 'data': 'synthetic',
             'config': base_config(args, world), 'kept_keypoints': counts[:2], 'sinkhorn_path': sink_path,
             'arithmetic': gemm_mode_name,
+            'cuda_device_max_connections': os.environ.get('CUDA_DEVICE_MAX_CONNECTIONS'),   # set by `import gims_b200`
             'clocks': clocks, 'e2e': e2e, 'gpu_launches': int(launches) * world, 'gpu_launches_per_rank': int(launches),
             'roofline': roof, 'roofline_other': other,
             'pair_gflop': pair_flops(counts[0], counts[1]) / 1e9,

@@ -17,18 +17,31 @@ for s in range(16):
     d['device'] = dev
     pool.append(d)
 
-def run(T, per_thread, read_back=True):
+pool_dev = [{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in d.items()} for d in pool]
+
+
+def run(T, per_thread, read_back=True, stagger_ms=0.0, resident=False, raw=False):
+    src = pool_dev if resident else pool
     streams = [torch.cuda.Stream(device=dev) for _ in range(T)]
     t_fwd = [0.0] * T
     t_read = [0.0] * T
     def worker(t):
         torch.cuda.set_device(dev)
+        if stagger_ms:
+            time.sleep(t * stagger_ms * 1e-3)
         with torch.no_grad(), torch.cuda.stream(streams[t]):
             for i in range(per_thread):
                 a = time.perf_counter()
-                pred = m(dict(pool[(t + i) % 16]))
+                d = src[(t + i) % 16]
+                if raw:      # the library call + the one metadata read-back, none of the dict handling of Matching.forward
+                    r = m.gmodel.run_pair(d['keypoints0'][0], d['descriptors0'][0], d['scores0'][0], d['keypoints1'][0],
+                                          d['descriptors1'][0], d['scores1'][0], d['image0'].shape, d['image1'].shape)
+                    r['meta'].cpu()
+                    pred = None
+                else:
+                    pred = m(dict(d))
                 b = time.perf_counter()
-                if read_back:
+                if read_back and pred is not None:
                     pred['matches0'].cpu(); pred['matching_scores0'].cpu()
                 c = time.perf_counter()
                 t_fwd[t] += b - a; t_read[t] += c - b
@@ -39,11 +52,12 @@ def run(T, per_thread, read_back=True):
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     k = T * per_thread
-    print('T=%2d read_back=%d: %.1f pairs/s | per pair and thread: forward() %.2f ms, read-back %.2f ms' %
-          (T, read_back, k / dt, 1e3 * sum(t_fwd) / k, 1e3 * sum(t_read) / k))
+    print('T=%2d read_back=%d resident=%d raw=%d: %.1f pairs/s | per pair and thread: forward() %.2f ms, read-back %.2f ms' %
+          (T, read_back, resident, raw, k / dt, 1e3 * sum(t_fwd) / k, 1e3 * sum(t_read) / k))
 
 run(8, 4)
-for T in (1, 2, 4, 8, 16):
-    run(T, 256 // T if T > 1 else 64)
-run(8, 32, read_back=False)
-os.environ['X'] = '1'
+for rep in range(2):
+    run(8, 64)
+    run(8, 64, resident=True)
+    run(8, 64, resident=True, raw=True)
+    run(8, 64, resident=False, raw=True)
