@@ -56,8 +56,9 @@ def run(T, per_thread, read_back=True, stagger_ms=0.0, resident=False, raw=False
           (T, read_back, resident, raw, k / dt, 1e3 * sum(t_fwd) / k, 1e3 * sum(t_read) / k))
 
 run(8, 4)
-for rep in range(2):
+for si in (0.005, 0.0005, 0.00005):
+    sys.setswitchinterval(si)
+    print('switch interval', si)
     run(8, 64)
-    run(8, 64, resident=True)
-    run(8, 64, resident=True, raw=True)
-    run(8, 64, resident=False, raw=True)
+    run(12, 48)
+    run(16, 32)
