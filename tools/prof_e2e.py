@@ -20,9 +20,10 @@ for s in range(16):
 pool_dev = [{k: (v.to(dev) if torch.is_tensor(v) else v) for k, v in d.items()} for d in pool]
 
 
-def run(T, per_thread, read_back=True, stagger_ms=0.0, resident=False, raw=False):
+def run(T, per_thread, read_back=True, stagger_ms=0.0, resident=False, raw=False, pinned_sync=False):
     src = pool_dev if resident else pool
     streams = [torch.cuda.Stream(device=dev) for _ in range(T)]
+    pins = [torch.empty(8 + 2 * 4096, dtype=torch.int32).pin_memory() for _ in range(T)]
     t_fwd = [0.0] * T
     t_read = [0.0] * T
     def worker(t):
@@ -36,7 +37,12 @@ def run(T, per_thread, read_back=True, stagger_ms=0.0, resident=False, raw=False
                 if raw:      # the library call + the one metadata read-back, none of the dict handling of Matching.forward
                     r = m.gmodel.run_pair(d['keypoints0'][0], d['descriptors0'][0], d['scores0'][0], d['keypoints1'][0],
                                           d['descriptors1'][0], d['scores1'][0], d['image0'].shape, d['image1'].shape)
-                    r['meta'].cpu()
+                    if pinned_sync:
+                        buf = pins[t][:r['meta'].numel()]
+                        buf.copy_(r['meta'], non_blocking=True)
+                        streams[t].synchronize()
+                    else:
+                        r['meta'].cpu()
                     pred = None
                 else:
                     pred = m(dict(d))
@@ -52,13 +58,12 @@ def run(T, per_thread, read_back=True, stagger_ms=0.0, resident=False, raw=False
     torch.cuda.synchronize()
     dt = time.perf_counter() - t0
     k = T * per_thread
-    print('T=%2d read_back=%d resident=%d raw=%d: %.1f pairs/s | per pair and thread: forward() %.2f ms, read-back %.2f ms' %
-          (T, read_back, resident, raw, k / dt, 1e3 * sum(t_fwd) / k, 1e3 * sum(t_read) / k))
+    print('T=%2d read_back=%d resident=%d raw=%d pinned_sync=%d: %.1f pairs/s | per pair and thread: forward() %.2f ms, read-back %.2f ms' %
+          (T, read_back, resident, raw, pinned_sync, k / dt, 1e3 * sum(t_fwd) / k, 1e3 * sum(t_read) / k))
 
 run(8, 4)
-for si in (0.005, 0.0005, 0.00005):
-    sys.setswitchinterval(si)
-    print('switch interval', si)
-    run(8, 64)
-    run(12, 48)
-    run(16, 32)
+for rep in range(2):
+    run(8, 64, raw=True)
+    run(8, 64, raw=True, pinned_sync=True)
+    run(12, 48, raw=True, pinned_sync=True)
+    run(16, 32, raw=True, pinned_sync=True)
