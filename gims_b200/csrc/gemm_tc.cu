@@ -135,6 +135,7 @@ struct TcArgs {
   float* qp; void* kp; void* vt; int ldv; int rows_total; int vbase[kMaxSegs];
   unsigned* status;              // 16-bit planes / fp16 operands: overflow flag
   const float* wscale_inv;       // PREC 1: the W planes hold W * 2^e; the accumulators are multiplied by *wscale_inv = 2^-e
+  int single_chain;              // persistent kernel, experiment knob (GIMS_GEMM_SINGLE_CHAIN=1)
 };
 
 // Optional pipeline trace (bring-up / profiling): CTA (0,0) stores clock64() stamps, see tools/gemm_trace.py.
@@ -632,7 +633,8 @@ k_gemm_tcp(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
   if (trace && threadIdx.x == 0) trace[0] = clock64();
 #define TCP_TRACE(k) do { if (trace && lt < 4) trace[8 + lt * 8 + (k)] = clock64(); } while (0)
   const int nkb = (g.K0 + g.K1) / Cfg::kBlockK;
-  const int n_issuers = nkb >= 2 ? 2 : 1;
+  const bool single = g.single_chain != 0;              // experiment: one issuer, one accumulation chain per tile
+  const int n_issuers = (nkb >= 2 && !single) ? 2 : 1;
 
   // the live row counts are device scalars: read once (a global load per tile per role cost ~800 clk at every tile
   // boundary), before the start-up barrier below
@@ -708,14 +710,16 @@ k_gemm_tcp(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
       constexpr uint32_t idesc = umma_idesc_f16(BM, BN, PLANES == 2 ? 0 : 1);
       const uint64_t d_stage0 = umma_desc_sw128(smem_u32(stage_ptr(0) + Cfg::kABytes));
       const uint32_t acc = tmem_base + t * BN;
+      const int kstep = single ? 1 : 2;
       int last = -1;
-      for (int kb = t; kb < nkb; kb += 2) last = kb;
+      if (!(single && t > 0))
+        for (int kb = t; kb < nkb; kb += kstep) last = kb;
       int lt = 0;                                          // live tiles so far
       for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
         TileCoord tcd;
         if (!decode(w, tcd)) continue;
         if (lt > 0 && last >= 0) { mbar_wait(acc_free, (uint32_t)(lt - 1) & 1u); tcgen05_fence_after(); }
-        for (int kb = t; kb < nkb; kb += 2) {
+        for (int kb = t; kb < nkb && last >= 0; kb += kstep) {
           const int gk = lt * nkb + kb;
           const int s = gk % Cfg::kStages, slot = gk % Cfg::kRing;
           mbar_wait(&conv[slot], (uint32_t)(gk / Cfg::kRing) & 1u);
@@ -724,7 +728,7 @@ k_gemm_tcp(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
           const uint64_t w_lo = w_hi + (Cfg::kWBytes >> 4);
           const uint32_t a_hi = tmem_base + Cfg::kRingCol + slot * 64;
           const uint32_t a_lo = a_hi + 32;
-          const uint32_t fresh = kb >= 2 ? 1u : 0u;        // 0: first k-block of this issuer in this tile
+          const uint32_t fresh = kb >= kstep ? 1u : 0u;    // 0: first k-block of this issuer in this tile
           if (t == 0 && kb == 0) TCP_TRACE(7);
 #pragma unroll
           for (int ks = 0; ks < 4; ++ks) {
@@ -750,7 +754,7 @@ k_gemm_tcp(const __grid_constant__ CUtensorMap mapA0, const __grid_constant__ CU
     const int q = warp & 3;
     const int t = 32 * q + lane;
     const uint32_t lane_base = tmem_base + ((uint32_t)(32 * q) << 16);
-    const int n_main = nkb < 2 ? nkb : 2;
+    const int n_main = (nkb < 2 || single) ? 1 : 2;
     // PARK = accumulator 0 + accumulator 1 of tile f (fp32, RN — what the one-tile epilogue computes), then the
     // accumulators go back to the issuers
     auto fold = [&](int f) {
@@ -915,6 +919,10 @@ int launch_tc(const CUtensorMap& a0, const CUtensorMap& a1, const CUtensorMap& w
 // GIMS_GEMM_TPC (default 2) tiles — what matters when several streams keep the GPU full is SM-time per tile, and a CTA's
 // fixed cost (prologue, first TMA round trip, last epilogue) is then paid once per two tiles; small problems (fewer
 // work items than half the SMs) keep one tile per CTA for latency.
+int single_chain_knob() {
+  static const int on = [] { const char* e = getenv("GIMS_GEMM_SINGLE_CHAIN"); return (e && e[0] == '1') ? 1 : 0; }();
+  return on;
+}
 bool persist_enabled() {
   static const bool on = [] { const char* e = getenv("GIMS_GEMM_PERSIST"); return !(e && e[0] == '0'); }();
   return on;
@@ -985,6 +993,7 @@ int launch_gemm_tc(const GemmArgs& a, const WPlanes& w, int prec, cudaStream_t s
   g.relu = a.relu; g.scale = 1.f; g.score = 0; g.segs = a.segs;
   g.qkv = 0; g.qp = nullptr; g.kp = g.vt = nullptr; g.ldv = 0; g.rows_total = total_rows; g.status = a.status;
   g.wscale_inv = prec ? w.sinv : nullptr;
+  g.single_chain = single_chain_knob();
   for (int i = 0; i < kMaxSegs; ++i) g.vbase[i] = 0;
   if (qkv) {
     if (a.N != 3 * kD || !a.bias) { set_error("launch_gemm_tc: qkv mode needs N = 768 and a bias"); return GIMS_ERR_ARG; }
@@ -1074,6 +1083,7 @@ int launch_score_gemm_tc(const float* mdesc, int n0_max, int n1_max, const int* 
   g.relu = 0; g.scale = 0.0625f; g.score = 1;
   g.qkv = 0; g.qp = nullptr; g.kp = g.vt = nullptr; g.ldv = 0; g.rows_total = (int)rows; g.status = status;
   g.wscale_inv = nullptr;
+  g.single_chain = single_chain_knob();
   for (int i = 0; i < kMaxSegs; ++i) { g.vbase[i] = 0; g.tile_end[i] = 0; }
   g.segs = two_segs(n0_max, n1_max, n_dev);
   g.tile_end[0] = cdiv(n0_max, BM);
