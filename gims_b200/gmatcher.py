@@ -9,9 +9,11 @@ Only the inference forward with the dynamic-threshold graph is implemented (SURV
 snapshot) raise NotImplementedError.
 """
 import ctypes as C
+import os
 from copy import deepcopy
 
 import threading
+import time
 
 import torch
 import torch.nn as nn
@@ -299,7 +301,16 @@ class GMatcher(nn.Module):
                 self._meta_pinned[key] = buf
         view = buf[:n]
         view.copy_(meta_dev, non_blocking=True)
-        st.synchronize()
+        if os.environ.get('GIMS_SPIN_SYNC') == '1':
+            st.synchronize()
+        else:
+            # The forward takes milliseconds: poll an event with short sleeps instead of spinning in the driver.  A spinning
+            # caller occupies a core for the whole forward; with more caller threads than cores (8 ranks x 8 callers on the
+            # 16-core host of an 8-GPU box) the spinners starve the threads that have launches to issue.
+            ev = torch.cuda.Event()
+            ev.record(st)
+            while not ev.query():
+                time.sleep(1e-4)
         return view.clone()
 
     def _prepare(self, kpts0, desc0, scores0, kpts1, desc1, scores1, shape0, shape1, radius, percentile, min_size,
