@@ -481,70 +481,58 @@ __global__ void __launch_bounds__(1024) k_iso_resolve(int n, const int* __restri
 // ---------------------------------------------------------------------------------------------
 // a-4  connected components: lock-free union-find, smaller root wins (root == smallest member id)
 // ---------------------------------------------------------------------------------------------
-__device__ __forceinline__ int uf_find(int* parent, int x) {
-  volatile int* p = parent;
-  int cur = x;
-  int par = p[cur];
+// The whole component search in ONE CTA with the parent array in SHARED memory (n <= 16384 nodes = 64 KB): a find is a
+// chain of dependent loads, and through L2 (volatile, ~500 clk per hop) the grid-wide version took 40-86 us for 15 k edges
+// however the unions were distributed; in shared memory a hop is ~30 clk.  Init, base-graph unions, isolated-node unions
+// and the final labelling are one launch instead of four.
+//   init: every node points at its smallest neighbour if that is smaller than itself (CSR rows are ascending, so it is the
+//   first entry) — pointers only ever go to strictly smaller ids along real edges, a forest with the same components;
+//   union: lock-free, smaller root wins (root == smallest member id whatever the order of the unions).
+__device__ __forceinline__ int ufs_find(volatile int* p, int x) {
+  int cur = x, par = p[cur];
   while (par != cur) {
-    int gp = p[par];
+    const int gp = p[par];
     if (gp != par) p[cur] = gp;   // path halving; only ever rewires non-roots to an ancestor
     cur = par;
     par = gp;
   }
   return cur;
 }
-
-__device__ __forceinline__ void uf_union(int* parent, int a, int b) {
+__device__ __forceinline__ void ufs_union(int* parent, int a, int b) {
   while (true) {
-    a = uf_find(parent, a);
-    b = uf_find(parent, b);
+    a = ufs_find(parent, a);
+    b = ufs_find(parent, b);
     if (a == b) return;
-    if (a > b) { int t = a; a = b; b = t; }
-    int old = atomicCAS(&parent[b], b, a);
-    if (old == b) return;
+    if (a > b) { const int t = a; a = b; b = t; }
+    if (atomicCAS(&parent[b], b, a) == b) return;
   }
 }
-
-// Start from a forest instead of singletons: every node points at its smallest neighbour if that is smaller than itself
-// (CSR rows are ascending, so it is the first entry).  Pointers only ever go to strictly smaller ids — no cycles — and
-// only along real edges, so components are unchanged; most unions afterwards find both ends under one root already
-// and return without a CAS (with singletons, every edge of the giant component fought for the same root word).
-__global__ void k_cc_init(int* parent, int n, const int* __restrict__ indptr, const int* __restrict__ idx, int edge_cap) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  int p = i;
-  const int e0 = indptr[i];
-  if (e0 < indptr[i + 1] && e0 < edge_cap) p = min(i, idx[e0]);
-  parent[i] = p;
-}
-
-// warp per node, lanes over its edges; the result does not depend on the order (smaller root wins)
-__global__ void k_cc_union_base(int* parent, int n, const int* __restrict__ indptr, const int* __restrict__ idx, int edge_cap) {
-  const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (i >= n) return;
-  const int e0 = indptr[i], e1 = min(indptr[i + 1], edge_cap);
-  for (int e = e0 + lane; e < e1; e += 32) {
-    const int j = idx[e];
-    if (j > i) uf_union(parent, i, j);
+__global__ void __launch_bounds__(1024) k_cc_components(int* __restrict__ parent_out, int n, const int* __restrict__ indptr,
+                                                        const int* __restrict__ idx, int edge_cap, const int* __restrict__ iso_u,
+                                                        const int* __restrict__ iso_v, const int* __restrict__ iso_count) {
+  extern __shared__ int sp[];
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int e0 = indptr[i];
+    sp[i] = (e0 < indptr[i + 1] && e0 < edge_cap) ? min(i, idx[e0]) : i;
   }
-}
-
-__global__ void k_cc_union_iso(int* parent, const int* __restrict__ iso_u, const int* __restrict__ iso_v,
-                               const int* __restrict__ iso_count) {
-  int k = blockIdx.x * blockDim.x + threadIdx.x;
-  if (k < *iso_count) uf_union(parent, iso_u[k], iso_v[k]);
-}
-
-// After every union has completed (kernel boundary): publish the root of each node.  A concurrent
-// reader may see either the old parent or the final root; both chains end at the same root.
-__global__ void k_cc_label(int* parent, int n) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  volatile int* p = parent;
-  int r = i;
-  while (p[r] != r) r = p[r];
-  p[i] = r;
+  __syncthreads();
+  // a thread per node (each undirected edge once, from its smaller end): with ~7 edges per node a warp per node leaves
+  // nine lanes in ten idle, and the unions of a node are short now that a hop costs a shared-memory access
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    const int e0 = indptr[i], e1 = min(indptr[i + 1], edge_cap);
+    for (int e = e0; e < e1; ++e) {
+      const int j = idx[e];
+      if (j > i) ufs_union(sp, i, j);
+    }
+  }
+  const int n_iso = *iso_count;
+  for (int k = threadIdx.x; k < n_iso; k += blockDim.x) ufs_union(sp, iso_u[k], iso_v[k]);
+  __syncthreads();
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    int r = i;
+    while (sp[r] != r) r = sp[r];
+    parent_out[i] = r;
+  }
 }
 
 __global__ void k_cc_count(const int* __restrict__ label, int n, int* comp_size) {
@@ -888,13 +876,9 @@ extern "C" int gims_agc_build(const float* kpts, const float* desc, int desc_cha
   k_iso_resolve<<<1, 1024, 0, st>>>(n, w.deg_base, n_base_edges, w.nn_iso, w.iso_u, w.iso_v, w.iso_count, w.extra_cnt);
   GIMS_LAUNCH_OK();
   // a-4
-  k_cc_init<<<cdiv(n, 256), 256, 0, st>>>(w.parent, n, w.indptr_base, w.idx_base, edge_cap);
-  GIMS_LAUNCH_OK();
-  k_cc_union_base<<<cdiv(n, 8), 256, 0, st>>>(w.parent, n, w.indptr_base, w.idx_base, edge_cap);
-  GIMS_LAUNCH_OK();
-  k_cc_union_iso<<<cdiv(n, 256), 256, 0, st>>>(w.parent, w.iso_u, w.iso_v, w.iso_count);
-  GIMS_LAUNCH_OK();
-  k_cc_label<<<cdiv(n, 256), 256, 0, st>>>(w.parent, n);
+  GIMS_CUDA_OK(cudaFuncSetAttribute(k_cc_components, cudaFuncAttributeMaxDynamicSharedMemorySize, GIMS_MAX_KPTS * (int)sizeof(int)));
+  k_cc_components<<<1, 1024, (size_t)n * sizeof(int), st>>>(w.parent, n, w.indptr_base, w.idx_base, edge_cap, w.iso_u, w.iso_v,
+                                                           w.iso_count);
   GIMS_LAUNCH_OK();
   k_cc_count<<<cdiv(n, 256), 256, 0, st>>>(w.parent, n, w.comp_size);
   GIMS_LAUNCH_OK();
