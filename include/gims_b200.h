@@ -23,7 +23,9 @@
  *     thread-local message;
  *   - features are node-major fp32 rows `[n][256]`; graphs are int32 CSR; counts that depend on the
  *     data (kept keypoints N', edges E) live in device memory (`*_dev` int pointers) so the whole
- *     forward can be enqueued (and captured in a CUDA graph) without a host round trip.
+ *     forward is enqueued without a host round trip.  (Stream capture of a whole forward is NOT supported: the
+ *     cooperative Sinkhorn kernels of different streams are ordered through process-wide events, and the two images'
+ *     graph chains fork onto a library-owned side stream.)
  */
 #ifndef GIMS_B200_H
 #define GIMS_B200_H
