@@ -115,6 +115,7 @@ class GMatcher(nn.Module):
         self._retired = []            # (handle, packed buffer) replaced by a re-pack, destroyed once idle
         self._ws = {}                 # (device, stream slot) -> [workspace tensor, n0 cap, n1 cap, edge cap]
         self._meta_pinned = {}        # (device, stream, thread) -> pinned staging buffer of the per-call metadata
+        self._in_pinned = {}          # (device, stream, thread, role) -> [pinned staging buffer of a pageable input, event]
         self.edge_cap_factor = 64     # initial capacity of the CSR edge list = factor * max(n0, n1); grows on overflow
         if cfg['weights_path']:
             weights = torch.load(cfg['weights_path'], map_location='cpu', weights_only=False)
@@ -286,6 +287,30 @@ class GMatcher(nn.Module):
             self._ws[key] = ws
             return ws
 
+    def _upload(self, t, dev, role):
+        """fp32 contiguous copy of an input on `dev`.  Device tensors and pinned host tensors go as they are (an asynchronous
+        copy); a PAGEABLE host tensor is first copied into a pinned staging buffer of the calling thread — a pageable
+        host->device copy is staged by the driver under the lock the other caller threads need for their launches (see
+        `_read_meta`).  One staging buffer per (thread, stream, input role), reused once its last upload has left the host."""
+        if t.device.type != 'cpu' or t.is_pinned():
+            return t.to(dev, torch.float32, non_blocking=True).contiguous()
+        t = t.to(torch.float32).contiguous()
+        st = torch.cuda.current_stream(dev)
+        key = (str(dev), st.cuda_stream, threading.get_ident(), role)
+        ent = self._in_pinned.get(key)
+        if ent is not None and ent[1] is not None:
+            ent[1].synchronize()                    # the previous upload from this buffer is done
+        if ent is None or ent[0].numel() < t.numel():
+            ent = [torch.empty(max(t.numel(), 1024), dtype=torch.float32).pin_memory(), None]
+            with _HANDLE_LOCK:
+                self._in_pinned[key] = ent
+        stage = ent[0][:t.numel()].view(t.shape)
+        stage.copy_(t)
+        out = stage.to(dev, non_blocking=True)
+        ent[1] = torch.cuda.Event()
+        ent[1].record(st)
+        return out
+
     def _read_meta(self, meta_dev, dev):
         """Device -> host copy of the per-call metadata through a PINNED staging buffer + a stream synchronize.
         `meta_dev.cpu()` is a pageable copy: the driver stages it while holding a lock that the other caller threads need for
@@ -356,7 +381,7 @@ class GMatcher(nn.Module):
         ins = ((kpts0, desc0, scores0), (kpts1, desc1, scores1))
         keep = []
         for s in (0, 1):
-            k, de, sc = [t.to(dev, torch.float32, non_blocking=True).contiguous() for t in ins[s]]
+            k, de, sc = [self._upload(t, dev, (s, i)) for i, t in enumerate(ins[s])]
             keep += [k, de, sc]
             pin.kpts[s], pin.desc[s], pin.scores[s] = k.data_ptr(), de.data_ptr(), sc.data_ptr()
             pin.n[s] = ns[s]
