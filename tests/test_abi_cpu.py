@@ -173,6 +173,34 @@ def test_c_packer_equals_python_packer(lib):
     assert rc != 0 and items[-1][0].encode() in lib.gims_last_error()
 
 
+def test_c_packer_other_config(lib):
+    """A smaller network (4 attention layers, a 3-conv keypoint encoder): blob count, offsets and the exactly reproducible
+    blobs of the two packers agree — the C packer derives every shape from the config, not from the default network."""
+    from gims_b200 import GMatcher, _lib
+    from gims_b200.packing import pack_state_dict
+    from gims_b200.synth import make_state_dict
+    cfg = {'transformer_layers': ['self', 'cross'] * 2, 'keypoint_encoder': [32, 64]}
+    sd = make_state_dict(8, config=cfg)
+    flat, offsets, names = pack_state_dict(sd, cfg)
+    c = GMatcher(cfg).c_config()
+    assert lib.gims_packed_blob_count(C.byref(c)) == len(offsets)
+    items = [(k, v.detach().float().contiguous()) for k, v in sd.items() if v.dtype.is_floating_point]
+    arr = (_lib.NamedTensor * len(items))()
+    for a, (k, v) in zip(arr, items):
+        a.name, a.data, a.numel = k.encode(), v.data_ptr(), v.numel()
+    n_floats = lib.gims_pack_weights_floats(C.byref(c))
+    assert n_floats == flat.numel()
+    out = torch.zeros(n_floats)
+    offs = (C.c_int64 * len(offsets))()
+    assert lib.gims_pack_weights(C.byref(c), arr, len(items), C.c_void_p(out.data_ptr()), n_floats, offs, len(offsets)) == 0
+    assert list(offs) == offsets
+    bounds = offsets + [flat.numel()]
+    for i, name in enumerate(names):
+        if '.w1' in name or '.b1' in name:
+            continue                                   # merge composition: summation order (see the test above)
+        assert torch.equal(flat[bounds[i]:bounds[i + 1]].view(torch.int32), out[bounds[i]:bounds[i + 1]].view(torch.int32)), name
+
+
 def test_packing_equals_oracle_sage_kenc():
     from gims_b200.packing import pack_state_dict
     from gims_b200.synth import make_state_dict
