@@ -396,6 +396,35 @@ def test_all_pruned_image():
     assert data['keypoints0'].shape == (1, 0, 2) and data['kept_kpts0_indices'] == [[]]
 
 
+def test_other_network_configuration_vs_oracle():
+    """The constructor config is honoured (gmatcher.py:166-176, 136-140): 4 attention layers in the order self / self /
+    cross / cross and a 3-conv keypoint encoder (its last conv is K = 64 -> N = 256: one k-block per tile in the persistent
+    GEMM), against the oracle run on the same weights and inputs."""
+    from gims_b200 import Matching
+    from oracle import gims_oracle as orc
+    cfg = {'transformer_layers': ['self', 'self', 'cross', 'cross'], 'keypoint_encoder': [32, 64],
+           'sinkhorn_iterations': 25, 'match_threshold': 0.01}
+    sd = make_state_dict(13, damped=True, config=cfg)
+    data = make_pair(420, 390, seed=633, width=360, height=280)
+    data.update({'radius': 25, 'percentile': 7, 'min_size': 8})
+    with torch.no_grad():
+        want = orc.gmatcher_forward(sd, dict(data), cfg)
+    m = Matching(cfg)
+    m.gmodel.load_state_dict(sd)
+    m = m.eval().to('cuda')
+    with torch.no_grad():
+        got = m({**data, 'device': 'cuda'})
+    torch.cuda.synchronize()
+    assert torch.equal(got['keypoints0'].cpu(), want['keypoints0']) and torch.equal(got['keypoints1'].cpu(), want['keypoints1'])
+    assert (got['matches0'].cpu() == want['matches0']).float().mean().item() >= 0.999
+    assert (got['matches1'].cpu() == want['matches1']).float().mean().item() >= 0.999
+    scale = max(1e-3, float(want['matching_scores0'].max()))
+    assert (got['matching_scores0'].cpu() - want['matching_scores0']).abs().max().item() <= 1e-4 * scale + 1e-6
+    md = want['mdesc0']
+    assert torch.allclose(got['mdesc0'].cpu(), md, rtol=1e-4, atol=1e-4 * float(md.abs().max()))
+    assert int((want['matches0'] >= 0).sum()) > 10
+
+
 def test_batch_of_two_equal_sizes():
     """Batch > 1 works in the reference only when every item keeps the same N' (torch.stack, gmatcher.py:244-249);
     with min_size = 1 nothing is pruned.  Each item must equal its own single call."""
