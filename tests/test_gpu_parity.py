@@ -257,6 +257,9 @@ def test_forward_stages_vs_oracle():
     (2048, 2040, 100, 2.6, True, 90.0),       # trained-like: scores ~ 90 +- 2.6 against a dustbin score of 0.7
     (1000, 3100, 10, 30.0, True, 0.0), (4500, 4000, 4, 1.0, True, 0.0), (4500, 4000, 100, 3.0, True, 90.0),
     (8200, 8100, 30, 1.0, True, 0.0),
+    (1500, 11000, 10, 2.0, True, 50.0),       # > 10240 columns: nine column groups per thread, rows re-read from the stage,
+                                              # one-row blocks (the widest streaming instantiation)
+    (600, 15000, 5, 1.0, True, 0.0),          # no room for two stages next to v and w: the exact kernel
     (3000, 2500, 10, 2.0, False, 50.0),       # unaligned pitch: the exact kernel
     (700, 650, 30, 60.0, True, 0.0),          # very spread scores
 ])
