@@ -428,6 +428,42 @@ def test_other_network_configuration_vs_oracle():
     assert int((want['matches0'] >= 0).sum()) > 10
 
 
+def test_forward_at_maximum_size_properties():
+    """GIMS_MAX_KPTS = 16384 keypoints per image (the CPU reference needs tens of minutes there): size-independent
+    properties of the result — status clean, kept indices ascending, CSR sorted / symmetric / loop-free, matches mutual,
+    scores in (0, 1], potentials finite.  16385 columns exceed the streaming kernel's shared-memory budget: this is the
+    exact Sinkhorn kernel at full size."""
+    from gims_b200 import Matching, _lib
+    n = _lib.MAX_KPTS
+    cfg = {'sinkhorn_iterations': 5, 'match_threshold': 0.0}
+    m = Matching(cfg)
+    m.gmodel.load_state_dict(make_state_dict(3, damped=True))
+    m = m.eval().to('cuda')
+    data = make_pair(n, n, seed=640, width=2400, height=1800)
+    data.update({'radius': 25, 'percentile': 7, 'min_size': 8, 'device': 'cuda'})
+    with torch.no_grad():
+        pred = m.gmodel(data)
+    torch.cuda.synchronize()
+    n0, n1 = pred['matches0'].shape[1], pred['matches1'].shape[1]
+    assert 0.9 * n <= n0 <= n and 0.9 * n <= n1 <= n
+    k0 = torch.tensor(data['kept_kpts0_indices'][0])
+    assert (k0[1:] > k0[:-1]).all() and k0.numel() == n0
+    indptr, indices = [t.cpu().long() for t in data['graph0'][0]]
+    assert indptr[0] == 0 and indptr[-1] == indices.numel() and (indptr[1:] >= indptr[:-1]).all()
+    rows = torch.repeat_interleave(torch.arange(n0), indptr[1:] - indptr[:-1])
+    assert (rows != indices).all()                                            # no self loops
+    key = rows * n0 + indices
+    assert (key[1:] > key[:-1]).all()                                         # rows ascending, neighbours ascending, no duplicates
+    assert torch.equal(torch.sort(indices * n0 + rows).values, key)           # every edge has its reverse
+    m0, m1 = pred['matches0'][0].cpu(), pred['matches1'][0].cpu()
+    i = torch.nonzero(m0 >= 0).squeeze(1)
+    assert i.numel() > 100 and (m1[m0[i]] == i).all()                         # mutual
+    j = torch.nonzero(m1 >= 0).squeeze(1)
+    assert (m0[m1[j]] == j).all() and i.numel() == j.numel()
+    s0 = pred['matching_scores0'][0].cpu()
+    assert torch.isfinite(s0).all() and (s0[i] > 0).all() and (s0 <= 1.0 + 1e-5).all() and (s0[m0 < 0] == 0).all()
+
+
 def test_batch_of_two_equal_sizes():
     """Batch > 1 works in the reference only when every item keeps the same N' (torch.stack, gmatcher.py:244-249);
     with min_size = 1 nothing is pruned.  Each item must equal its own single call."""
