@@ -428,6 +428,32 @@ def test_other_network_configuration_vs_oracle():
     assert int((want['matches0'] >= 0).sum()) > 10
 
 
+@pytest.mark.parametrize('n0,n1,seed', [(2, 2, 650), (3, 9, 651), (17, 5, 652)])
+def test_tiny_forward_vs_oracle(n0, n1, seed):
+    """The smallest inputs the reference accepts (two keypoints: one candidate pair for the percentile) through the whole
+    path, nothing pruned (min_size 1): one partial row tile, one key tile, a Sinkhorn slab of a single CTA."""
+    from gims_b200 import Matching
+    from oracle import gims_oracle as orc
+    cfg = {'sinkhorn_iterations': 15, 'match_threshold': 0.0}
+    sd = make_state_dict(2, damped=True)
+    data = make_pair(n0, n1, seed=seed, width=60, height=50)
+    data.update({'radius': 40, 'percentile': 7, 'min_size': 1})
+    with torch.no_grad():
+        want = orc.gmatcher_forward(sd, dict(data), cfg)
+    m = Matching(cfg)
+    m.gmodel.load_state_dict(sd)
+    m = m.eval().to('cuda')
+    with torch.no_grad():
+        got = m({**data, 'device': 'cuda'})
+    torch.cuda.synchronize()
+    assert got['keypoints0'].shape == want['keypoints0'].shape and got['keypoints1'].shape == want['keypoints1'].shape
+    assert torch.equal(got['keypoints0'].cpu(), want['keypoints0'])
+    assert torch.equal(got['matches0'].cpu(), want['matches0']) and torch.equal(got['matches1'].cpu(), want['matches1'])
+    assert torch.allclose(got['matching_scores0'].cpu(), want['matching_scores0'], atol=1e-5)
+    md = want['mdesc0']
+    assert torch.allclose(got['mdesc0'].cpu(), md, rtol=1e-4, atol=1e-4 * float(md.abs().max()))
+
+
 def test_forward_at_maximum_size_properties():
     """GIMS_MAX_KPTS = 16384 keypoints per image (the CPU reference needs tens of minutes there): size-independent
     properties of the result — status clean, kept indices ascending, CSR sorted / symmetric / loop-free, matches mutual,
